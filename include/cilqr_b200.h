@@ -1,0 +1,185 @@
+/*
+ * cilqr_b200.h — C ABI of libcilqr_b200.so: the batched, B200-native (sm_100a)
+ * replacement for the CILQR hot path of PuYuuu/toy-example-of-iLQR.
+ *
+ * Drop-in boundary.  The reference's only public solver surface is
+ *     CILQRSolver::CILQRSolver(const GlobalConfig*)        include/cilqr_solver.hpp:34, src/cilqr_solver.cpp:17-83
+ *     CILQRSolver::solve(x0, ref_waypoints, ref_velo,
+ *                        obs_preds, road_boaders) -> (u,x)  include/cilqr_solver.hpp:37-41, src/cilqr_solver.cpp:85-153
+ * called from src/motion_planning.cpp:178 and :194-196.  Everything below is
+ * what a binding for that surface needs: plain pointers and sizes, no C++ or
+ * torch types.  The C++ compat class (toy-example-of-ilqr_b200/host/cilqr_solver_compat.hpp)
+ * and the ctypes binding (toy-example-of-ilqr_b200/binding.py) sit on top of it;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every call returns 0 on success and a negative cilqr_error_t otherwise;
+ *    cilqr_b200_last_error() returns the message of the calling thread's last
+ *    failure.  Nothing throws across this boundary.
+ *  - "host layout" = the reference's per-solve matrices, row-major, batch
+ *    outermost, always double:  x0 [B][4], u [B][N][2], x [B][N+1][4],
+ *    K [B][N][2][4] (rows 2i,2i+1 of the reference's (2N)x4 K), d [B][N][2],
+ *    obs [B][max_obs][obs_len][3] = RoutingLine (x,y,yaw) of obstacle j at
+ *    tick k (src/utils.cpp:52-58), borders [B][2] = road_boaders.
+ *  - a handle is bound to one device and one stream and is not re-entrant
+ *    (the reference object is not thread-safe either); use one handle per GPU.
+ */
+#ifndef CILQR_B200_H
+#define CILQR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CILQR_B200_MAX_TEMPLATES 8
+#define CILQR_B200_NUM_ALPHAS 20 /* alpha = 1, 1/2, ... > 1e-6  (src/cilqr_solver.cpp:354) */
+
+/* The scalars the reference constructor reads from GlobalConfig
+ * (src/cilqr_solver.cpp:18-72).  nx = 4 and nu = 2 are fixed by the model. */
+typedef struct cilqr_params_t {
+    double dt;                      /* delta_t */
+    double w_pos, w_vel, w_yaw;     /* lqr/w_pos (twice), w_vel, w_yaw -> state_weight */
+    double w_acc, w_stl;            /* ctrl_weight */
+    double obstacle_exp_q1, obstacle_exp_q2, state_exp_q1, state_exp_q2;
+    double alm_rho_init, alm_gamma, max_rho, max_mu;
+    double init_lamb, lamb_decay, lamb_amplify, max_lamb;
+    double convergence_threshold, accept_step_threshold;
+    double wheelbase, width, length;
+    double velo_max, velo_min, yaw_lim /* read, never used: cpp:67 */, acc_max, acc_min, stl_lim, d_safe;
+    int32_t max_iter;
+    int32_t solve_type;        /* 0 = "barrier", 1 = "alm"   (lqr/slove_type, cpp:33-41) */
+    int32_t reference_point;   /* 0 = "rear_center", 1 = "gravity_center" (cpp:72-76) */
+    int32_t use_last_solution; /* lqr/use_last_solution (cpp:32) */
+} cilqr_params_t;
+
+typedef enum cilqr_dtype_t { CILQR_F64 = 0, CILQR_F32 = 1 } cilqr_dtype_t;
+
+/* LQRSolveStatus, include/cilqr_solver.hpp:23-29 (same numbering). */
+typedef enum cilqr_status_t {
+    CILQR_RUNNING = 0,
+    CILQR_CONVERGED = 1,
+    CILQR_BACKWARD_PASS_FAIL = 2,
+    CILQR_FORWARD_PASS_FAIL = 3,
+    CILQR_FORWARD_PASS_SMALL_STEP = 4
+} cilqr_status_t;
+
+/* How solve() left its loop (src/cilqr_solver.cpp:127-148). */
+typedef enum cilqr_exit_t { CILQR_EXIT_MAX_ITER = 0, CILQR_EXIT_CONVERGED = 1, CILQR_EXIT_MAX_LAMB = 2 } cilqr_exit_t;
+
+typedef enum cilqr_error_t {
+    CILQR_OK = 0,
+    CILQR_ERR_INVALID = -1,   /* bad argument */
+    CILQR_ERR_RANGE = -2,     /* obstacle track shorter than N+1: the reference throws std::out_of_range (src/utils.cpp:53-55) */
+    CILQR_ERR_CUDA = -3,      /* CUDA runtime failure, message in last_error */
+    CILQR_ERR_NO_DEVICE = -4  /* no usable sm_100 device: the product has no CPU fallback */
+} cilqr_error_t;
+
+typedef struct cilqr_handle cilqr_handle_t;
+
+const char* cilqr_b200_last_error(void);
+const char* cilqr_b200_version(void);
+
+/* Replaces the constructor (cpp:17-83).  Allocates every device buffer for
+ * max_batch problems of horizon N with up to max_obs obstacles each; nothing
+ * is allocated by later calls.  `params` becomes template 0. */
+int cilqr_b200_create(const cilqr_params_t* params, int device, int max_batch, int N, int max_obs,
+                      int dtype, cilqr_handle_t** out);
+int cilqr_b200_destroy(cilqr_handle_t* h);
+
+/* Launch stream (a cudaStream_t); NULL = the handle's own stream. */
+int cilqr_b200_set_stream(cilqr_handle_t* h, void* cuda_stream);
+
+/* Scenario template t: solver scalars and the reference line's waypoints
+ * (ReferenceLine::{x,y,yaw}, include/utils.hpp:44-46; M <= 65535 because the
+ * reference indexes them with uint16_t, cpp:291-292).  Either part may be NULL
+ * to keep what is there. */
+int cilqr_b200_set_template(cilqr_handle_t* h, int tmpl, const cilqr_params_t* params, const double* wx,
+                            const double* wy, const double* wyaw, int M);
+
+/* Forget the warm start: every instance behaves as is_first_solve == true (cpp:17, :97-102). */
+int cilqr_b200_reset(cilqr_handle_t* h);
+
+/* Replaces solve() (cpp:85-153) for B independent problems, host buffers in,
+ * host buffers out; the copies are part of the call.  tmpl (NULL = all 0) and
+ * n_obs select template and obstacle count per problem.  Any output may be
+ * NULL.  J_out [B][2] = {cost of the initial trajectory (the `J` the reference
+ * logs, cpp:104), cost of the returned trajectory}; step_cost_out [B][N+1];
+ * K_out / d_out = gains of the last backward pass (cpp:343); status_out =
+ * current_solve_status at return; iters_out = iter_step calls made. */
+int cilqr_b200_solve_batch(cilqr_handle_t* h, int B, const double* x0, const double* ref_velo,
+                           const double* borders, const int32_t* tmpl, const int32_t* n_obs,
+                           const double* obs, int obs_len, double* u_out, double* x_out, double* J_out,
+                           double* K_out, double* d_out, double* step_cost_out, int32_t* status_out,
+                           int32_t* iters_out, int32_t* exit_out);
+
+/* The same in three steps, so that a caller can keep problems resident in HBM
+ * and time the solve alone (bench.py `value`). */
+int cilqr_b200_upload(cilqr_handle_t* h, int B, const double* x0, const double* ref_velo,
+                      const double* borders, const int32_t* tmpl, const int32_t* n_obs, const double* obs,
+                      int obs_len);
+int cilqr_b200_solve_resident(cilqr_handle_t* h, int B);
+int cilqr_b200_download(cilqr_handle_t* h, int B, double* u_out, double* x_out, double* J_out, double* K_out,
+                        double* d_out, double* step_cost_out, int32_t* status_out, int32_t* iters_out,
+                        int32_t* exit_out);
+
+/* Counters of the last solve: total iter_step calls over the batch, line-search
+ * rounds run, kernels launched, instances per exit reason. */
+typedef struct cilqr_counters_t {
+    int64_t total_iters;
+    int32_t rounds;
+    int32_t launches;
+    int32_t exits[3];
+    int32_t reserved;
+} cilqr_counters_t;
+int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
+
+/* ---- stage operators (one per reference function; host layout in and out) ----
+ * Used by the parity tests and by bench.py's roofline leg.  Each uploads its
+ * inputs, runs exactly the kernel(s) the solve uses for that stage, and
+ * downloads the result. */
+
+/* get_init_traj / get_init_traj_increment (cpp:155-197): warm != 0 shifts last_u [B][N][2]. */
+int cilqr_b200_stage_init(cilqr_handle_t* h, int B, const double* x0, const int32_t* tmpl, int warm,
+                          const double* last_u, double* u_out, double* x_out);
+/* get_ref_exact_points (cpp:289-314): indices of the matched waypoints, [B][N+1]. */
+int cilqr_b200_stage_ref_match(cilqr_handle_t* h, int B, const double* x, const int32_t* tmpl, int32_t* idx_out);
+/* get_total_cost (cpp:199-287): J [B], step_cost [B][N+1].  alm_mu [B][N][8+2*max_obs], alm_rho [B] only in ALM mode. */
+int cilqr_b200_stage_cost(cilqr_handle_t* h, int B, const double* u, const double* x, const double* ref_velo,
+                          const double* borders, const int32_t* tmpl, const int32_t* n_obs, const double* obs,
+                          int obs_len, const double* alm_mu, const double* alm_rho, double* J_out,
+                          double* step_cost_out);
+/* get_total_cost_derivatives_and_Hessians (cpp:463-690) + get_kinematic_model_derivatives
+ * (src/utils.cpp:285-342), dense reference layout out: lx [B][N+1][4], lu [B][N][2],
+ * lxx [B][N+1][4][4], luu [B][N][2][2], A [B][N][4][4], Bm [B][N][4][2]. */
+int cilqr_b200_stage_derivs(cilqr_handle_t* h, int B, const double* u, const double* x, const double* ref_velo,
+                            const double* borders, const int32_t* tmpl, const int32_t* n_obs, const double* obs,
+                            int obs_len, const double* alm_mu, const double* alm_rho, double* lx, double* lu,
+                            double* lxx, double* luu, double* A, double* Bm, double* alm_mu_next);
+/* The Riccati recursion of backward_pass (cpp:391-439) on explicit inputs (dense layout in);
+ * d [B][N][2], K [B][N][2][4], dV [B][2], status [B] (RUNNING or BACKWARD_PASS_FAIL). */
+int cilqr_b200_stage_backward(cilqr_handle_t* h, int B, const double* lx, const double* lu, const double* lxx,
+                              const double* luu, const double* A, const double* Bm, const double* lamb,
+                              double* d_out, double* K_out, double* dV_out, int32_t* status_out);
+/* forward_pass (cpp:442-461) for one alpha per problem. */
+int cilqr_b200_stage_forward(cilqr_handle_t* h, int B, const double* u, const double* x, const double* d,
+                             const double* K, const double* alpha, const int32_t* tmpl, double* new_u,
+                             double* new_x);
+
+/* Roofline leg: run the backward-pass kernel `reps` times on the derivative
+ * records currently resident in the handle (left there by stage_derivs /
+ * stage_backward / a solve), timing each launch with CUDA events on the launch
+ * stream.  ms_out [reps] per-launch milliseconds; bytes_per_launch = algorithmic
+ * bytes of the compact record layout the kernel moves, (38*N + 18) * sizeof(T) * B. */
+int cilqr_b200_bench_backward(cilqr_handle_t* h, int B, double lamb, int reps, int flush_l2, float* ms_out,
+                              double* bytes_per_launch);
+/* Replicate the first B0 resident derivative records up to B (device-side copy), so the
+ * roofline leg can run at batch sizes whose inputs were produced from a smaller solve. */
+int cilqr_b200_bench_tile_records(cilqr_handle_t* h, int B0, int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CILQR_B200_H */

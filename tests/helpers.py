@@ -1,0 +1,42 @@
+"""Shared helpers for the parity tests (oracle = checker, never the thing under test)."""
+import numpy as np
+
+import cilqr_b200 as cb
+from oracle import oracle_py as op
+
+
+def rollout(params, N, x0, u, dtype="f64"):
+    """x[k+1] = f(x[k], u[k]) with the oracle's propagate (forward pass with K = 0, d = 0)."""
+    x = np.zeros((N + 1, 4))
+    x[0] = x0
+    nu, nx = op.forward(params, N, u, x, np.zeros((N, 2)), np.zeros((N, 2, 4)), 0.0, dtype)
+    return nx
+
+
+def perturbed_trajectories(pb, seed=0, scale=(0.8, 0.03)):
+    """A trajectory per instance: smooth random controls rolled out from x0."""
+    rng = np.random.default_rng(seed)
+    B, N = pb.B, pb.N
+    u = np.zeros((B, N, 2))
+    x = np.zeros((B, N + 1, 4))
+    for b in range(B):
+        a = np.cumsum(rng.normal(0, 0.25, N)) * scale[0] / 2
+        s = np.cumsum(rng.normal(0, 0.25, N)) * scale[1] / 2
+        u[b, :, 0] = np.clip(a, -2.5, 2.5)
+        u[b, :, 1] = np.clip(s, -0.1, 0.1)
+        x[b] = rollout(pb.templates[pb.tmpl[b]].params, N, pb.x0[b], u[b])
+    return u, x
+
+
+def oracle_stage(pb, b, u, x, dtype="f64"):
+    td = pb.templates[pb.tmpl[b]]
+    J, sc = op.total_cost(td, pb.N, pb.ref_velo[b], pb.n_obs[b], pb.obs[b], pb.borders[b], u, x, dtype)
+    dv = op.cost_derivs(td, pb.N, pb.ref_velo[b], pb.n_obs[b], pb.obs[b], pb.borders[b], u, x, dtype)
+    A, Bm = op.dyn_derivs(td.params, pb.N, u, x, dtype)
+    idx = op.ref_match(td.wx, td.wy, x, dtype)
+    return J, sc, dv, A, Bm, idx
+
+
+def relerr(a, b, floor=1.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0

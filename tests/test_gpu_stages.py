@@ -1,0 +1,105 @@
+"""Stage-level parity: every CUDA kernel, called through the C ABI, against the CPU oracle on
+the same inputs.  Tolerances: fp64 1e-9 relative (the north-star bar is 1e-6; CUDA libm and FMA
+contraction differ from glibc by a few ulp), fp32 against the fp32 oracle 2e-4 relative."""
+import numpy as np
+import pytest
+
+import cilqr_b200 as cb
+from oracle import oracle_py as op
+from helpers import oracle_stage, perturbed_trajectories, relerr, rollout
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": 1e-9, "f32": 3e-4}
+
+
+def _solver(pb, dtype):
+    return cb.BatchSolver(pb.templates, max_batch=pb.B, N=pb.N, max_obs=pb.max_obs, dtype=dtype)
+
+
+@pytest.mark.parametrize("cfg,B", [("C1", 48), ("C3", 64)])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_init_and_forward(cfg, B, dtype):
+    pb = cb.synthetic_batch(cfg, B, N=50)
+    with _solver(pb, dtype) as s:
+        u, x = s.stage_init(pb.x0, pb.tmpl)
+        assert np.all(u == 0)
+        for b in range(B):
+            p = pb.templates[pb.tmpl[b]].params
+            nx = rollout(p, pb.N, pb.x0[b], np.zeros((pb.N, 2)), dtype)
+            assert relerr(x[b], nx) < TOL[dtype]
+        # warm start: shifted controls
+        rng = np.random.default_rng(1)
+        last_u = rng.normal(0, 0.05, (B, pb.N, 2))
+        uw, xw = s.stage_init(pb.x0, pb.tmpl, warm=True, last_u=last_u)
+        exp = np.concatenate([last_u[:, 1:], last_u[:, -1:]], axis=1)
+        if dtype == "f64":
+            assert np.array_equal(uw, exp)
+        else:
+            assert np.allclose(uw, exp, rtol=1e-6, atol=1e-7)
+        # forward pass with gains
+        u2, x2 = perturbed_trajectories(pb, seed=3)
+        d = rng.normal(0, 0.05, (B, pb.N, 2))
+        K = rng.normal(0, 0.05, (B, pb.N, 2, 4))
+        alpha = 0.5 ** rng.integers(0, 6, B)
+        nu, nx = s.stage_forward(u2, x2, d, K, alpha, pb.tmpl)
+        for b in range(B):
+            p = pb.templates[pb.tmpl[b]].params
+            eu, ex = op.forward(p, pb.N, u2[b], x2[b], d[b], K[b], alpha[b], dtype)
+            assert relerr(nu[b], eu) < TOL[dtype]
+            assert relerr(nx[b], ex) < TOL[dtype]
+
+
+@pytest.mark.parametrize("cfg,B", [("C1", 48), ("C3", 64)])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_ref_match_cost_derivs(cfg, B, dtype):
+    pb = cb.synthetic_batch(cfg, B, N=50)
+    u, x = perturbed_trajectories(pb, seed=5)
+    with _solver(pb, dtype) as s:
+        idx = s.stage_ref_match(x, pb.tmpl)
+        J, sc = s.stage_cost(pb, u, x)
+        dv = s.stage_derivs(pb, u, x)
+    n_idx_bad = 0
+    for b in range(B):
+        eJ, esc, edv, eA, eB, eidx = oracle_stage(pb, b, u[b], x[b], dtype)
+        if not np.array_equal(idx[b], eidx):
+            n_idx_bad += 1
+            continue  # a waypoint tie broken the other way; counted below
+        assert relerr(J[b], eJ) < TOL[dtype] * 10
+        assert relerr(sc[b], esc) < TOL[dtype] * 10
+        for k in ("lx", "lu", "lxx", "luu"):
+            assert relerr(dv[k][b], edv[k]) < TOL[dtype] * 10, k
+        assert relerr(dv["A"][b], eA) < TOL[dtype]
+        assert relerr(dv["B"][b], eB) < TOL[dtype]
+    assert n_idx_bad <= (0 if dtype == "f64" else B // 8)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_backward_pass(dtype):
+    pb = cb.synthetic_batch("C3", 64, N=50)
+    u, x = perturbed_trajectories(pb, seed=9)
+    B, N = pb.B, pb.N
+    lx, lu = np.zeros((B, N + 1, 4)), np.zeros((B, N, 2))
+    lxx, luu = np.zeros((B, N + 1, 4, 4)), np.zeros((B, N, 2, 2))
+    A, Bm = np.zeros((B, N, 4, 4)), np.zeros((B, N, 4, 2))
+    for b in range(B):
+        _, _, dv, A[b], Bm[b], _ = oracle_stage(pb, b, u[b], x[b], "f64")
+        lx[b], lu[b], lxx[b], luu[b] = dv["lx"], dv["lu"], dv["lxx"], dv["luu"]
+    lamb = np.where(np.arange(B) % 3 == 0, 0.0, 2.0 ** (np.arange(B) % 5))
+    with _solver(pb, dtype) as s:
+        d, K, dV, st = s.stage_backward(lx, lu, lxx, luu, A, Bm, lamb)
+        # a non-PD case: negative control Hessian at one step -> BACKWARD_PASS_FAIL, zeroed rows below
+        luu2 = luu.copy()
+        luu2[:, N // 2] = -1e6 * np.eye(2)
+        d2, K2, dV2, st2 = s.stage_backward(lx, lu, lxx, luu2, A, Bm, lamb)
+    tol = 1e-7 if dtype == "f64" else 5e-3
+    for b in range(B):
+        ed, eK, edV, est = op.riccati(N, lx[b], lu[b], lxx[b], luu[b], A[b], Bm[b], lamb[b], dtype)
+        assert st[b] == est
+        assert relerr(d[b], ed) < tol
+        assert relerr(K[b], eK) < tol
+        assert relerr(dV[b], edV) < tol
+        ed, eK, edV, est = op.riccati(N, lx[b], lu[b], lxx[b], luu2[b], A[b], Bm[b], lamb[b], dtype)
+        assert est == 2 and st2[b] == 2
+        assert np.all(d2[b, : N // 2 + 1] == 0) and np.all(K2[b, : N // 2 + 1] == 0)
+        assert relerr(d2[b], ed) < tol and relerr(K2[b], eK) < tol

@@ -1,0 +1,1009 @@
+// libcilqr_b200.so — C ABI (include/cilqr_b200.h) over the sm_100a kernels.
+// One handle = one device, one stream, all buffers allocated at create time.
+// There is deliberately no CPU path: without a Blackwell device every entry
+// point fails with CILQR_ERR_NO_DEVICE.
+#include "../../include/cilqr_b200.h"
+#include "cilqr_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace cilqr;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(CILQR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kRunAhead = 2;     // rounds the host may queue beyond the last one it has a count for
+constexpr int kMaxWaypoints = 1 << 20;
+
+// Type-erased part of a handle; the typed buffers live in Impl<T>.
+struct Base {
+    int dtype = 0, device = 0, max_batch = 0, N = 0, max_obs = 0, Bs = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cilqr_params_t params[CILQR_B200_MAX_TEMPLATES];
+    bool tmpl_set[CILQR_B200_MAX_TEMPLATES] = {false};
+    int wp_off[CILQR_B200_MAX_TEMPLATES] = {0}, wp_len[CILQR_B200_MAX_TEMPLATES] = {0};
+    std::vector<double> h_wx, h_wy, h_wyaw;  // concatenated tables
+    bool any_alm = false;
+    int max_rounds = 0;
+    int* h_active = nullptr;  // pinned
+    cudaEvent_t ev[kRunAhead + 1] = {nullptr};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    double* stage = nullptr;  // device staging in host layout
+    size_t stage_bytes = 0;
+    int* istage = nullptr;    // device staging for int arrays [max_batch]
+    float* flush = nullptr;
+    size_t flush_n = 0;
+    cilqr_counters_t counters{};
+    int launches = 0;
+    virtual ~Base() {}
+};
+
+template <typename T>
+struct Impl : Base {
+    Dev<T> D{};
+    DevParams<T>* dP = nullptr;
+    T* d_wp = nullptr;  // wx | wy | wyaw, each kMaxWaypoints? (sized on demand)
+    size_t wp_cap = 0;
+    std::vector<void*> allocs;
+};
+
+template <typename T>
+DevParams<T> convert_params(const cilqr_params_t& p) {
+    DevParams<T> d{};
+    d.dt = T(p.dt);
+    d.wheelbase = T(p.wheelbase);
+    d.width = T(p.width);
+    d.Q[0] = T(p.w_pos);
+    d.Q[1] = T(p.w_pos);
+    d.Q[2] = T(p.w_vel);
+    d.Q[3] = T(p.w_yaw);
+    d.R[0] = T(p.w_acc);
+    d.R[1] = T(p.w_stl);
+    d.obs_q1 = T(p.obstacle_exp_q1);
+    d.obs_q2 = T(p.obstacle_exp_q2);
+    d.st_q1 = T(p.state_exp_q1);
+    d.st_q2 = T(p.state_exp_q2);
+    d.acc_max = T(p.acc_max);
+    d.acc_min = T(p.acc_min);
+    d.stl_lim = T(p.stl_lim);
+    d.velo_max = T(p.velo_max);
+    d.velo_min = T(p.velo_min);
+    // src/utils.cpp:387-393 with obs_attr = {width, length, d_safe} and radius = width/2
+    T radius = T(0.5) * T(p.width);
+    T a = T(0.5) * T(p.length) + T(p.d_safe) * 6 + radius;
+    T b = T(0.5) * T(p.width) + T(p.d_safe) + radius;
+    d.ell_a2 = a * a;
+    d.ell_b2 = b * b;
+    d.alm_rho_init = T(p.alm_rho_init);
+    d.alm_gamma = T(p.alm_gamma);
+    d.max_rho = T(p.max_rho);
+    d.max_mu = T(p.max_mu);
+    d.init_lamb = T(p.init_lamb);
+    d.lamb_decay = T(p.lamb_decay);
+    d.lamb_amplify = T(p.lamb_amplify);
+    d.max_lamb = T(p.max_lamb);
+    d.conv_thr = T(p.convergence_threshold);
+    d.accept_thr = T(p.accept_step_threshold);
+    d.max_iter = p.max_iter;
+    d.solve_type = p.solve_type;
+    d.ref_point = p.reference_point;
+    d.use_last = p.use_last_solution;
+    return d;
+}
+
+int check_params(const cilqr_params_t* p) {
+    if (!p) return fail(CILQR_ERR_INVALID, "params is NULL");
+    if (!(p->dt > 0)) return fail(CILQR_ERR_INVALID, "delta_t must be positive");
+    if (!(p->wheelbase > 0)) return fail(CILQR_ERR_INVALID, "vehicle/wheelbase must be positive");
+    if (p->max_iter < 0 || p->max_iter > 100000) return fail(CILQR_ERR_INVALID, "iteration/max_iter out of range");
+    if (p->solve_type != 0 && p->solve_type != 1) return fail(CILQR_ERR_INVALID, "solve_type must be 0 (barrier) or 1 (alm)");
+    if (p->reference_point != 0 && p->reference_point != 1)
+        return fail(CILQR_ERR_INVALID, "reference_point must be 0 (rear_center) or 1 (gravity_center)");
+    return 0;
+}
+
+template <typename T, typename P>
+int dalloc(Impl<T>* h, P** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(P);
+    CK(cudaMalloc(&q, bytes));
+    CK(cudaMemsetAsync(q, 0, bytes, h->stream));
+    h->allocs.push_back(q);
+    *p = static_cast<P*>(q);
+    return 0;
+}
+
+template <typename T>
+int alloc_alm(Impl<T>* h) {
+    if (h->D.mu) return 0;
+    size_t n = size_t(h->N) * h->D.alm_cols * h->Bs;
+    int rc;
+    if ((rc = dalloc(h, &h->D.mu, n))) return rc;
+    if ((rc = dalloc(h, &h->D.mu_next, n))) return rc;
+    if ((rc = dalloc(h, &h->D.rho, h->Bs))) return rc;
+    return 0;
+}
+
+template <typename T>
+int upload_templates(Impl<T>* h) {
+    // waypoints
+    size_t total = h->h_wx.size();
+    if (total > h->wp_cap) {
+        size_t cap = std::max<size_t>(total, 4096);
+        T* q = nullptr;
+        CK(cudaMalloc(&q, cap * 3 * sizeof(T)));
+        h->allocs.push_back(q);
+        h->d_wp = q;
+        h->wp_cap = cap;
+    }
+    if (total) {
+        std::vector<T> tmp(h->wp_cap * 3, T(0));
+        for (size_t i = 0; i < total; ++i) {
+            tmp[i] = T(h->h_wx[i]);
+            tmp[h->wp_cap + i] = T(h->h_wy[i]);
+            tmp[2 * h->wp_cap + i] = T(h->h_wyaw[i]);
+        }
+        CK(cudaMemcpyAsync(h->d_wp, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->D.wx = h->d_wp;
+    h->D.wy = h->d_wp + h->wp_cap;
+    h->D.wyaw = h->d_wp + 2 * h->wp_cap;
+    std::vector<DevParams<T>> hp(CILQR_B200_MAX_TEMPLATES);
+    h->any_alm = false;
+    int max_iter = 0;
+    for (int t = 0; t < CILQR_B200_MAX_TEMPLATES; ++t) {
+        const cilqr_params_t& src = h->tmpl_set[t] ? h->params[t] : h->params[0];
+        hp[t] = convert_params<T>(src);
+        hp[t].wp_off = h->wp_off[t];
+        hp[t].wp_len = h->wp_len[t];
+        if (h->tmpl_set[t]) {
+            h->any_alm |= src.solve_type == 1;
+            max_iter = std::max(max_iter, src.max_iter);
+        }
+    }
+    CK(cudaMemcpyAsync(h->dP, hp.data(), hp.size() * sizeof(DevParams<T>), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->any_alm) {
+        int rc = alloc_alm(h);
+        if (rc) return rc;
+    }
+    int need = max_iter * kNumAlphas + 8;
+    if (need > h->max_rounds) {
+        int* q = nullptr;
+        CK(cudaMalloc(&q, size_t(need) * sizeof(int)));
+        h->allocs.push_back(q);
+        h->D.active = q;
+        if (h->h_active) CK(cudaFreeHost(h->h_active));
+        CK(cudaHostAlloc(&h->h_active, size_t(need) * sizeof(int), cudaHostAllocDefault));
+        h->max_rounds = need;
+    }
+    return 0;
+}
+
+template <typename T>
+int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, int max_obs, cilqr_handle_t** out) {
+    auto* h = new Impl<T>();
+    h->dtype = std::is_same<T, float>::value ? CILQR_F32 : CILQR_F64;
+    h->device = device;
+    h->max_batch = max_batch;
+    h->N = N;
+    h->max_obs = max_obs;
+    h->Bs = (max_batch + 127) / 128 * 128;
+    int rc = 0;
+    auto body = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        for (auto& e : h->ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreate(&h->t0));
+        CK(cudaEventCreate(&h->t1));
+        Dev<T>& D = h->D;
+        D.N = N;
+        D.Bs = h->Bs;
+        D.max_obs = max_obs;
+        D.alm_cols = 8 + 2 * max_obs;
+        const size_t Bs = h->Bs;
+        int r;
+        if ((r = dalloc(h, &h->dP, CILQR_B200_MAX_TEMPLATES))) return r;
+        D.P = h->dP;
+        if ((r = dalloc(h, &D.ref_velo, Bs))) return r;
+        if ((r = dalloc(h, &D.borders, 2 * Bs))) return r;
+        if ((r = dalloc(h, &D.tmpl, Bs))) return r;
+        if ((r = dalloc(h, &D.n_obs, Bs))) return r;
+        if ((r = dalloc(h, &D.obs, size_t(max_obs) * (N + 1) * 3 * Bs))) return r;
+        if ((r = dalloc(h, &D.x0, 4 * Bs))) return r;
+        if ((r = dalloc(h, &D.X, size_t(2) * (N + 1) * 4 * Bs))) return r;
+        if ((r = dalloc(h, &D.U, size_t(2) * N * 2 * Bs))) return r;
+        if ((r = dalloc(h, &D.ridx, size_t(2) * (N + 1) * Bs))) return r;
+        if ((r = dalloc(h, &D.sc, size_t(2) * (N + 1) * Bs))) return r;
+        if ((r = dalloc(h, &D.cur, Bs))) return r;
+        if ((r = dalloc(h, &D.rec, size_t(N + 1) * kRecFields * Bs))) return r;
+        if ((r = dalloc(h, &D.Kg, size_t(N) * 8 * Bs))) return r;
+        if ((r = dalloc(h, &D.dg, size_t(N) * 2 * Bs))) return r;
+        if ((r = dalloc(h, &D.dV, 2 * Bs))) return r;
+        if ((r = dalloc(h, &D.lamb, Bs))) return r;
+        if ((r = dalloc(h, &D.J_cur, Bs))) return r;
+        if ((r = dalloc(h, &D.J_init, Bs))) return r;
+        if ((r = dalloc(h, &D.alpha, Bs))) return r;
+        if ((r = dalloc(h, &D.status, Bs))) return r;
+        if ((r = dalloc(h, &D.phase, Bs))) return r;
+        if ((r = dalloc(h, &D.aidx, Bs))) return r;
+        if ((r = dalloc(h, &D.iters, Bs))) return r;
+        if ((r = dalloc(h, &D.exit_reason, Bs))) return r;
+        if ((r = dalloc(h, &D.rec_valid, Bs))) return r;
+        if ((r = dalloc(h, &D.last_u, size_t(N) * 2 * Bs))) return r;
+        if ((r = dalloc(h, &D.first, Bs))) return r;
+        if ((r = dalloc(h, &h->istage, Bs))) return r;
+        // staging: one chunk of trajectories in host layout; 64 MiB or one trajectory's largest array
+        size_t per_traj = std::max<size_t>(size_t(N + 1) * 16, size_t(max_obs) * (N + 1) * 3) * sizeof(double);
+        h->stage_bytes = std::max<size_t>(size_t(64) << 20, per_traj * 4);
+        if ((r = dalloc(h, reinterpret_cast<char**>(&h->stage), h->stage_bytes))) return r;
+        h->params[0] = *params;
+        h->tmpl_set[0] = true;
+        if ((r = upload_templates(h))) return r;
+        CK(cudaMemsetAsync(D.first, 0, Bs * sizeof(int), h->stream));
+        return 0;
+    };
+    rc = body();
+    if (rc == 0) {
+        // first = 1 everywhere
+        std::vector<int> ones(h->Bs, 1);
+        cudaError_t e = cudaMemcpyAsync(h->D.first, ones.data(), ones.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(CILQR_ERR_CUDA, "initialising warm-start flags: %s", cudaGetErrorString(e));
+    }
+    if (rc) {
+        for (void* p : h->allocs) cudaFree(p);
+        delete h;
+        return rc;
+    }
+    *out = reinterpret_cast<cilqr_handle_t*>(static_cast<Base*>(h));
+    return 0;
+}
+
+inline Base* base(cilqr_handle_t* h) { return reinterpret_cast<Base*>(h); }
+
+#define DISPATCH(h, fn, ...)                                                        \
+    (base(h)->dtype == CILQR_F64 ? fn(static_cast<Impl<double>*>(base(h)), ##__VA_ARGS__) \
+                                 : fn(static_cast<Impl<float>*>(base(h)), ##__VA_ARGS__))
+
+inline dim3 grid1(int B) { return dim3((B + 127) / 128); }
+inline dim3 grid2(int B, int rows) { return dim3((B + 127) / 128, rows); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(Base* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args&&... args) {
+    kernel<<<grid, block, 0, h->stream>>>(std::forward<Args>(args)...);
+    h->launches++;
+}
+#define LAUNCH(h, kernel, grid, block, ...) launch_kernel(h, kernel, grid, block, __VA_ARGS__)
+
+// host layout (double [B][E_src rows]) -> device SoA, chunked through the staging buffer.
+// rows_src/rows_dst/inner: when the source has more rows per block than the destination keeps
+// (obstacle tracks longer than N+1), only the first rows_dst rows of each block are kept.
+template <typename T>
+__global__ void k_pack_rows(const double* __restrict__ src, T* __restrict__ dst, int B, int blocks, int rows_src,
+                            int rows_dst, int inner, size_t Bs, int b_off) {
+    __shared__ double tile[32][33];
+    const int E = blocks * rows_src * inner;
+    int e0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int b = b0 + r, e = e0 + threadIdx.x;
+        if (b < B && e < E) tile[r][threadIdx.x] = src[size_t(b) * E + e];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int e = e0 + r, b = b0 + threadIdx.x;
+        if (b < B && e < E) {
+            int c = e % inner;
+            int row = (e / inner) % rows_src;
+            int blk = e / (inner * rows_src);
+            if (row < rows_dst) dst[(size_t(blk) * rows_dst + row) * inner * Bs + size_t(c) * Bs + b_off + b] = T(tile[threadIdx.x][r]);
+        }
+    }
+}
+
+template <typename T>
+int pack_to_device(Impl<T>* h, const double* src, T* dst, int B, int blocks, int rows_src, int rows_dst, int inner) {
+    if (!src) return fail(CILQR_ERR_INVALID, "NULL input array");
+    const size_t E = size_t(blocks) * rows_src * inner;
+    if (E == 0 || B == 0) return 0;
+    size_t per = E * sizeof(double);
+    int chunk = int(std::min<size_t>(size_t(B), std::max<size_t>(h->stage_bytes / per, 1)));
+    if (per > h->stage_bytes) return fail(CILQR_ERR_INVALID, "one trajectory's array (%zu bytes) exceeds the staging buffer", per);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        int nb = std::min(chunk, B - b0);
+        CK(cudaMemcpyAsync(h->stage, src + size_t(b0) * E, size_t(nb) * per, cudaMemcpyHostToDevice, h->stream));
+        dim3 g((unsigned(E) + 31) / 32, (nb + 31) / 32), blk(32, 8);
+        k_pack_rows<T><<<g, blk, 0, h->stream>>>(h->stage, dst, nb, blocks, rows_src, rows_dst, inner, h->Bs, b0);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+__global__ void k_unpack_rows(const T* __restrict__ src, double* __restrict__ dst, int B, int E, size_t Bs,
+                              const int* __restrict__ sel, size_t buf_stride, int b_off) {
+    __shared__ double tile[32][33];
+    int e0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int e = e0 + r, b = b0 + threadIdx.x;
+        if (b < B && e < E) {
+            size_t off = sel ? size_t(sel[b_off + b]) * buf_stride : 0;
+            tile[r][threadIdx.x] = double(src[off + size_t(e) * Bs + b_off + b]);
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int b = b0 + r, e = e0 + threadIdx.x;
+        if (b < B && e < E) dst[size_t(b) * E + e] = tile[threadIdx.x][r];
+    }
+}
+
+template <typename T>
+int unpack_to_host(Impl<T>* h, const T* src, double* dst, int B, int E, const int* sel, size_t buf_stride) {
+    if (!dst || E == 0 || B == 0) return 0;
+    size_t per = size_t(E) * sizeof(double);
+    int chunk = int(std::min<size_t>(size_t(B), std::max<size_t>(h->stage_bytes / per, 1)));
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        int nb = std::min(chunk, B - b0);
+        dim3 g((E + 31) / 32, (nb + 31) / 32), blk(32, 8);
+        k_unpack_rows<T><<<g, blk, 0, h->stream>>>(src, h->stage, nb, E, h->Bs, sel, buf_stride, b0);
+        h->launches++;
+        CK(cudaMemcpyAsync(dst + size_t(b0) * E, h->stage, size_t(nb) * per, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int upload_ints(Impl<T>* h, const int32_t* src, int* dst, int B, int fill) {
+    if (src) {
+        CK(cudaMemcpyAsync(dst, src, size_t(B) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        k_pack_int<<<grid1(B), 128, 0, h->stream>>>(nullptr, dst, B, fill);
+        h->launches++;
+    }
+    return 0;
+}
+
+template <typename T>
+int download_ints(Impl<T>* h, const int* src, int32_t* dst, int B) {
+    if (!dst) return 0;
+    CK(cudaMemcpyAsync(dst, src, size_t(B) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+int check_batch(Base* h, int B) {
+    if (!h) return fail(CILQR_ERR_INVALID, "handle is NULL");
+    if (B < 0 || B > h->max_batch) return fail(CILQR_ERR_INVALID, "batch %d outside [0, max_batch=%d]", B, h->max_batch);
+    return 0;
+}
+
+int check_tmpl_nobs(Base* h, int B, const int32_t* tmpl, const int32_t* n_obs, int obs_len) {
+    if (tmpl)
+        for (int b = 0; b < B; ++b)
+            if (tmpl[b] < 0 || tmpl[b] >= CILQR_B200_MAX_TEMPLATES || !h->tmpl_set[tmpl[b]])
+                return fail(CILQR_ERR_INVALID, "instance %d uses template %d, which was never set", b, tmpl[b]);
+    for (int t = 0; t < CILQR_B200_MAX_TEMPLATES; ++t)
+        if (h->tmpl_set[t] && h->wp_len[t] <= 0 && (!tmpl || std::find(tmpl, tmpl + B, t) != tmpl + B))
+            return fail(CILQR_ERR_INVALID, "template %d has no reference line (cilqr_b200_set_template)", t);
+    bool any = false;
+    if (n_obs)
+        for (int b = 0; b < B; ++b) {
+            if (n_obs[b] < 0 || n_obs[b] > h->max_obs)
+                return fail(CILQR_ERR_INVALID, "instance %d has n_obs=%d outside [0, max_obs=%d]", b, n_obs[b], h->max_obs);
+            any |= n_obs[b] > 0;
+        }
+    if (any && obs_len < h->N + 1)
+        return fail(CILQR_ERR_RANGE, "obstacle tracks hold %d samples, need N+1=%d (RoutingLine index out of range)", obs_len, h->N + 1);
+    return 0;
+}
+
+template <typename T>
+int upload_problem_data(Impl<T>* h, int B, const double* ref_velo, const double* borders, const int32_t* tmpl,
+                        const int32_t* n_obs, const double* obs, int obs_len) {
+    int rc;
+    if ((rc = check_tmpl_nobs(h, B, tmpl, n_obs, obs_len))) return rc;
+    if ((rc = upload_ints(h, tmpl, h->D.tmpl, B, 0))) return rc;
+    if ((rc = upload_ints(h, n_obs, h->D.n_obs, B, 0))) return rc;
+    if ((rc = pack_to_device(h, ref_velo, h->D.ref_velo, B, 1, 1, 1, 1))) return rc;
+    if ((rc = pack_to_device(h, borders, h->D.borders, B, 1, 2, 2, 1))) return rc;
+    bool any = false;
+    if (n_obs)
+        for (int b = 0; b < B && !any; ++b) any = n_obs[b] > 0;
+    if (any && h->max_obs > 0) {
+        if ((rc = pack_to_device(h, obs, h->D.obs, B, h->max_obs, obs_len, h->N + 1, 3))) return rc;
+    }
+    return 0;
+}
+
+template <typename T>
+int do_upload(Impl<T>* h, int B, const double* x0, const double* ref_velo, const double* borders,
+              const int32_t* tmpl, const int32_t* n_obs, const double* obs, int obs_len) {
+    int rc;
+    CK(cudaSetDevice(h->device));
+    if ((rc = upload_problem_data(h, B, ref_velo, borders, tmpl, n_obs, obs, obs_len))) return rc;
+    if ((rc = pack_to_device(h, x0, h->D.x0, B, 1, 4, 4, 1))) return rc;
+    return 0;
+}
+
+// cost of the trajectory in buffer `which` (0 current / 1 trial): waypoint match + per-step costs
+template <typename T>
+void launch_cost(Impl<T>* h, int B, int which, int need_phase) {
+    constexpr int G = 8;
+    int threads = 128;
+    int per_block = threads / G;
+    LAUNCH(h, k_ref_match<T, G>, dim3((B + per_block - 1) / per_block), threads, h->D, B, which, need_phase);
+    LAUNCH(h, k_cost<T>, grid2(B, h->N + 1), 128, h->D, B, which, need_phase);
+}
+
+template <typename T>
+int do_solve_resident(Impl<T>* h, int B) {
+    CK(cudaSetDevice(h->device));
+    if (B == 0) return 0;
+    const int N = h->N;
+    h->launches = 0;
+    CK(cudaMemsetAsync(h->D.active, 0, size_t(h->max_rounds) * sizeof(int), h->stream));
+    LAUNCH(h, k_init<T>, grid1(B), 128, h->D, B, -1, 1);
+    launch_cost(h, B, 0, -1);
+    LAUNCH(h, k_sum_cost<T>, grid1(B), 128, h->D, B);
+    int rounds = 0;
+    for (int r = 0; r < h->max_rounds; ++r) {
+        if (h->any_alm) {
+            LAUNCH(h, k_cost<T>, grid2(B, N + 1), 128, h->D, B, 0, int(PH_BACKWARD));
+            LAUNCH(h, k_refresh_cost<T>, grid1(B), 128, h->D, B);
+        }
+        LAUNCH(h, k_derivs<T>, grid2(B, N + 1), 128, h->D, B, 1);
+        LAUNCH(h, k_backward<T>, grid1(B), 128, h->D, B, 1);
+        LAUNCH(h, k_forward<T>, grid1(B), 128, h->D, B, 1);
+        launch_cost(h, B, 1, int(PH_SEARCH));
+        LAUNCH(h, k_decide<T>, grid1(B), 128, h->D, B, r);
+        CK(cudaMemcpyAsync(&h->h_active[r], &h->D.active[r], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev[r % (kRunAhead + 1)], h->stream));
+        rounds = r + 1;
+        if (r >= kRunAhead) {
+            int q = r - kRunAhead;
+            CK(cudaEventSynchronize(h->ev[q % (kRunAhead + 1)]));
+            if (h->h_active[q] == 0) break;
+        }
+    }
+    LAUNCH(h, k_store_last_u<T>, grid2(B, N), 128, h->D, B);
+    CK(cudaGetLastError());
+    h->counters.rounds = rounds;
+    h->counters.launches = h->launches;
+    return 0;
+}
+
+template <typename T>
+int do_download(Impl<T>* h, int B, double* u_out, double* x_out, double* J_out, double* K_out, double* d_out,
+                double* step_cost_out, int32_t* status_out, int32_t* iters_out, int32_t* exit_out) {
+    CK(cudaSetDevice(h->device));
+    const int N = h->N;
+    const size_t Bs = h->Bs;
+    int rc;
+    if ((rc = unpack_to_host(h, h->D.U, u_out, B, N * 2, h->D.cur, size_t(N) * 2 * Bs))) return rc;
+    if ((rc = unpack_to_host(h, h->D.X, x_out, B, (N + 1) * 4, h->D.cur, size_t(N + 1) * 4 * Bs))) return rc;
+    if ((rc = unpack_to_host(h, h->D.Kg, K_out, B, N * 8, nullptr, 0))) return rc;
+    if ((rc = unpack_to_host(h, h->D.dg, d_out, B, N * 2, nullptr, 0))) return rc;
+    if ((rc = unpack_to_host(h, h->D.sc, step_cost_out, B, N + 1, h->D.cur, size_t(N + 1) * Bs))) return rc;
+    if (J_out) {
+        // J_init and J_cur are two [Bs] arrays; emit [B][2]
+        std::vector<double> tmp(size_t(B) * 2);
+        std::vector<T> a(B), c(B);
+        CK(cudaMemcpyAsync(a.data(), h->D.J_init, size_t(B) * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(c.data(), h->D.J_cur, size_t(B) * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int b = 0; b < B; ++b) {
+            J_out[size_t(b) * 2] = double(a[b]);
+            J_out[size_t(b) * 2 + 1] = double(c[b]);
+        }
+    }
+    if ((rc = download_ints(h, h->D.status, status_out, B))) return rc;
+    if ((rc = download_ints(h, h->D.iters, iters_out, B))) return rc;
+    if ((rc = download_ints(h, h->D.exit_reason, exit_out, B))) return rc;
+    // counters
+    std::vector<int> it(B), ex(B);
+    CK(cudaMemcpyAsync(it.data(), h->D.iters, size_t(B) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ex.data(), h->D.exit_reason, size_t(B) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->counters.total_iters = 0;
+    h->counters.exits[0] = h->counters.exits[1] = h->counters.exits[2] = 0;
+    for (int b = 0; b < B; ++b) {
+        h->counters.total_iters += it[b];
+        if (ex[b] >= 0 && ex[b] < 3) h->counters.exits[ex[b]]++;
+    }
+    return 0;
+}
+
+// ---- stage operators -------------------------------------------------------
+
+template <typename T>
+int stage_init(Impl<T>* h, int B, const double* x0, const int32_t* tmpl, int warm, const double* last_u,
+               double* u_out, double* x_out) {
+    CK(cudaSetDevice(h->device));
+    int rc;
+    const int N = h->N;
+    if ((rc = upload_ints(h, tmpl, h->D.tmpl, B, 0))) return rc;
+    if ((rc = pack_to_device(h, x0, h->D.x0, B, 1, 4, 4, 1))) return rc;
+    if (warm) {
+        if ((rc = pack_to_device(h, last_u, h->D.last_u, B, 1, N * 2, N * 2, 1))) return rc;
+    }
+    LAUNCH(h, k_init<T>, grid1(B), 128, h->D, B, warm ? 1 : 0, 0);
+    if ((rc = unpack_to_host(h, h->D.U, u_out, B, N * 2, nullptr, 0))) return rc;
+    if ((rc = unpack_to_host(h, h->D.X, x_out, B, (N + 1) * 4, nullptr, 0))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename T>
+int load_traj(Impl<T>* h, int B, const double* u, const double* x) {
+    int rc;
+    const int N = h->N;
+    CK(cudaMemsetAsync(h->D.cur, 0, size_t(h->Bs) * sizeof(int), h->stream));
+    if (u && (rc = pack_to_device(h, u, h->D.U, B, 1, N * 2, N * 2, 1))) return rc;
+    if (x && (rc = pack_to_device(h, x, h->D.X, B, 1, (N + 1) * 4, (N + 1) * 4, 1))) return rc;
+    return 0;
+}
+
+template <typename T>
+int stage_ref_match(Impl<T>* h, int B, const double* x, const int32_t* tmpl, int32_t* idx_out) {
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = check_tmpl_nobs(h, B, tmpl, nullptr, 0))) return rc;
+    if ((rc = upload_ints(h, tmpl, h->D.tmpl, B, 0))) return rc;
+    if ((rc = load_traj(h, B, nullptr, x))) return rc;
+    constexpr int G = 8;
+    LAUNCH(h, k_ref_match<T, G>, dim3((B + 15) / 16), 128, h->D, B, 0, -1);
+    // ridx is [N+1][Bs] ints: transpose on the host (test path only)
+    const int N = h->N;
+    std::vector<int> tmp(size_t(N + 1) * h->Bs);
+    CK(cudaMemcpyAsync(tmp.data(), h->D.ridx, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k <= N; ++k) idx_out[size_t(b) * (N + 1) + k] = tmp[size_t(k) * h->Bs + b];
+    return 0;
+}
+
+template <typename T>
+int load_alm(Impl<T>* h, int B, const double* alm_mu, const double* alm_rho) {
+    if (!h->any_alm) return 0;
+    if (!alm_mu || !alm_rho) return fail(CILQR_ERR_INVALID, "ALM template needs alm_mu and alm_rho");
+    int rc;
+    if ((rc = pack_to_device(h, alm_mu, h->D.mu, B, 1, h->N * h->D.alm_cols, h->N * h->D.alm_cols, 1))) return rc;
+    if ((rc = pack_to_device(h, alm_rho, h->D.rho, B, 1, 1, 1, 1))) return rc;
+    return 0;
+}
+
+template <typename T>
+int stage_cost(Impl<T>* h, int B, const double* u, const double* x, const double* ref_velo, const double* borders,
+               const int32_t* tmpl, const int32_t* n_obs, const double* obs, int obs_len, const double* alm_mu,
+               const double* alm_rho, double* J_out, double* step_cost_out) {
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload_problem_data(h, B, ref_velo, borders, tmpl, n_obs, obs, obs_len))) return rc;
+    if ((rc = load_traj(h, B, u, x))) return rc;
+    if ((rc = load_alm(h, B, alm_mu, alm_rho))) return rc;
+    launch_cost(h, B, 0, -1);
+    LAUNCH(h, k_sum_cost<T>, grid1(B), 128, h->D, B);
+    if ((rc = unpack_to_host(h, h->D.J_cur, J_out, B, 1, nullptr, 0))) return rc;
+    if ((rc = unpack_to_host(h, h->D.sc, step_cost_out, B, h->N + 1, nullptr, 0))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// dense per-stage outputs are written by a kernel straight into the staging buffer, chunk by chunk
+template <typename T>
+int stage_derivs(Impl<T>* h, int B, const double* u, const double* x, const double* ref_velo, const double* borders,
+                 const int32_t* tmpl, const int32_t* n_obs, const double* obs, int obs_len, const double* alm_mu,
+                 const double* alm_rho, double* lx, double* lu, double* lxx, double* luu, double* A, double* Bm,
+                 double* alm_mu_next) {
+    CK(cudaSetDevice(h->device));
+    int rc;
+    const int N = h->N;
+    if ((rc = upload_problem_data(h, B, ref_velo, borders, tmpl, n_obs, obs, obs_len))) return rc;
+    if ((rc = load_traj(h, B, u, x))) return rc;
+    if ((rc = load_alm(h, B, alm_mu, alm_rho))) return rc;
+    constexpr int G = 8;
+    LAUNCH(h, k_ref_match<T, G>, dim3((B + 15) / 16), 128, h->D, B, 0, -1);
+    LAUNCH(h, k_derivs<T>, grid2(B, N + 1), 128, h->D, B, 0);
+    // dense conversion on device into a temporary allocation (test path; not part of create-time budget)
+    size_t n_lx = size_t(B) * (N + 1) * 4, n_lu = size_t(B) * N * 2, n_lxx = size_t(B) * (N + 1) * 16,
+           n_luu = size_t(B) * N * 4, n_A = size_t(B) * N * 16, n_B = size_t(B) * N * 8;
+    double* tmp = nullptr;
+    size_t total = n_lx + n_lu + n_lxx + n_luu + n_A + n_B;
+    CK(cudaMalloc(&tmp, total * sizeof(double)));
+    double *p_lx = tmp, *p_lu = p_lx + n_lx, *p_lxx = p_lu + n_lu, *p_luu = p_lxx + n_lxx, *p_A = p_luu + n_luu,
+           *p_B = p_A + n_A;
+    LAUNCH(h, k_records_to_dense<T>, grid2(B, N + 1), 128, h->D, B, p_lx, p_lu, p_lxx, p_luu, p_A, p_B);
+    cudaError_t e = cudaSuccess;
+    auto get = [&](double* dst, const double* src, size_t n) {
+        if (dst && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    };
+    get(lx, p_lx, n_lx);
+    get(lu, p_lu, n_lu);
+    get(lxx, p_lxx, n_lxx);
+    get(luu, p_luu, n_luu);
+    get(A, p_A, n_A);
+    get(Bm, p_B, n_B);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(CILQR_ERR_CUDA, "stage_derivs download: %s", cudaGetErrorString(e));
+    if (h->any_alm && alm_mu_next) {
+        if ((rc = unpack_to_host(h, h->D.mu_next, alm_mu_next, B, N * h->D.alm_cols, nullptr, 0))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+template <typename T>
+int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const double* lxx, const double* luu,
+                   const double* A, const double* Bm, const double* lamb, double* d_out, double* K_out,
+                   double* dV_out, int32_t* status_out) {
+    CK(cudaSetDevice(h->device));
+    int rc;
+    const int N = h->N;
+    size_t n_lx = size_t(B) * (N + 1) * 4, n_lu = size_t(B) * N * 2, n_lxx = size_t(B) * (N + 1) * 16,
+           n_luu = size_t(B) * N * 4, n_A = size_t(B) * N * 16, n_B = size_t(B) * N * 8;
+    size_t total = n_lx + n_lu + n_lxx + n_luu + n_A + n_B;
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, total * sizeof(double)));
+    double *p_lx = tmp, *p_lu = p_lx + n_lx, *p_lxx = p_lu + n_lu, *p_luu = p_lxx + n_lxx, *p_A = p_luu + n_luu,
+           *p_B = p_A + n_A;
+    cudaError_t e = cudaSuccess;
+    auto put = [&](double* dst, const double* src, size_t n) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    };
+    put(p_lx, lx, n_lx);
+    put(p_lu, lu, n_lu);
+    put(p_lxx, lxx, n_lxx);
+    put(p_luu, luu, n_luu);
+    put(p_A, A, n_A);
+    put(p_B, Bm, n_B);
+    if (e != cudaSuccess) {
+        cudaFree(tmp);
+        return fail(CILQR_ERR_CUDA, "stage_backward upload: %s", cudaGetErrorString(e));
+    }
+    LAUNCH(h, k_records_from_dense<T>, grid2(B, N + 1), 128, h->D, B, p_lx, p_lu, p_lxx, p_luu, p_A, p_B);
+    if ((rc = pack_to_device(h, lamb, h->D.lamb, B, 1, 1, 1, 1))) {
+        cudaFree(tmp);
+        return rc;
+    }
+    LAUNCH(h, k_backward<T>, grid1(B), 128, h->D, B, 0);
+    e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(CILQR_ERR_CUDA, "stage_backward: %s", cudaGetErrorString(e));
+    if ((rc = unpack_to_host(h, h->D.dg, d_out, B, N * 2, nullptr, 0))) return rc;
+    if ((rc = unpack_to_host(h, h->D.Kg, K_out, B, N * 8, nullptr, 0))) return rc;
+    if ((rc = unpack_to_host(h, h->D.dV, dV_out, B, 2, nullptr, 0))) return rc;
+    if ((rc = download_ints(h, h->D.status, status_out, B))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename T>
+int stage_forward(Impl<T>* h, int B, const double* u, const double* x, const double* d, const double* K,
+                  const double* alpha, const int32_t* tmpl, double* new_u, double* new_x) {
+    CK(cudaSetDevice(h->device));
+    int rc;
+    const int N = h->N;
+    if ((rc = upload_ints(h, tmpl, h->D.tmpl, B, 0))) return rc;
+    if ((rc = load_traj(h, B, u, x))) return rc;
+    if ((rc = pack_to_device(h, d, h->D.dg, B, 1, N * 2, N * 2, 1))) return rc;
+    if ((rc = pack_to_device(h, K, h->D.Kg, B, 1, N * 8, N * 8, 1))) return rc;
+    if ((rc = pack_to_device(h, alpha, h->D.alpha, B, 1, 1, 1, 1))) return rc;
+    LAUNCH(h, k_forward<T>, grid1(B), 128, h->D, B, 0);
+    if ((rc = unpack_to_host(h, h->D.U + size_t(N) * 2 * h->Bs, new_u, B, N * 2, nullptr, 0))) return rc;
+    if ((rc = unpack_to_host(h, h->D.X + size_t(N + 1) * 4 * h->Bs, new_x, B, (N + 1) * 4, nullptr, 0))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename T>
+int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float* ms_out, double* bytes_per_launch) {
+    CK(cudaSetDevice(h->device));
+    if (flush_l2 && !h->flush) {
+        h->flush_n = (size_t(256) << 20) / sizeof(float);
+        CK(cudaMalloc(&h->flush, h->flush_n * sizeof(float)));
+        h->allocs.push_back(h->flush);
+        CK(cudaMemsetAsync(h->flush, 0, h->flush_n * sizeof(float), h->stream));
+    }
+    std::vector<T> l(B, T(lamb));
+    CK(cudaMemcpyAsync(h->D.lamb, l.data(), size_t(B) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < reps; ++r) {
+        if (flush_l2) {
+            k_flush_l2<<<148 * 8, 256, 0, h->stream>>>(h->flush, h->flush_n);
+        }
+        CK(cudaEventRecord(h->t0, h->stream));
+        LAUNCH(h, k_backward<T>, grid1(B), 128, h->D, B, 0);
+        CK(cudaEventRecord(h->t1, h->stream));
+        CK(cudaEventSynchronize(h->t1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->t0, h->t1));
+        if (ms_out) ms_out[r] = ms;
+    }
+    CK(cudaGetLastError());
+    if (bytes_per_launch) *bytes_per_launch = double(38 * h->N + 18) * sizeof(T) * double(B);
+    return 0;
+}
+
+template <typename T>
+int bench_tile(Impl<T>* h, int B0, int B) {
+    CK(cudaSetDevice(h->device));
+    if (B0 <= 0 || B0 > B) return fail(CILQR_ERR_INVALID, "need 0 < B0 <= B");
+    LAUNCH(h, k_tile_records<T>, grid2(B, (h->N + 1) * kRecFields), 128, h->D, B0, B);
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename T>
+int do_reset(Impl<T>* h) {
+    CK(cudaSetDevice(h->device));
+    std::vector<int> ones(h->Bs, 1);
+    CK(cudaMemcpyAsync(h->D.first, ones.data(), ones.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename T>
+int do_set_template(Impl<T>* h, int t, const cilqr_params_t* params, const double* wx, const double* wy,
+                    const double* wyaw, int M) {
+    CK(cudaSetDevice(h->device));
+    if (params) {
+        int rc = check_params(params);
+        if (rc) return rc;
+        h->params[t] = *params;
+        h->tmpl_set[t] = true;
+    } else if (!h->tmpl_set[t]) {
+        h->params[t] = h->params[0];
+        h->tmpl_set[t] = true;
+    }
+    if (wx || wy || wyaw) {
+        if (!(wx && wy && wyaw)) return fail(CILQR_ERR_INVALID, "reference line needs x, y and yaw");
+        if (M <= 0 || M > 65535)
+            return fail(CILQR_ERR_INVALID, "reference line must hold 1..65535 waypoints (uint16_t index in the reference), got %d", M);
+        // rebuild the concatenated table with template t replaced
+        std::vector<double> nx, ny, nyaw;
+        int off[CILQR_B200_MAX_TEMPLATES], len[CILQR_B200_MAX_TEMPLATES];
+        for (int i = 0; i < CILQR_B200_MAX_TEMPLATES; ++i) {
+            off[i] = int(nx.size());
+            if (i == t) {
+                nx.insert(nx.end(), wx, wx + M);
+                ny.insert(ny.end(), wy, wy + M);
+                nyaw.insert(nyaw.end(), wyaw, wyaw + M);
+                len[i] = M;
+            } else {
+                int o = h->wp_off[i], l = h->wp_len[i];
+                nx.insert(nx.end(), h->h_wx.begin() + o, h->h_wx.begin() + o + l);
+                ny.insert(ny.end(), h->h_wy.begin() + o, h->h_wy.begin() + o + l);
+                nyaw.insert(nyaw.end(), h->h_wyaw.begin() + o, h->h_wyaw.begin() + o + l);
+                len[i] = l;
+            }
+        }
+        h->h_wx.swap(nx);
+        h->h_wy.swap(ny);
+        h->h_wyaw.swap(nyaw);
+        for (int i = 0; i < CILQR_B200_MAX_TEMPLATES; ++i) {
+            h->wp_off[i] = off[i];
+            h->wp_len[i] = len[i];
+        }
+    }
+    return upload_templates(h);
+}
+
+template <typename T>
+int do_destroy(Impl<T>* h) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_active) cudaFreeHost(h->h_active);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cilqr_b200_last_error(void) { return g_err.c_str(); }
+const char* cilqr_b200_version(void) { return "cilqr_b200 0.1 (sm_100a)"; }
+
+int cilqr_b200_create(const cilqr_params_t* params, int device, int max_batch, int N, int max_obs, int dtype,
+                      cilqr_handle_t** out) {
+    if (!out) return fail(CILQR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (max_batch <= 0) return fail(CILQR_ERR_INVALID, "max_batch must be positive");
+    if (N < 1 || N > 4096) return fail(CILQR_ERR_INVALID, "horizon N must be in [1, 4096]");
+    if (max_obs < 0 || max_obs > 64) return fail(CILQR_ERR_INVALID, "max_obs must be in [0, 64]");
+    if (dtype != CILQR_F64 && dtype != CILQR_F32) return fail(CILQR_ERR_INVALID, "dtype must be CILQR_F64 or CILQR_F32");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(CILQR_ERR_NO_DEVICE, "no CUDA device (%s); cilqr_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(CILQR_ERR_INVALID, "device %d outside [0, %d)", device, count);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CILQR_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    return dtype == CILQR_F64 ? create_impl<double>(params, device, max_batch, N, max_obs, out)
+                              : create_impl<float>(params, device, max_batch, N, max_obs, out);
+}
+
+int cilqr_b200_destroy(cilqr_handle_t* h) {
+    if (!h) return 0;
+    return DISPATCH(h, do_destroy);
+}
+
+int cilqr_b200_set_stream(cilqr_handle_t* h, void* cuda_stream) {
+    if (!h) return fail(CILQR_ERR_INVALID, "handle is NULL");
+    Base* b = base(h);
+    b->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->own_stream;
+    return 0;
+}
+
+int cilqr_b200_set_template(cilqr_handle_t* h, int tmpl, const cilqr_params_t* params, const double* wx,
+                            const double* wy, const double* wyaw, int M) {
+    if (!h) return fail(CILQR_ERR_INVALID, "handle is NULL");
+    if (tmpl < 0 || tmpl >= CILQR_B200_MAX_TEMPLATES) return fail(CILQR_ERR_INVALID, "template id %d outside [0, %d)", tmpl, CILQR_B200_MAX_TEMPLATES);
+    return DISPATCH(h, do_set_template, tmpl, params, wx, wy, wyaw, M);
+}
+
+int cilqr_b200_reset(cilqr_handle_t* h) {
+    if (!h) return fail(CILQR_ERR_INVALID, "handle is NULL");
+    return DISPATCH(h, do_reset);
+}
+
+int cilqr_b200_upload(cilqr_handle_t* h, int B, const double* x0, const double* ref_velo, const double* borders,
+                      const int32_t* tmpl, const int32_t* n_obs, const double* obs, int obs_len) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    rc = DISPATCH(h, do_upload, B, x0, ref_velo, borders, tmpl, n_obs, obs, obs_len);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(base(h)->stream));
+    return 0;
+}
+
+int cilqr_b200_solve_resident(cilqr_handle_t* h, int B) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    return DISPATCH(h, do_solve_resident, B);
+}
+
+int cilqr_b200_download(cilqr_handle_t* h, int B, double* u_out, double* x_out, double* J_out, double* K_out,
+                        double* d_out, double* step_cost_out, int32_t* status_out, int32_t* iters_out,
+                        int32_t* exit_out) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    rc = DISPATCH(h, do_download, B, u_out, x_out, J_out, K_out, d_out, step_cost_out, status_out, iters_out, exit_out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(base(h)->stream));
+    return 0;
+}
+
+int cilqr_b200_solve_batch(cilqr_handle_t* h, int B, const double* x0, const double* ref_velo, const double* borders,
+                           const int32_t* tmpl, const int32_t* n_obs, const double* obs, int obs_len, double* u_out,
+                           double* x_out, double* J_out, double* K_out, double* d_out, double* step_cost_out,
+                           int32_t* status_out, int32_t* iters_out, int32_t* exit_out) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    rc = DISPATCH(h, do_upload, B, x0, ref_velo, borders, tmpl, n_obs, obs, obs_len);
+    if (rc) return rc;
+    rc = DISPATCH(h, do_solve_resident, B);
+    if (rc) return rc;
+    rc = DISPATCH(h, do_download, B, u_out, x_out, J_out, K_out, d_out, step_cost_out, status_out, iters_out, exit_out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(base(h)->stream));
+    return 0;
+}
+
+int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out) {
+    if (!h || !out) return fail(CILQR_ERR_INVALID, "NULL argument");
+    *out = base(h)->counters;
+    return 0;
+}
+
+int cilqr_b200_stage_init(cilqr_handle_t* h, int B, const double* x0, const int32_t* tmpl, int warm,
+                          const double* last_u, double* u_out, double* x_out) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    return DISPATCH(h, stage_init, B, x0, tmpl, warm, last_u, u_out, x_out);
+}
+
+int cilqr_b200_stage_ref_match(cilqr_handle_t* h, int B, const double* x, const int32_t* tmpl, int32_t* idx_out) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    return DISPATCH(h, stage_ref_match, B, x, tmpl, idx_out);
+}
+
+int cilqr_b200_stage_cost(cilqr_handle_t* h, int B, const double* u, const double* x, const double* ref_velo,
+                          const double* borders, const int32_t* tmpl, const int32_t* n_obs, const double* obs,
+                          int obs_len, const double* alm_mu, const double* alm_rho, double* J_out,
+                          double* step_cost_out) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    return DISPATCH(h, stage_cost, B, u, x, ref_velo, borders, tmpl, n_obs, obs, obs_len, alm_mu, alm_rho, J_out, step_cost_out);
+}
+
+int cilqr_b200_stage_derivs(cilqr_handle_t* h, int B, const double* u, const double* x, const double* ref_velo,
+                            const double* borders, const int32_t* tmpl, const int32_t* n_obs, const double* obs,
+                            int obs_len, const double* alm_mu, const double* alm_rho, double* lx, double* lu,
+                            double* lxx, double* luu, double* A, double* Bm, double* alm_mu_next) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    return DISPATCH(h, stage_derivs, B, u, x, ref_velo, borders, tmpl, n_obs, obs, obs_len, alm_mu, alm_rho, lx, lu, lxx, luu, A, Bm, alm_mu_next);
+}
+
+int cilqr_b200_stage_backward(cilqr_handle_t* h, int B, const double* lx, const double* lu, const double* lxx,
+                              const double* luu, const double* A, const double* Bm, const double* lamb,
+                              double* d_out, double* K_out, double* dV_out, int32_t* status_out) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!lx || !lu || !lxx || !luu || !A || !Bm || !lamb) return fail(CILQR_ERR_INVALID, "NULL input array");
+    return DISPATCH(h, stage_backward, B, lx, lu, lxx, luu, A, Bm, lamb, d_out, K_out, dV_out, status_out);
+}
+
+int cilqr_b200_stage_forward(cilqr_handle_t* h, int B, const double* u, const double* x, const double* d,
+                             const double* K, const double* alpha, const int32_t* tmpl, double* new_u,
+                             double* new_x) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    return DISPATCH(h, stage_forward, B, u, x, d, K, alpha, tmpl, new_u, new_x);
+}
+
+int cilqr_b200_bench_backward(cilqr_handle_t* h, int B, double lamb, int reps, int flush_l2, float* ms_out,
+                              double* bytes_per_launch) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0 || reps <= 0) return fail(CILQR_ERR_INVALID, "need B > 0 and reps > 0");
+    return DISPATCH(h, bench_backward, B, lamb, reps, flush_l2, ms_out, bytes_per_launch);
+}
+
+int cilqr_b200_bench_tile_records(cilqr_handle_t* h, int B0, int B) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    return DISPATCH(h, bench_tile, B0, B);
+}
+
+}  // extern "C"

@@ -1,0 +1,898 @@
+// Batched CILQR kernels for sm_100a.
+//
+// Memory layout ("step-major SoA"): every per-trajectory array is stored as
+// [step][field][batch] with the batch index innermost and a batch stride Bs
+// (multiple of 128).  Consecutive lanes of a warp own consecutive
+// trajectories, so every global access below is a fully coalesced 128-byte
+// (fp32) or 256-byte (fp64) row, whichever stage is running:
+//   * step-parallel stages (cost, derivatives): one thread per (trajectory, step);
+//   * serial chains (rollouts, Riccati recursion): one thread per trajectory,
+//     the 4x4 / 4x2 / 2x2 blocks held in registers, A and B in their sparse
+//     form (5 + 4 non-trivial entries), V_xx / l_xx symmetric (10 entries);
+//   * waypoint matching: G lanes per trajectory scan a G-wide window of the
+//     reference line per probe and pick the first local minimum by ballot.
+// No tensor cores: the largest contraction is 4x4x4.
+#pragma once
+
+#include "cilqr_model.cuh"
+
+namespace cilqr {
+
+constexpr int kRecFields = 28;  // compact derivative record per step
+constexpr int kRecLx = 0;       // l_x   [4]
+constexpr int kRecLxx = 4;      // l_xx  sym: 00 01 02 03 11 12 13 22 23 33
+constexpr int kRecLu = 14;      // l_u   [2]
+constexpr int kRecLuu = 16;     // l_uu  sym: 00 01 11
+constexpr int kRecA = 19;       // A     a02 a03 a12 a13 a32
+constexpr int kRecB = 24;       // B     b01 b11 b20 b31
+constexpr int kRecTerminal = 14;  // the terminal record holds l_x and l_xx only
+
+constexpr int kNumAlphas = 20;  // alpha = 2^0 .. 2^-19  (cpp:354)
+
+enum Phase : int { PH_BACKWARD = 0, PH_SEARCH = 1, PH_DONE = 2 };
+enum Status : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BWD_FAIL = 2, ST_FWD_FAIL = 3, ST_SMALL_STEP = 4 };
+enum ExitReason : int { EX_MAX_ITER = 0, EX_CONVERGED = 1, EX_MAX_LAMB = 2 };
+
+// Everything a kernel needs, passed by value.
+template <typename T>
+struct Dev {
+    int N, Bs, max_obs, alm_cols;
+    const DevParams<T>* P;  // [CILQR_B200_MAX_TEMPLATES]
+    const T* wx;
+    const T* wy;
+    const T* wyaw;
+    // problem data
+    T* ref_velo;  // [Bs]
+    T* borders;   // [2][Bs]
+    int* tmpl;    // [Bs]
+    int* n_obs;   // [Bs]
+    T* obs;       // [max_obs][N+1][3][Bs]
+    T* x0;        // [4][Bs]
+    // trajectories and what is derived from them, ping-pong pairs selected by cur[b]
+    T* X;       // [2][N+1][4][Bs]
+    T* U;       // [2][N][2][Bs]
+    int* ridx;  // [2][N+1][Bs]   matched waypoint per step
+    T* sc;      // [2][N+1][Bs]   per-step cost
+    int* cur;   // [Bs]
+    // derivative records and gains
+    T* rec;  // [N+1][28][Bs]
+    T* Kg;   // [N][8][Bs]
+    T* dg;   // [N][2][Bs]
+    T* dV;   // [2][Bs]
+    // solver state per instance
+    T* lamb;
+    T* J_cur;
+    T* J_init;
+    T* alpha;  // [Bs] explicit step length for the stage operator
+    int* status;
+    int* phase;
+    int* aidx;
+    int* iters;
+    int* exit_reason;
+    int* rec_valid;
+    T* last_u;  // [N][2][Bs]
+    int* first; // [Bs]
+    // augmented-Lagrangian state (allocated only when a template asks for it)
+    T* mu;       // [N][alm_cols][Bs]
+    T* mu_next;  // [N][alm_cols][Bs]
+    T* rho;      // [Bs]
+    int* active; // [max_rounds] instances still running after each round
+};
+
+template <typename T>
+__device__ __forceinline__ size_t at(const Dev<T>& D, int step, int field, int nfields, int b) {
+    return (size_t(step) * nfields + field) * D.Bs + b;
+}
+template <typename T>
+__device__ __forceinline__ size_t xbuf(const Dev<T>& D, int buf) { return size_t(buf) * (D.N + 1) * 4 * D.Bs; }
+template <typename T>
+__device__ __forceinline__ size_t ubuf(const Dev<T>& D, int buf) { return size_t(buf) * D.N * 2 * D.Bs; }
+template <typename T>
+__device__ __forceinline__ size_t sbuf(const Dev<T>& D, int buf) { return size_t(buf) * (D.N + 1) * D.Bs; }
+
+// ---------------------------------------------------------------------------
+// K0  initial trajectory: get_init_traj (cpp:155-161, :182-197) or the shifted
+//     warm start get_init_traj_increment (cpp:163-180); also resets the
+//     per-instance solver state the way solve() does (cpp:88-109).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, int reset_state) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const DevParams<T>& P = D.P[D.tmpl[b]];
+    const int N = D.N;
+    bool warm = force_warm > 0 || (force_warm < 0 && P.use_last && !D.first[b]);
+    T* X = D.X;  // buffer 0
+    T* U = D.U;
+    T x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        x[c] = D.x0[size_t(c) * D.Bs + b];
+        X[at(D, 0, c, 4, b)] = x[c];
+    }
+    for (int i = 0; i < N; ++i) {
+        T a = 0, s = 0;
+        if (warm) {
+            int src = (i + 1 < N) ? i + 1 : N - 1;
+            a = D.last_u[at(D, src, 0, 2, b)];
+            s = D.last_u[at(D, src, 1, 2, b)];
+        }
+        U[at(D, i, 0, 2, b)] = a;
+        U[at(D, i, 1, 2, b)] = s;
+        T nx[4];
+        propagate(x, a, s, P.dt, P.wheelbase, P.ref_point, nx);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            x[c] = nx[c];
+            X[at(D, i + 1, c, 4, b)] = nx[c];
+        }
+    }
+    D.cur[b] = 0;
+    if (reset_state) {
+        if (P.solve_type == 1 && D.mu && (!P.use_last || D.first[b])) {  // cpp:88-93
+            D.rho[b] = P.alm_rho_init;
+            for (int i = 0; i < N * D.alm_cols; ++i) {
+                D.mu[size_t(i) * D.Bs + b] = 0;
+                D.mu_next[size_t(i) * D.Bs + b] = 0;
+            }
+        }
+        D.first[b] = 0;
+        D.status[b] = ST_RUNNING;
+        D.lamb[b] = P.init_lamb;
+        D.iters[b] = 0;
+        D.phase[b] = PH_BACKWARD;
+        D.aidx[b] = 0;
+        D.rec_valid[b] = 0;
+        D.exit_reason[b] = EX_MAX_ITER;
+        D.dV[b] = 0;
+        D.dV[D.Bs + b] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1  get_ref_exact_points (cpp:289-314).  For each step the reference scans
+//     j = start, start+1, ... and stops at the first j whose successor is not
+//     strictly closer (or at the last waypoint); the next step starts there.
+//     Equivalent formulation used here: first j >= start with
+//     !(dist[j+1] < dist[j]) (NaN stops the scan, as in the reference).
+//     G lanes per trajectory evaluate a window of G waypoints per probe.
+//     `which` = 0: the current trajectory, 1: the line-search trial.
+// ---------------------------------------------------------------------------
+template <typename T, int G>
+__global__ void __launch_bounds__(128) k_ref_match(Dev<T> D, int B, int which, int need_phase) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % G;
+    const int grp_shift = lane - sub;  // first lane of my group inside the warp
+    int b = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    bool live = b < B;
+    if (live && need_phase >= 0) live = D.phase[b] == need_phase;
+    int bb = b < B ? b : B - 1;  // keep addresses valid for idle groups
+    const DevParams<T>& P = D.P[D.tmpl[bb]];
+    const int M = P.wp_len;
+    const T* wx = D.wx + P.wp_off;
+    const T* wy = D.wy + P.wp_off;
+    const int buf = which ? 1 - D.cur[bb] : D.cur[bb];
+    const T* X = D.X + xbuf(D, buf);
+    int* R = D.ridx + sbuf(D, buf);
+    const unsigned grp_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << grp_shift);
+    int start = 0;
+    for (int k = 0; k <= D.N; ++k) {
+        T px = X[at(D, k, 0, 4, bb)];
+        T py = X[at(D, k, 1, 4, bb)];
+        int found = -1;
+        bool done = !live;
+        // all groups of the warp iterate together; finished groups idle
+        while (!__all_sync(0xffffffffu, done)) {
+            int j = start + sub;
+            int jc = j < M ? j : M - 1;
+            T dj = m_hypot(px - wx[jc], py - wy[jc]);
+            T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
+            bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
+            unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
+            if (!done) {
+                if (m) {
+                    found = start + (__ffs(m) - 1 - grp_shift);
+                    done = true;
+                } else {
+                    start += G - 1;
+                }
+            }
+        }
+        if (live) {
+            if (found > M - 1) found = M - 1;
+            if (sub == 0) R[size_t(k) * D.Bs + b] = found;
+            start = found;
+        }
+    }
+}
+
+// The eight box constraints of one step in the reference's order
+// (cpp:222-241): acc up/lo, steer up/lo, velocity up/lo, lateral up/lo.
+template <typename T>
+__device__ __forceinline__ void ctrl_constraints(const DevParams<T>& P, T acc, T steer, T c[4]) {
+    c[0] = acc - P.acc_max;
+    c[1] = P.acc_min - acc;
+    c[2] = steer - P.stl_lim;
+    c[3] = -P.stl_lim - steer;
+}
+
+// ---------------------------------------------------------------------------
+// K2  get_total_cost (cpp:199-287), one thread per (trajectory, step k):
+//     state term of x_k, control term of u_k (k < N), constraint terms of
+//     step k (k >= 1: u_{k-1}, x_k, ref_k, obstacles at tick k).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_cost(Dev<T> D, int B, int which, int need_phase) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (b >= B) return;
+    if (need_phase >= 0 && D.phase[b] != need_phase) return;
+    const DevParams<T>& P = D.P[D.tmpl[b]];
+    const int N = D.N;
+    const int buf = which ? 1 - D.cur[b] : D.cur[b];
+    const T* X = D.X + xbuf(D, buf);
+    const T* U = D.U + ubuf(D, buf);
+    const int ri = D.ridx[sbuf(D, buf) + size_t(k) * D.Bs + b];
+    T x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = X[at(D, k, c, 4, b)];
+    const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
+    const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
+    T cost = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        T e = x[c] - ref[c];
+        cost += e * P.Q[c] * e;
+    }
+    if (k < N) {
+        T a = U[at(D, k, 0, 2, b)], s = U[at(D, k, 1, 2, b)];
+        T ce = a * P.R[0] * a;
+        ce += s * P.R[1] * s;
+        cost += ce;
+    }
+    if (k >= 1) {
+        T a = U[at(D, k - 1, 0, 2, b)], s = U[at(D, k - 1, 1, 2, b)];
+        T c[8];
+        ctrl_constraints(P, a, s, c);
+        c[4] = x[2] - P.velo_max;
+        c[5] = P.velo_min - x[2];
+        T d_sign, hyp;
+        T cur_d = lateral_offset(x[0], x[1], rx, ry, ryaw, &d_sign, &hyp);
+        c[6] = cur_d - (D.borders[b] - P.width / 2);
+        c[7] = (D.borders[D.Bs + b] + P.width / 2) - cur_d;
+        T Jk = 0;
+        const bool alm = P.solve_type == 1;
+        const T rho = alm ? D.rho[b] : T(0);
+        const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * D.Bs + b : nullptr;
+        if (!alm) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) Jk += exp_barrier(c[m], P.st_q1, P.st_q2);
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) Jk += alm_item(c[m], rho, mu[size_t(m) * D.Bs]);
+        }
+        const int no = D.n_obs[b];
+        if (no > 0) {
+            EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
+            for (int j = 0; j < no; ++j) {
+                const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 3 * D.Bs + b;
+                T ox = ob[0], oy = ob[D.Bs], oyaw = ob[2 * size_t(D.Bs)];
+                T so, co;
+                m_sincos(oyaw, &so, &co);
+                T cf = ellipse_margin<T, false>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
+                T cr = ellipse_margin<T, false>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
+                if (!alm) {
+                    Jk += exp_barrier(cf, P.obs_q1, P.obs_q2);
+                    Jk += exp_barrier(cr, P.obs_q1, P.obs_q2);
+                } else {
+                    Jk += alm_item(cf, rho, mu[size_t(8 + 2 * j) * D.Bs]);
+                    Jk += alm_item(cr, rho, mu[size_t(9 + 2 * j) * D.Bs]);
+                }
+            }
+        }
+        cost += Jk;
+    }
+    D.sc[sbuf(D, buf) + size_t(k) * D.Bs + b] = cost;
+}
+
+// J = sum of the step costs of the current trajectory (used once after init).
+template <typename T>
+__global__ void __launch_bounds__(128) k_sum_cost(Dev<T> D, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const T* sc = D.sc + sbuf(D, D.cur[b]);
+    T J = 0;
+    for (int k = 0; k <= D.N; ++k) J += sc[size_t(k) * D.Bs + b];
+    D.J_cur[b] = J;
+    D.J_init[b] = J;
+}
+
+// One constraint's gradient / Gauss-Newton Hessian weight: returns (g, h) with
+// grad += g * c_dot and hess += h * c_dot c_dot^T.  Barrier: g = q2*b, h = q2^2*b
+// (cpp:692-699); ALM: g = rho*(c + mu/rho) if that is > 0 else 0, h = g (cpp:701-713).
+template <typename T>
+__device__ __forceinline__ void constraint_weights(bool alm, T c, T q1, T q2, T rho, T mu, T* g, T* h) {
+    if (!alm) {
+        T bv = exp_barrier(c, q1, q2);
+        *g = q2 * bv;
+        *h = (q2 * q2) * bv;
+    } else {
+        T t = c + mu / rho;
+        T w = (t > 0) ? rho * t : T(0);
+        *g = w;
+        *h = w;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3 + K4  get_total_cost_derivatives_and_Hessians (cpp:463-690) and
+//     get_kinematic_model_derivatives (src/utils.cpp:285-342), one thread per
+//     (trajectory, step k), writing the compact record of step k:
+//     l_x[k], l_xx[k] (constraints of x_k if k >= 1), and for k < N
+//     l_u[k], l_uu[k] (constraints of u_k, i.e. the reference's step k+1), A_k, B_k.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (b >= B) return;
+    if (masked && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) return;
+    const DevParams<T>& P = D.P[D.tmpl[b]];
+    const int N = D.N;
+    const int buf = D.cur[b];
+    const T* X = D.X + xbuf(D, buf);
+    const T* U = D.U + ubuf(D, buf);
+    const int ri = D.ridx[sbuf(D, buf) + size_t(k) * D.Bs + b];
+    const bool alm = P.solve_type == 1;
+    const T rho = alm ? D.rho[b] : T(0);
+    T x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = X[at(D, k, c, 4, b)];
+    const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
+    const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
+
+    T gx[4] = {0, 0, 0, 0};
+    T H[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
+    if (k >= 1) {
+        const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * D.Bs + b : nullptr;
+        T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * D.Bs + b : nullptr;
+        // velocity bounds: c_dot = (0,0,+-1,0)
+        T cv[2] = {x[2] - P.velo_max, P.velo_min - x[2]};
+        T g, h;
+        constraint_weights(alm, cv[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4) * D.Bs] : T(0), &g, &h);
+        gx[2] += g;
+        H[7] += h;
+        constraint_weights(alm, cv[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(5) * D.Bs] : T(0), &g, &h);
+        gx[2] += -g;
+        H[7] += h;
+        // road borders: c_dot = +-(px-rx, py-ry)/hypot, flipped when d_sign < 0 (cpp:527-533)
+        T d_sign, hyp;
+        T cur_d = lateral_offset(x[0], x[1], rx, ry, ryaw, &d_sign, &hyp);
+        T cp[2] = {cur_d - (D.borders[b] - P.width / 2), (D.borders[D.Bs + b] + P.width / 2) - cur_d};
+        T n0 = (x[0] - rx) / hyp, n1 = (x[1] - ry) / hyp;
+        if (d_sign < 0) {
+            n0 = -n0;
+            n1 = -n1;
+        }
+        constraint_weights(alm, cp[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(6) * D.Bs] : T(0), &g, &h);
+        gx[0] += g * n0;
+        gx[1] += g * n1;
+        H[0] += h * (n0 * n0);
+        H[1] += h * (n0 * n1);
+        H[4] += h * (n1 * n1);
+        constraint_weights(alm, cp[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(7) * D.Bs] : T(0), &g, &h);
+        gx[0] += g * (-n0);
+        gx[1] += g * (-n1);
+        H[0] += h * (n0 * n0);
+        H[1] += h * (n0 * n1);
+        H[4] += h * (n1 * n1);
+        if (alm) {
+            mun[size_t(4) * D.Bs] = std_min(std_max(mu[size_t(4) * D.Bs] + rho * cv[0], T(0)), P.max_mu);
+            mun[size_t(5) * D.Bs] = std_min(std_max(mu[size_t(5) * D.Bs] + rho * cv[1], T(0)), P.max_mu);
+            mun[size_t(6) * D.Bs] = std_min(std_max(mu[size_t(6) * D.Bs] + rho * cp[0], T(0)), P.max_mu);
+            mun[size_t(7) * D.Bs] = std_min(std_max(mu[size_t(7) * D.Bs] + rho * cp[1], T(0)), P.max_mu);
+        }
+        // obstacles: front and rear circle against each ellipse (cpp:648-664)
+        const int no = D.n_obs[b];
+        if (no > 0) {
+            EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
+            for (int j = 0; j < no; ++j) {
+                const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 3 * D.Bs + b;
+                T ox = ob[0], oy = ob[D.Bs], oyaw = ob[2 * size_t(D.Bs)];
+                T so, co;
+                m_sincos(oyaw, &so, &co);
+                T gfx, gfy, grx, gry;
+                T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
+                T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
+                // chain through the 4x2 centre Jacobians: (gx, gy, 0, yaw row)
+                T f3 = e.jf0 * gfx + e.jf1 * gfy;
+                T r3 = e.jr0 * grx + e.jr1 * gry;
+                T gf, hf, gr, hr;
+                constraint_weights(alm, cf, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(8 + 2 * j) * D.Bs] : T(0), &gf, &hf);
+                constraint_weights(alm, cr, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(9 + 2 * j) * D.Bs] : T(0), &gr, &hr);
+                // front + rear first, then into the row (cpp:662-664)
+                gx[0] += gf * gfx + gr * grx;
+                gx[1] += gf * gfy + gr * gry;
+                gx[3] += gf * f3 + gr * r3;
+                H[0] += hf * (gfx * gfx) + hr * (grx * grx);
+                H[1] += hf * (gfx * gfy) + hr * (grx * gry);
+                H[3] += hf * (gfx * f3) + hr * (grx * r3);
+                H[4] += hf * (gfy * gfy) + hr * (gry * gry);
+                H[6] += hf * (gfy * f3) + hr * (gry * r3);
+                H[9] += hf * (f3 * f3) + hr * (r3 * r3);
+                if (alm) {
+                    mun[size_t(8 + 2 * j) * D.Bs] =
+                        std_min(std_max(mu[size_t(8 + 2 * j) * D.Bs] + rho * cf, T(0)), P.max_mu);
+                    mun[size_t(9 + 2 * j) * D.Bs] =
+                        std_min(std_max(mu[size_t(9 + 2 * j) * D.Bs] + rho * cr, T(0)), P.max_mu);
+                }
+            }
+        }
+    }
+    // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
+    T* rec = D.rec + size_t(k) * kRecFields * D.Bs + b;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) rec[size_t(kRecLx + c) * D.Bs] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
+    H[0] += 2 * P.Q[0];
+    H[4] += 2 * P.Q[1];
+    H[7] += 2 * P.Q[2];
+    H[9] += 2 * P.Q[3];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) rec[size_t(kRecLxx + c) * D.Bs] = H[c];
+
+    if (k < N) {
+        T a = U[at(D, k, 0, 2, b)], s = U[at(D, k, 1, 2, b)];
+        T c[4];
+        ctrl_constraints(P, a, s, c);
+        const T* mu = alm ? D.mu + size_t(k) * D.alm_cols * D.Bs + b : nullptr;
+        T g[4], h[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            constraint_weights(alm, c[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * D.Bs] : T(0), &g[m], &h[m]);
+        T gu0 = g[0] + (-g[1]);
+        T gu1 = g[2] + (-g[3]);
+        T hu0 = h[0] + h[1];
+        T hu1 = h[2] + h[3];
+        if (alm) {
+            T* mun = D.mu_next + size_t(k) * D.alm_cols * D.Bs + b;
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                mun[size_t(m) * D.Bs] = std_min(std_max(mu[size_t(m) * D.Bs] + rho * c[m], T(0)), P.max_mu);
+        }
+        rec[size_t(kRecLu + 0) * D.Bs] = 2 * (a * P.R[0]) + gu0;
+        rec[size_t(kRecLu + 1) * D.Bs] = 2 * (s * P.R[1]) + gu1;
+        rec[size_t(kRecLuu + 0) * D.Bs] = 2 * P.R[0] + hu0;
+        rec[size_t(kRecLuu + 1) * D.Bs] = 0;
+        rec[size_t(kRecLuu + 2) * D.Bs] = 2 * P.R[1] + hu1;
+        T ja[5], jb[4];
+        model_jacobians(x[2], x[3], s, P.dt, P.wheelbase, P.ref_point, ja, jb);
+#pragma unroll
+        for (int c2 = 0; c2 < 5; ++c2) rec[size_t(kRecA + c2) * D.Bs] = ja[c2];
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2) rec[size_t(kRecB + c2) * D.Bs] = jb[c2];
+    }
+}
+
+// solve()'s bookkeeping after an iter_step (cpp:113-141): lambda schedule,
+// iteration count, the three exits.
+template <typename T>
+__device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T>& P, int b, int status) {
+    T lamb = D.lamb[b];
+    if (status == ST_BWD_FAIL || status == ST_FWD_FAIL) {
+        lamb = std_max(P.lamb_amplify, lamb * P.lamb_amplify);
+    } else if (status == ST_RUNNING) {
+        lamb *= P.lamb_decay;
+    }
+    D.lamb[b] = lamb;
+    D.status[b] = status;
+    int it = D.iters[b] + 1;
+    D.iters[b] = it;
+    D.aidx[b] = 0;
+    if (lamb > P.max_lamb) {
+        D.phase[b] = PH_DONE;
+        D.exit_reason[b] = EX_MAX_LAMB;
+    } else if (status == ST_CONVERGED) {
+        D.phase[b] = PH_DONE;
+        D.exit_reason[b] = EX_CONVERGED;
+    } else if (it >= P.max_iter) {
+        D.phase[b] = PH_DONE;
+        D.exit_reason[b] = EX_MAX_ITER;
+    } else {
+        D.phase[b] = PH_BACKWARD;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5  backward_pass (cpp:391-439): the Riccati recursion, one thread per
+//     trajectory.  Per step it streams the 28-scalar record (l_x 4, l_xx 10,
+//     l_u 2, l_uu 3, A 5, B 4) and writes K (8) and d (2):
+//     (38 N + 18) * sizeof(T) algorithmic bytes per trajectory.
+//     Q_uu + lambda*I is tested exactly like Eigen::LLT (lower, unblocked):
+//     fail iff a pivot <= 0, NaN passes (cpp:415-420); the inverse is the
+//     adjugate times 1/det (cpp:421).  `solver` != 0: act on instances in
+//     PH_BACKWARD, drive the state machine; 0: standalone stage.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (solver && D.phase[b] != PH_BACKWARD) return;
+    const int N = D.N;
+    const size_t Bs = D.Bs;
+    const T lamb = D.lamb[b];
+    const T* rec = D.rec + size_t(N) * kRecFields * Bs + b;
+    T Vx[4], V[10];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Vx[c] = rec[size_t(kRecLx + c) * Bs];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) V[c] = rec[size_t(kRecLxx + c) * Bs];
+    T dV0 = 0, dV1 = 0;
+    bool failed = false;
+    int i = N - 1;
+    for (; i >= 0; --i) {
+        rec -= size_t(kRecFields) * Bs;
+        T r[kRecFields];
+#pragma unroll
+        for (int c = 0; c < kRecFields; ++c) r[c] = rec[size_t(c) * Bs];
+        const T a02 = r[kRecA + 0], a03 = r[kRecA + 1], a12 = r[kRecA + 2], a13 = r[kRecA + 3], a32 = r[kRecA + 4];
+        const T b01 = r[kRecB + 0], b11 = r[kRecB + 1], b20 = r[kRecB + 2], b31 = r[kRecB + 3];
+        // symmetric V: 00 01 02 03 11 12 13 22 23 33
+        const T V00 = V[0], V01 = V[1], V02 = V[2], V03 = V[3], V11 = V[4], V12 = V[5], V13 = V[6], V22 = V[7],
+                V23 = V[8], V33 = V[9];
+        // W = V A  (columns 0,1 unchanged)
+        const T W02 = a02 * V00 + a12 * V01 + V02 + a32 * V03;
+        const T W12 = a02 * V01 + a12 * V11 + V12 + a32 * V13;
+        const T W22 = a02 * V02 + a12 * V12 + V22 + a32 * V23;
+        const T W32 = a02 * V03 + a12 * V13 + V23 + a32 * V33;
+        const T W03 = a03 * V00 + a13 * V01 + V03;
+        const T W13 = a03 * V01 + a13 * V11 + V13;
+        const T W23 = a03 * V02 + a13 * V12 + V23;
+        const T W33 = a03 * V03 + a13 * V13 + V33;
+        // Q_xx = l_xx + A^T V A  (symmetric, upper triangle)
+        T Qxx[10];
+        Qxx[0] = r[kRecLxx + 0] + V00;
+        Qxx[1] = r[kRecLxx + 1] + V01;
+        Qxx[2] = r[kRecLxx + 2] + W02;
+        Qxx[3] = r[kRecLxx + 3] + W03;
+        Qxx[4] = r[kRecLxx + 4] + V11;
+        Qxx[5] = r[kRecLxx + 5] + W12;
+        Qxx[6] = r[kRecLxx + 6] + W13;
+        Qxx[7] = r[kRecLxx + 7] + (a02 * W02 + a12 * W12 + W22 + a32 * W32);
+        Qxx[8] = r[kRecLxx + 8] + (a02 * W03 + a12 * W13 + W23 + a32 * W33);
+        Qxx[9] = r[kRecLxx + 9] + (a03 * W03 + a13 * W13 + W33);
+        // Q_x = l_x + A^T V_x ; Q_u = l_u + B^T V_x
+        T Qx[4];
+        Qx[0] = r[kRecLx + 0] + Vx[0];
+        Qx[1] = r[kRecLx + 1] + Vx[1];
+        Qx[2] = r[kRecLx + 2] + (a02 * Vx[0] + a12 * Vx[1] + Vx[2] + a32 * Vx[3]);
+        Qx[3] = r[kRecLx + 3] + (a03 * Vx[0] + a13 * Vx[1] + Vx[3]);
+        const T Qu0 = r[kRecLu + 0] + b20 * Vx[2];
+        const T Qu1 = r[kRecLu + 1] + (b01 * Vx[0] + b11 * Vx[1] + b31 * Vx[3]);
+        // G = B^T V (2x4)
+        const T G00 = b20 * V02, G01 = b20 * V12, G02 = b20 * V22, G03 = b20 * V23;
+        const T G10 = b01 * V00 + b11 * V01 + b31 * V03;
+        const T G11 = b01 * V01 + b11 * V11 + b31 * V13;
+        const T G12 = b01 * V02 + b11 * V12 + b31 * V23;
+        const T G13 = b01 * V03 + b11 * V13 + b31 * V33;
+        // Q_ux = G A (2x4)
+        T Qux[8];
+        Qux[0] = G00;
+        Qux[1] = G01;
+        Qux[2] = a02 * G00 + a12 * G01 + G02 + a32 * G03;
+        Qux[3] = a03 * G00 + a13 * G01 + G03;
+        Qux[4] = G10;
+        Qux[5] = G11;
+        Qux[6] = a02 * G10 + a12 * G11 + G12 + a32 * G13;
+        Qux[7] = a03 * G10 + a13 * G11 + G13;
+        // Q_uu = l_uu + G B + lambda I  (both off-diagonals kept, as the reference computes them)
+        const T Quu00 = (r[kRecLuu + 0] + G02 * b20) + lamb;
+        const T Quu01 = r[kRecLuu + 1] + (G00 * b01 + G01 * b11 + G03 * b31);
+        const T Quu10 = r[kRecLuu + 1] + G12 * b20;
+        const T Quu11 = (r[kRecLuu + 2] + (G10 * b01 + G11 * b11 + G13 * b31)) + lamb;
+        // LLT positive-definiteness test
+        if (Quu00 <= T(0)) {
+            failed = true;
+            break;
+        }
+        {
+            const T l10 = Quu10 / m_sqrt(Quu00);
+            if (Quu11 - l10 * l10 <= T(0)) {
+                failed = true;
+                break;
+            }
+        }
+        const T invdet = T(1) / (Quu00 * Quu11 - Quu10 * Quu01);
+        const T i00 = Quu11 * invdet, i01 = -Quu01 * invdet, i10 = -Quu10 * invdet, i11 = Quu00 * invdet;
+        const T d0 = (-i00) * Qu0 + (-i01) * Qu1;
+        const T d1 = (-i10) * Qu0 + (-i11) * Qu1;
+        T K[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            K[c] = (-i00) * Qux[c] + (-i01) * Qux[4 + c];
+            K[4 + c] = (-i10) * Qux[c] + (-i11) * Qux[4 + c];
+        }
+        D.dg[at(D, i, 0, 2, b)] = d0;
+        D.dg[at(D, i, 1, 2, b)] = d1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) D.Kg[at(D, i, c, 8, b)] = K[c];
+        // value function update (cpp:427-432), regularised Q_uu
+        T M0[4], M1[4];  // K^T Q_uu, columns 0 and 1
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            M0[c] = K[c] * Quu00 + K[4 + c] * Quu10;
+            M1[c] = K[c] * Quu01 + K[4 + c] * Quu11;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            T t1 = M0[c] * d0 + M1[c] * d1;
+            T t2 = K[c] * Qu0 + K[4 + c] * Qu1;
+            T t3 = Qux[c] * d0 + Qux[4 + c] * d1;
+            Vx[c] = ((Qx[c] + t1) + t2) + t3;
+        }
+        {
+            int e = 0;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int cc = rr; cc < 4; ++cc, ++e) {
+                    T t1 = M0[rr] * K[cc] + M1[rr] * K[4 + cc];
+                    T t2 = K[rr] * Qux[cc] + K[4 + rr] * Qux[4 + cc];
+                    T t3 = Qux[rr] * K[cc] + Qux[4 + rr] * K[4 + cc];
+                    V[e] = ((Qxx[e] + t1) + t2) + t3;
+                }
+        }
+        // expected cost reduction (cpp:435-436)
+        const T h0 = T(0.5) * d0, h1 = T(0.5) * d1;
+        dV0 += (h0 * Quu00 + h1 * Quu10) * d0 + (h0 * Quu01 + h1 * Quu11) * d1;
+        dV1 += d0 * Qu0 + d1 * Qu1;
+    }
+    if (failed) {
+        // the reference returns freshly zeroed d, K rows for the steps it never reached
+        for (; i >= 0; --i) {
+            D.dg[at(D, i, 0, 2, b)] = 0;
+            D.dg[at(D, i, 1, 2, b)] = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) D.Kg[at(D, i, c, 8, b)] = 0;
+        }
+    }
+    D.dV[b] = dV0;
+    D.dV[Bs + b] = dV1;
+    if (solver) {
+        D.rec_valid[b] = 1;
+        if (failed) {
+            end_iteration(D, D.P[D.tmpl[b]], b, ST_BWD_FAIL);  // cpp:345-347, :118-120
+        } else {
+            D.status[b] = ST_RUNNING;  // set by the derivative stage (cpp:472/475)
+            D.phase[b] = PH_SEARCH;
+            D.aidx[b] = 0;
+        }
+    } else {
+        D.status[b] = failed ? ST_BWD_FAIL : ST_RUNNING;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K6  forward_pass (cpp:442-461): u' = u + K (x' - x) + alpha d, x' = f(x', u'),
+//     one thread per trajectory, written to the trial buffer.  In the solver
+//     alpha = 2^-aidx; the stage operator passes explicit alphas.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (solver && D.phase[b] != PH_SEARCH) return;
+    const DevParams<T>& P = D.P[D.tmpl[b]];
+    const int N = D.N;
+    const int buf = D.cur[b];
+    const T* X = D.X + xbuf(D, buf);
+    const T* U = D.U + ubuf(D, buf);
+    T* Xn = D.X + xbuf(D, 1 - buf);
+    T* Un = D.U + ubuf(D, 1 - buf);
+    const T alpha = solver ? T(1) / T(1 << D.aidx[b]) : D.alpha[b];
+    T xn[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        xn[c] = X[at(D, 0, c, 4, b)];
+        Xn[at(D, 0, c, 4, b)] = xn[c];
+    }
+    for (int i = 0; i < N; ++i) {
+        T dx[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dx[c] = xn[c] - X[at(D, i, c, 4, b)];
+        T un[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            T s = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s += D.Kg[at(D, i, r * 4 + c, 8, b)] * dx[c];
+            un[r] = (U[at(D, i, r, 2, b)] + s) + alpha * D.dg[at(D, i, r, 2, b)];
+            Un[at(D, i, r, 2, b)] = un[r];
+        }
+        T nx[4];
+        propagate(xn, un[0], un[1], P.dt, P.wheelbase, P.ref_point, nx);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            xn[c] = nx[c];
+            Xn[at(D, i + 1, c, 4, b)] = nx[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K7  the line-search verdict of iter_step (cpp:356-380) for the trial each
+//     searching instance just evaluated, then solve()'s bookkeeping.  Also
+//     counts the instances still running after this round.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int round) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    bool running = false;
+    if (b < B) {
+        int ph = D.phase[b];
+        if (ph == PH_SEARCH) {
+            const DevParams<T>& P = D.P[D.tmpl[b]];
+            const int cur = D.cur[b];
+            const T* sc = D.sc + sbuf(D, 1 - cur);
+            T new_J = 0;
+            for (int k = 0; k <= D.N; ++k) new_J += sc[size_t(k) * D.Bs + b];
+            const int a = D.aidx[b];
+            const T alpha = T(1) / T(1 << a);
+            const T actual = D.J_cur[b] - new_J;
+            if (a == 0 && m_fabs(actual) < P.conv_thr) {
+                end_iteration(D, P, b, ST_CONVERGED);  // trial discarded (cpp:358-361)
+            } else {
+                const T approx = -(alpha * alpha * D.dV[b] + alpha * D.dV[D.Bs + b]);
+                if (actual > T(0) && (approx < T(0) || actual / approx > P.accept_thr)) {
+                    D.cur[b] = 1 - cur;  // x, u <- new (cpp:113-116)
+                    D.J_cur[b] = new_J;
+                    D.rec_valid[b] = 0;
+                    end_iteration(D, P, b, a == 0 ? ST_RUNNING : ST_SMALL_STEP);
+                } else if (a + 1 >= kNumAlphas) {
+                    if (P.solve_type == 1 && D.mu) {  // cpp:377-378
+                        for (int i = 0; i < D.N * D.alm_cols; ++i)
+                            D.mu[size_t(i) * D.Bs + b] = D.mu_next[size_t(i) * D.Bs + b];
+                        D.rho[b] = std_min((1 + P.alm_gamma) * D.rho[b], P.max_rho);
+                        D.rec_valid[b] = 0;
+                    }
+                    end_iteration(D, P, b, ST_FWD_FAIL);
+                } else {
+                    D.aidx[b] = a + 1;
+                }
+            }
+            ph = D.phase[b];
+        }
+        running = ph != PH_DONE;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, running);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&D.active[round], __popc(m));
+}
+
+// In ALM mode the multipliers changed after a failed line search, so the cost of
+// the unchanged trajectory must be re-evaluated (the reference recomputes ori_cost
+// at every iter_step, cpp:342).  Barrier mode never needs this.
+template <typename T>
+__global__ void __launch_bounds__(128) k_refresh_cost(Dev<T> D, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (D.phase[b] != PH_BACKWARD || D.rec_valid[b]) return;
+    const T* sc = D.sc + sbuf(D, D.cur[b]);
+    T J = 0;
+    for (int k = 0; k <= D.N; ++k) J += sc[size_t(k) * D.Bs + b];
+    D.J_cur[b] = J;
+}
+
+// last_solve_u = u (cpp:144)
+template <typename T>
+__global__ void __launch_bounds__(128) k_store_last_u(Dev<T> D, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (b >= B) return;
+    const T* U = D.U + ubuf(D, D.cur[b]);
+    D.last_u[at(D, i, 0, 2, b)] = U[at(D, i, 0, 2, b)];
+    D.last_u[at(D, i, 1, 2, b)] = U[at(D, i, 1, 2, b)];
+}
+
+__global__ void k_pack_int(const int* __restrict__ src, int* __restrict__ dst, int B, int fill) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) dst[b] = src ? src[b] : fill;
+}
+
+// Dense reference layout <-> compact record, for the stage operators.
+// dense (host layout, per trajectory): lx [N+1][4], lu [N][2], lxx [N+1][16], luu [N][4], A [N][16], B [N][8].
+template <typename T>
+__global__ void k_records_from_dense(Dev<T> D, int B, const double* lx, const double* lu, const double* lxx,
+                                     const double* luu, const double* A, const double* Bm) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (b >= B) return;
+    const int N = D.N;
+    T* rec = D.rec + size_t(k) * kRecFields * D.Bs + b;
+    const double* px = lx + (size_t(b) * (N + 1) + k) * 4;
+    const double* pxx = lxx + (size_t(b) * (N + 1) + k) * 16;
+    for (int c = 0; c < 4; ++c) rec[size_t(kRecLx + c) * D.Bs] = T(px[c]);
+    int e = 0;
+    for (int r = 0; r < 4; ++r)
+        for (int c = r; c < 4; ++c, ++e) rec[size_t(kRecLxx + e) * D.Bs] = T(pxx[r * 4 + c]);
+    if (k < N) {
+        const double* pu = lu + (size_t(b) * N + k) * 2;
+        const double* puu = luu + (size_t(b) * N + k) * 4;
+        const double* pa = A + (size_t(b) * N + k) * 16;
+        const double* pb = Bm + (size_t(b) * N + k) * 8;
+        rec[size_t(kRecLu + 0) * D.Bs] = T(pu[0]);
+        rec[size_t(kRecLu + 1) * D.Bs] = T(pu[1]);
+        rec[size_t(kRecLuu + 0) * D.Bs] = T(puu[0]);
+        rec[size_t(kRecLuu + 1) * D.Bs] = T(puu[1]);
+        rec[size_t(kRecLuu + 2) * D.Bs] = T(puu[3]);
+        rec[size_t(kRecA + 0) * D.Bs] = T(pa[0 * 4 + 2]);
+        rec[size_t(kRecA + 1) * D.Bs] = T(pa[0 * 4 + 3]);
+        rec[size_t(kRecA + 2) * D.Bs] = T(pa[1 * 4 + 2]);
+        rec[size_t(kRecA + 3) * D.Bs] = T(pa[1 * 4 + 3]);
+        rec[size_t(kRecA + 4) * D.Bs] = T(pa[3 * 4 + 2]);
+        rec[size_t(kRecB + 0) * D.Bs] = T(pb[0 * 2 + 1]);
+        rec[size_t(kRecB + 1) * D.Bs] = T(pb[1 * 2 + 1]);
+        rec[size_t(kRecB + 2) * D.Bs] = T(pb[2 * 2 + 0]);
+        rec[size_t(kRecB + 3) * D.Bs] = T(pb[3 * 2 + 1]);
+    }
+}
+
+template <typename T>
+__global__ void k_records_to_dense(Dev<T> D, int B, double* lx, double* lu, double* lxx, double* luu, double* A,
+                                   double* Bm) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (b >= B) return;
+    const int N = D.N;
+    const T* rec = D.rec + size_t(k) * kRecFields * D.Bs + b;
+    double* px = lx + (size_t(b) * (N + 1) + k) * 4;
+    double* pxx = lxx + (size_t(b) * (N + 1) + k) * 16;
+    for (int c = 0; c < 4; ++c) px[c] = double(rec[size_t(kRecLx + c) * D.Bs]);
+    int e = 0;
+    for (int r = 0; r < 4; ++r)
+        for (int c = r; c < 4; ++c, ++e) {
+            double v = double(rec[size_t(kRecLxx + e) * D.Bs]);
+            pxx[r * 4 + c] = v;
+            pxx[c * 4 + r] = v;
+        }
+    if (k < N) {
+        double* pu = lu + (size_t(b) * N + k) * 2;
+        double* puu = luu + (size_t(b) * N + k) * 4;
+        double* pa = A + (size_t(b) * N + k) * 16;
+        double* pb = Bm + (size_t(b) * N + k) * 8;
+        pu[0] = double(rec[size_t(kRecLu + 0) * D.Bs]);
+        pu[1] = double(rec[size_t(kRecLu + 1) * D.Bs]);
+        puu[0] = double(rec[size_t(kRecLuu + 0) * D.Bs]);
+        puu[1] = puu[2] = double(rec[size_t(kRecLuu + 1) * D.Bs]);
+        puu[3] = double(rec[size_t(kRecLuu + 2) * D.Bs]);
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) pa[r * 4 + c] = (r == c) ? 1.0 : 0.0;
+        pa[0 * 4 + 2] = double(rec[size_t(kRecA + 0) * D.Bs]);
+        pa[0 * 4 + 3] = double(rec[size_t(kRecA + 1) * D.Bs]);
+        pa[1 * 4 + 2] = double(rec[size_t(kRecA + 2) * D.Bs]);
+        pa[1 * 4 + 3] = double(rec[size_t(kRecA + 3) * D.Bs]);
+        pa[3 * 4 + 2] = double(rec[size_t(kRecA + 4) * D.Bs]);
+        for (int c = 0; c < 8; ++c) pb[c] = 0.0;
+        pb[0 * 2 + 1] = double(rec[size_t(kRecB + 0) * D.Bs]);
+        pb[1 * 2 + 1] = double(rec[size_t(kRecB + 1) * D.Bs]);
+        pb[2 * 2 + 0] = double(rec[size_t(kRecB + 2) * D.Bs]);
+        pb[3 * 2 + 1] = double(rec[size_t(kRecB + 3) * D.Bs]);
+    }
+}
+
+// Replicate the records of trajectories [0, B0) over [B0, B) (roofline leg).
+template <typename T>
+__global__ void k_tile_records(Dev<T> D, int B0, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int row = blockIdx.y;  // (step, field) flattened
+    if (b >= B || b < B0) return;
+    T* p = D.rec + size_t(row) * D.Bs;
+    p[b] = p[b % B0];
+}
+
+// Writes a buffer larger than L2 so that the next timed launch starts cold.
+__global__ void k_flush_l2(float* buf, size_t n) {
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride) buf[i] = buf[i] * 0.5f + 1.0f;
+}
+
+}  // namespace cilqr

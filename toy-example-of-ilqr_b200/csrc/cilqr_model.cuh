@@ -1,0 +1,196 @@
+// Device functions of the CILQR hot path: bicycle model, model Jacobians, ego
+// circle centres, obstacle ellipse margin + gradient, barrier / augmented-
+// Lagrangian terms.  Written for sm_100a; everything stays in registers, the
+// callers own the memory layout.  Reference behaviour cited per function
+// (paths relative to the reference tree).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cilqr {
+
+// ---- scalar math, overloaded on the compute type --------------------------
+__device__ __forceinline__ double m_sin(double v) { return sin(v); }
+__device__ __forceinline__ float m_sin(float v) { return sinf(v); }
+__device__ __forceinline__ double m_cos(double v) { return cos(v); }
+__device__ __forceinline__ float m_cos(float v) { return cosf(v); }
+__device__ __forceinline__ void m_sincos(double v, double* s, double* c) { sincos(v, s, c); }
+__device__ __forceinline__ void m_sincos(float v, float* s, float* c) { sincosf(v, s, c); }
+__device__ __forceinline__ double m_tan(double v) { return tan(v); }
+__device__ __forceinline__ float m_tan(float v) { return tanf(v); }
+__device__ __forceinline__ double m_atan(double v) { return atan(v); }
+__device__ __forceinline__ float m_atan(float v) { return atanf(v); }
+__device__ __forceinline__ double m_exp(double v) { return exp(v); }
+__device__ __forceinline__ float m_exp(float v) { return expf(v); }
+__device__ __forceinline__ double m_hypot(double a, double b) { return hypot(a, b); }
+__device__ __forceinline__ float m_hypot(float a, float b) { return hypotf(a, b); }
+__device__ __forceinline__ double m_sqrt(double v) { return sqrt(v); }
+__device__ __forceinline__ float m_sqrt(float v) { return sqrtf(v); }
+__device__ __forceinline__ double m_fabs(double v) { return fabs(v); }
+__device__ __forceinline__ float m_fabs(float v) { return fabsf(v); }
+// std::max / std::min semantics (NaN in the first argument is kept), as the
+// reference uses them (cpp:82, :120, :378, :623).
+template <typename T>
+__device__ __forceinline__ T std_max(T a, T b) { return (a < b) ? b : a; }
+template <typename T>
+__device__ __forceinline__ T std_min(T a, T b) { return (b < a) ? b : a; }
+
+// Per-template solver scalars in the compute type (converted once on the host
+// from cilqr_params_t; derived ellipse semi-axes follow src/utils.cpp:387-393
+// with ego_pnt_radius = width/2, src/cilqr_solver.cpp:330, :78).
+template <typename T>
+struct DevParams {
+    T dt, wheelbase, width;
+    T Q[4];  // diag(w_pos, w_pos, w_vel, w_yaw)  (cpp:23-27)
+    T R[2];  // diag(w_acc, w_stl)                (cpp:28-30)
+    T obs_q1, obs_q2, st_q1, st_q2;
+    T acc_max, acc_min, stl_lim, velo_max, velo_min;
+    T ell_a2, ell_b2;  // squared semi-axes
+    T alm_rho_init, alm_gamma, max_rho, max_mu;
+    T init_lamb, lamb_decay, lamb_amplify, max_lamb, conv_thr, accept_thr;
+    int max_iter, solve_type, ref_point, use_last;
+    int wp_off, wp_len;  // slice of the handle's waypoint table
+};
+
+// src/utils.cpp:262-283 — one Euler step of the rear-axle (ref_point 0) or
+// centre-of-gravity (1) bicycle model; all right-hand sides use the old state.
+template <typename T>
+__device__ __forceinline__ void propagate(const T x[4], T acc, T steer, T dt, T wheelbase,
+                                          int ref_point, T out[4]) {
+    if (ref_point == 0) {
+        T s, c;
+        m_sincos(x[3], &s, &c);
+        out[0] = x[0] + x[2] * c * dt;
+        out[1] = x[1] + x[2] * s * dt;
+        out[2] = x[2] + acc * dt;
+        out[3] = x[3] + x[2] * m_tan(steer) * dt / wheelbase;
+    } else {
+        T beta = m_atan(m_tan(steer) / 2);
+        T s, c;
+        m_sincos(beta + x[3], &s, &c);
+        out[0] = x[0] + x[2] * c * dt;
+        out[1] = x[1] + x[2] * s * dt;
+        out[2] = x[2] + acc * dt;
+        out[3] = x[3] + 2 * x[2] * m_sin(beta) * dt / wheelbase;
+    }
+}
+
+// src/utils.cpp:285-342 — the non-trivial entries of A = df/dx (identity plus
+// a02 a03 a12 a13 a32) and B = df/du (b01 b11 b20 b31).  Keeps the reference's
+// quirk: the Jacobian's beta is atan(tan(steer/2)), not the step's
+// atan(tan(steer)/2), while d(beta)/d(steer) is that of the step's beta.
+template <typename T>
+__device__ __forceinline__ void model_jacobians(T velo, T yaw, T steer, T dt, T wheelbase,
+                                                int ref_point, T a[5], T b[4]) {
+    if (ref_point == 0) {
+        T s, c;
+        m_sincos(yaw, &s, &c);
+        a[0] = c * dt;
+        a[1] = velo * (-s) * dt;
+        a[2] = s * dt;
+        a[3] = velo * c * dt;
+        a[4] = m_tan(steer) * dt / wheelbase;
+        T cd = m_cos(steer);
+        b[0] = 0;
+        b[1] = 0;
+        b[2] = dt;
+        b[3] = (velo * dt / wheelbase) / (cd * cd);
+    } else {
+        T beta = m_atan(m_tan(steer / 2));
+        T td = m_tan(steer);
+        T t2 = td * td;
+        T dbeta = T(0.5) * (1 + t2) / (1 + T(0.25) * t2);
+        T s, c;
+        m_sincos(beta + yaw, &s, &c);
+        a[0] = c * dt;
+        a[1] = velo * (-s) * dt;
+        a[2] = s * dt;
+        a[3] = velo * c * dt;
+        a[4] = 2 * m_sin(beta) * dt / wheelbase;
+        b[0] = velo * (-s) * dt * dbeta;
+        b[1] = velo * c * dt * dbeta;
+        b[2] = dt;
+        b[3] = (2 * velo * dt / wheelbase) * m_cos(beta) * dbeta;
+    }
+}
+
+// Ego geometry shared by all obstacles of one step: circle centres
+// (src/utils.cpp:344-361) and the yaw rows of their 4x2 Jacobians (:363-385).
+template <typename T>
+struct EgoCircles {
+    T fx, fy, rx, ry;      // front / rear circle centres
+    T jf0, jf1, jr0, jr1;  // d(front)/d(yaw), d(rear)/d(yaw)
+};
+
+template <typename T>
+__device__ __forceinline__ EgoCircles<T> ego_circles(const T x[4], T wheelbase, int ref_point) {
+    EgoCircles<T> e;
+    T s, c;
+    m_sincos(x[3], &s, &c);
+    T wx = wheelbase * c, wy = wheelbase * s;
+    T half = T(0.5) * wheelbase;
+    if (ref_point == 0) {
+        e.fx = x[0] + wx;
+        e.fy = x[1] + wy;
+        e.rx = x[0];
+        e.ry = x[1];
+        e.jf0 = wheelbase * (-s);
+        e.jf1 = wheelbase * c;
+        e.jr0 = 0;
+        e.jr1 = 0;
+    } else {
+        e.fx = x[0] + T(0.5) * wx;
+        e.fy = x[1] + T(0.5) * wy;
+        e.rx = x[0] - T(0.5) * wx;
+        e.ry = x[1] - T(0.5) * wy;
+        e.jf0 = half * (-s);
+        e.jf1 = half * c;
+        e.jr0 = -half * (-s);
+        e.jr1 = -half * c;
+    }
+    return e;
+}
+
+// src/utils.cpp:395-407 and :409-439 for one circle centre against one
+// obstacle sample (ox, oy, sin/cos of its yaw): margin c = 1 - (xs^2/a^2 + ys^2/b^2)
+// and, when wanted, its gradient w.r.t. the point.
+template <typename T, bool kGrad>
+__device__ __forceinline__ T ellipse_margin(T px, T py, T ox, T oy, T so, T co, T a2, T b2, T* gx, T* gy) {
+    T dx = px - ox, dy = py - oy;
+    T xs = co * dx + so * dy;
+    T ys = -so * dx + co * dy;
+    T margin = 1 - ((xs * xs) / a2 + (ys * ys) / b2);
+    if (kGrad) {
+        T g0 = -2 * xs / a2, g1 = -2 * ys / b2;
+        *gx = co * g0 + (-so) * g1;
+        *gy = so * g0 + co * g1;
+    }
+    return margin;
+}
+
+// Lateral offset to the matched waypoint (cpp:235-241): signed *distance to the
+// waypoint*, sign from the cross product; sign(0) = +1 (include/utils.hpp:110-117).
+template <typename T>
+__device__ __forceinline__ T lateral_offset(T px, T py, T rx, T ry, T ryaw, T* d_sign, T* hyp) {
+    T s, c;
+    m_sincos(ryaw, &s, &c);
+    T ds = (py - ry) * c - (px - rx) * s;
+    T h = m_hypot(px - rx, py - ry);
+    *d_sign = ds;
+    *hyp = h;
+    return (ds < 0 ? T(-1) : T(1)) * h;
+}
+
+// include/cilqr_solver.hpp:80 and :81-83
+template <typename T>
+__device__ __forceinline__ T exp_barrier(T c, T q1, T q2) {
+    return q1 * m_exp(q2 * c);
+}
+template <typename T>
+__device__ __forceinline__ T alm_item(T c, T rho, T mu) {
+    T v = std_max(c + mu / rho, T(0));
+    return rho * (v * v) / 2;
+}
+
+}  // namespace cilqr
