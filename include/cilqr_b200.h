@@ -126,15 +126,33 @@ int cilqr_b200_download(cilqr_handle_t* h, int B, double* u_out, double* x_out, 
                         int32_t* exit_out);
 
 /* Counters of the last solve: total iter_step calls over the batch, line-search
- * rounds run, kernels launched, instances per exit reason. */
+ * trials (forward pass + cost) evaluated, device rounds run, kernels launched,
+ * instances per exit reason. */
 typedef struct cilqr_counters_t {
     int64_t total_iters;
+    int64_t total_trials;
     int32_t rounds;
     int32_t launches;
     int32_t exits[3];
     int32_t reserved;
 } cilqr_counters_t;
 int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
+
+/* Execution options; none of them changes a result bit.
+ *  CILQR_OPT_WIDE_SEARCH (default 1): instances in a streak of rejected steps evaluate all
+ *      remaining alphas of iter_step's line search (cpp:354-372) in one device round and
+ *      keep the first that passes; 0 evaluates one alpha per round.
+ *  CILQR_OPT_RUN_AHEAD (default 3): device rounds the host may queue beyond the last one
+ *      whose active count it has seen. */
+typedef enum cilqr_option_t { CILQR_OPT_WIDE_SEARCH = 0, CILQR_OPT_RUN_AHEAD = 1 } cilqr_option_t;
+int cilqr_b200_set_option(cilqr_handle_t* h, int option, int value);
+
+/* Per-iteration decision trace (lockstep tests): record the first `cap` iter_step outcomes of
+ * every instance of subsequent solves; get_trace returns status [B][cap] (cilqr_status_t after
+ * each iter_step), alpha [B][cap] (index of the accepted / converged alpha, -1 if none) and
+ * cost [B][cap] (cost iter_step returned).  Rows beyond iters_out[b] are undefined. */
+int cilqr_b200_enable_trace(cilqr_handle_t* h, int cap);
+int cilqr_b200_get_trace(cilqr_handle_t* h, int B, int32_t* status, int32_t* alpha, double* cost);
 
 /* ---- stage operators (one per reference function; host layout in and out) ----
  * Used by the parity tests and by bench.py's roofline leg.  Each uploads its

@@ -332,10 +332,17 @@ int oracle_solve_batch(int dtype, int N, int n_tmpl, const Params* params, const
                        const double* borders, const int32_t* n_obs, int max_obs, int obs_len,
                        const double* obs, double* u_out, double* x_out, double* K_out, double* d_out,
                        double* J_out, int32_t* status_out, int32_t* iters_out, int32_t* exit_out,
-                       int nthreads) {
+                       int trace_cap, int32_t* tr_status, int32_t* tr_alpha, double* tr_cost, int nthreads) {
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(0);
     std::atomic<int> bad(0);
+    auto copy_trace = [&](const std::vector<IterTrace>& tr, int b) {
+        for (int i = 0; i < trace_cap && i < int(tr.size()); ++i) {
+            if (tr_status) tr_status[size_t(b) * trace_cap + i] = tr[i].status;
+            if (tr_alpha) tr_alpha[size_t(b) * trace_cap + i] = tr[i].alpha_index;
+            if (tr_cost) tr_cost[size_t(b) * trace_cap + i] = tr[i].new_cost;
+        }
+    };
     auto worker = [&]() {
         for (;;) {
             int b = next.fetch_add(1);
@@ -357,12 +364,14 @@ int oracle_solve_batch(int dtype, int N, int n_tmpl, const Params* params, const
                 Solver<double> s(params[t], N);
                 solve_one(s, M, wx + off, wy + off, wyaw + off, ref_velo[b], n_obs[b], obs_len, ob,
                           borders + size_t(b) * 2, x0 + size_t(b) * 4, uo, xo, Ko, dout, J2, nullptr,
-                          info, nullptr, false);
+                          info, nullptr, trace_cap > 0);
+                copy_trace(s.trace, b);
             } else {
                 Solver<float> s(params[t], N);
                 solve_one(s, M, wx + off, wy + off, wyaw + off, ref_velo[b], n_obs[b], obs_len, ob,
                           borders + size_t(b) * 2, x0 + size_t(b) * 4, uo, xo, Ko, dout, J2, nullptr,
-                          info, nullptr, false);
+                          info, nullptr, trace_cap > 0);
+                copy_trace(s.trace, b);
             }
             if (J_out) {
                 J_out[size_t(b) * 2 + 0] = J2[0];

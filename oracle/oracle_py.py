@@ -193,9 +193,12 @@ class BatchResult:
     status: np.ndarray
     iters: np.ndarray
     exit_reason: np.ndarray
+    tr_status: np.ndarray = None
+    tr_alpha: np.ndarray = None
+    tr_cost: np.ndarray = None
 
 
-def solve_batch(pb, dtype="f64", nthreads=None, want_traj=True):
+def solve_batch(pb, dtype="f64", nthreads=None, want_traj=True, trace_cap=0):
     """B independent first solves on `nthreads` host threads (one solve per thread at a time)."""
     if nthreads is None:
         nthreads = os.cpu_count() or 1
@@ -219,9 +222,14 @@ def solve_batch(pb, dtype="f64", nthreads=None, want_traj=True):
         u = x = K = d = None
     J = np.empty((B, 2))
     st, it, ex = np.empty(B, np.int32), np.empty(B, np.int32), np.empty(B, np.int32)
+    trs = tra = trc = None
+    if trace_cap > 0:
+        trs, tra = np.zeros((B, trace_cap), np.int32), np.zeros((B, trace_cap), np.int32)
+        trc = np.zeros((B, trace_cap))
     rc = lib().oracle_solve_batch(DT[dtype], N, nt, parr, _ip(off), _dp(wx), _dp(wy), _dp(wyaw), B, _ip(tm),
                                   _dp(x0), _dp(rv), _dp(bd), _ip(no), int(pb.max_obs), int(pb.obs_len), _dp(ob),
-                                  _dp(u), _dp(x), _dp(K), _dp(d), _dp(J), _ip(st), _ip(it), _ip(ex), int(nthreads))
+                                  _dp(u), _dp(x), _dp(K), _dp(d), _dp(J), _ip(st), _ip(it), _ip(ex),
+                                  int(trace_cap), _ip(trs), _ip(tra), _dp(trc), int(nthreads))
     if rc != 0:
         raise RuntimeError("oracle_solve_batch failed: %d" % rc)
-    return BatchResult(u, x, K, d, J, st, it, ex)
+    return BatchResult(u, x, K, d, J, st, it, ex, trs, tra, trc)

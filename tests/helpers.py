@@ -40,3 +40,23 @@ def oracle_stage(pb, b, u, x, dtype="f64"):
 def relerr(a, b, floor=1.0):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+def compare_traces(gpu_solver, out, ref, cap):
+    """Lockstep comparison of per-iteration decisions (status, accepted alpha) of a GPU solve
+    against the oracle's.  Returns (same, prefix_len): `same[b]` is True when the whole decision
+    sequence agrees; prefix_len[b] is the number of leading iterations that agree."""
+    st, al, co = gpu_solver.get_trace(len(out.iters))
+    B = len(out.iters)
+    same = np.zeros(B, bool)
+    prefix = np.zeros(B, int)
+    worst_prefix_cost = 0.0
+    for b in range(B):
+        n = min(out.iters[b], ref.iters[b], cap)
+        eq = (st[b, :n] == ref.tr_status[b, :n]) & (al[b, :n] == ref.tr_alpha[b, :n])
+        k = n if eq.all() else int(np.argmin(eq))
+        prefix[b] = k
+        same[b] = (k == n) and out.iters[b] == ref.iters[b] and out.exit_reason[b] == ref.exit_reason[b]
+        if k > 0:
+            worst_prefix_cost = max(worst_prefix_cost, relerr(co[b, :k], ref.tr_cost[b, :k]))
+    return same, prefix, worst_prefix_cost

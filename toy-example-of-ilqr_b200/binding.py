@@ -31,6 +31,7 @@ EXPORTS = [
     "cilqr_b200_last_error", "cilqr_b200_version", "cilqr_b200_create", "cilqr_b200_destroy",
     "cilqr_b200_set_stream", "cilqr_b200_set_template", "cilqr_b200_reset", "cilqr_b200_solve_batch",
     "cilqr_b200_upload", "cilqr_b200_solve_resident", "cilqr_b200_download", "cilqr_b200_counters",
+    "cilqr_b200_set_option", "cilqr_b200_enable_trace", "cilqr_b200_get_trace",
     "cilqr_b200_stage_init", "cilqr_b200_stage_ref_match", "cilqr_b200_stage_cost", "cilqr_b200_stage_derivs",
     "cilqr_b200_stage_backward", "cilqr_b200_stage_forward", "cilqr_b200_bench_backward",
     "cilqr_b200_bench_tile_records",
@@ -49,8 +50,8 @@ class CilqrParams(C.Structure):
 
 
 class Counters(C.Structure):
-    _fields_ = [("total_iters", C.c_int64), ("rounds", C.c_int32), ("launches", C.c_int32),
-                ("exits", C.c_int32 * 3), ("reserved", C.c_int32)]
+    _fields_ = [("total_iters", C.c_int64), ("total_trials", C.c_int64), ("rounds", C.c_int32),
+                ("launches", C.c_int32), ("exits", C.c_int32 * 3), ("reserved", C.c_int32)]
 
 
 class CilqrError(RuntimeError):
@@ -153,8 +154,24 @@ class BatchSolver:
     def counters(self):
         c = Counters()
         self._ck(self.lib.cilqr_b200_counters(self.h, C.byref(c)))
-        return {"total_iters": int(c.total_iters), "rounds": int(c.rounds), "launches": int(c.launches),
-                "exits": dict(zip(EXIT_NAMES, list(c.exits)))}
+        return {"total_iters": int(c.total_iters), "total_trials": int(c.total_trials), "rounds": int(c.rounds),
+                "launches": int(c.launches), "exits": dict(zip(EXIT_NAMES, list(c.exits)))}
+
+    OPT_WIDE_SEARCH, OPT_RUN_AHEAD = 0, 1
+
+    def set_option(self, option, value):
+        self._ck(self.lib.cilqr_b200_set_option(self.h, int(option), int(value)))
+
+    def enable_trace(self, cap):
+        self._trace_cap = int(cap)
+        self._ck(self.lib.cilqr_b200_enable_trace(self.h, int(cap)))
+
+    def get_trace(self, B):
+        """(status, alpha, cost), each [B][cap]: outcome of every iter_step of the last solve."""
+        cap = self._trace_cap
+        st, al, co = np.empty((B, cap), np.int32), np.empty((B, cap), np.int32), np.empty((B, cap))
+        self._ck(self.lib.cilqr_b200_get_trace(self.h, int(B), _ip(st), _ip(al), _dp(co)))
+        return st, al, co
 
     # -- solve ---------------------------------------------------------------
     def _alloc_out(self, B, want_gains=True, pinned=None):

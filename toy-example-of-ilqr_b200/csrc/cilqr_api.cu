@@ -35,8 +35,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(CILQR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kRunAhead = 2;     // rounds the host may queue beyond the last one it has a count for
-constexpr int kMaxWaypoints = 1 << 20;
+constexpr int kGridCap = 148 * 8;  // grid-stride kernels: at most 8 CTAs of 128 threads per SM
 
 // Type-erased part of a handle; the typed buffers live in Impl<T>.
 struct Base {
@@ -48,8 +47,8 @@ struct Base {
     std::vector<double> h_wx, h_wy, h_wyaw;  // concatenated tables
     bool any_alm = false;
     int max_rounds = 0;
-    int* h_active = nullptr;  // pinned
-    cudaEvent_t ev[kRunAhead + 1] = {nullptr};
+    int run_ahead = 3;
+    volatile int* h_ctl = nullptr;  // mapped pinned: [0] rounds completed, [1] instances active after it
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     double* stage = nullptr;  // device staging in host layout
     size_t stage_bytes = 0;
@@ -191,16 +190,7 @@ int upload_templates(Impl<T>* h) {
         int rc = alloc_alm(h);
         if (rc) return rc;
     }
-    int need = max_iter * kNumAlphas + 8;
-    if (need > h->max_rounds) {
-        int* q = nullptr;
-        CK(cudaMalloc(&q, size_t(need) * sizeof(int)));
-        h->allocs.push_back(q);
-        h->D.active = q;
-        if (h->h_active) CK(cudaFreeHost(h->h_active));
-        CK(cudaHostAlloc(&h->h_active, size_t(need) * sizeof(int), cudaHostAllocDefault));
-        h->max_rounds = need;
-    }
+    h->max_rounds = max_iter * kNumAlphas + 8;
     return 0;
 }
 
@@ -218,16 +208,29 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
-        for (auto& e : h->ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventCreate(&h->t0));
         CK(cudaEventCreate(&h->t1));
         Dev<T>& D = h->D;
         D.N = N;
         D.Bs = h->Bs;
+        // trial pool: room for every instance's single trial plus wide searches of the stragglers
+        D.Vs = int(std::min<size_t>(size_t(h->Bs) * 4, size_t(h->Bs) + (size_t(1) << 21)));
         D.max_obs = max_obs;
         D.alm_cols = 8 + 2 * max_obs;
-        const size_t Bs = h->Bs;
+        D.wide_mode = 1;
+        D.trace_cap = 0;
+        const size_t Bs = h->Bs, Vs = D.Vs;
         int r;
+        {
+            int* hc = nullptr;
+            CK(cudaHostAlloc(&hc, 2 * sizeof(int), cudaHostAllocMapped));
+            hc[0] = hc[1] = 0;
+            h->h_ctl = hc;
+            int* dc = nullptr;
+            CK(cudaHostGetDevicePointer(&dc, hc, 0));
+            D.h_ctl = dc;
+        }
+        if ((r = dalloc(h, &D.ctl, CTL_WORDS))) return r;
         if ((r = dalloc(h, &h->dP, CILQR_B200_MAX_TEMPLATES))) return r;
         D.P = h->dP;
         if ((r = dalloc(h, &D.ref_velo, Bs))) return r;
@@ -236,11 +239,20 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.n_obs, Bs))) return r;
         if ((r = dalloc(h, &D.obs, size_t(max_obs) * (N + 1) * 3 * Bs))) return r;
         if ((r = dalloc(h, &D.x0, 4 * Bs))) return r;
-        if ((r = dalloc(h, &D.X, size_t(2) * (N + 1) * 4 * Bs))) return r;
-        if ((r = dalloc(h, &D.U, size_t(2) * N * 2 * Bs))) return r;
-        if ((r = dalloc(h, &D.ridx, size_t(2) * (N + 1) * Bs))) return r;
-        if ((r = dalloc(h, &D.sc, size_t(2) * (N + 1) * Bs))) return r;
-        if ((r = dalloc(h, &D.cur, Bs))) return r;
+        if ((r = dalloc(h, &D.X, size_t(N + 1) * 4 * Bs))) return r;
+        if ((r = dalloc(h, &D.U, size_t(N) * 2 * Bs))) return r;
+        if ((r = dalloc(h, &D.ridx, size_t(N + 1) * Bs))) return r;
+        if ((r = dalloc(h, &D.sc, size_t(N + 1) * Bs))) return r;
+        if ((r = dalloc(h, &D.Xt, size_t(N + 1) * 4 * Vs))) return r;
+        if ((r = dalloc(h, &D.Ut, size_t(N) * 2 * Vs))) return r;
+        if ((r = dalloc(h, &D.ridx_t, size_t(N + 1) * Vs))) return r;
+        if ((r = dalloc(h, &D.sc_t, size_t(N + 1) * Vs))) return r;
+        if ((r = dalloc(h, &D.t_inst, Vs))) return r;
+        if ((r = dalloc(h, &D.t_aidx, Vs))) return r;
+        if ((r = dalloc(h, &D.t_first, Bs))) return r;
+        if ((r = dalloc(h, &D.t_count, Bs))) return r;
+        if ((r = dalloc(h, &D.commit_src, Bs))) return r;
+        if ((r = dalloc(h, &D.wide, Bs))) return r;
         if ((r = dalloc(h, &D.rec, size_t(N + 1) * kRecFields * Bs))) return r;
         if ((r = dalloc(h, &D.Kg, size_t(N) * 8 * Bs))) return r;
         if ((r = dalloc(h, &D.dg, size_t(N) * 2 * Bs))) return r;
@@ -293,6 +305,9 @@ inline Base* base(cilqr_handle_t* h) { return reinterpret_cast<Base*>(h); }
 
 inline dim3 grid1(int B) { return dim3((B + 127) / 128); }
 inline dim3 grid2(int B, int rows) { return dim3((B + 127) / 128, rows); }
+// grid-stride launches: enough CTAs for `count` items, capped at a multiple of the 148 SMs
+inline dim3 gs1(int count) { return dim3(std::max(1, std::min((count + 127) / 128, kGridCap))); }
+inline dim3 gs2(int count, int rows) { return dim3(std::max(1, std::min((count + 127) / 128, kGridCap)), rows); }
 
 template <typename... KArgs, typename... Args>
 inline void launch_kernel(Base* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args&&... args) {
@@ -347,15 +362,12 @@ int pack_to_device(Impl<T>* h, const double* src, T* dst, int B, int blocks, int
 
 template <typename T>
 __global__ void k_unpack_rows(const T* __restrict__ src, double* __restrict__ dst, int B, int E, size_t Bs,
-                              const int* __restrict__ sel, size_t buf_stride, int b_off) {
+                              int b_off) {
     __shared__ double tile[32][33];
     int e0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         int e = e0 + r, b = b0 + threadIdx.x;
-        if (b < B && e < E) {
-            size_t off = sel ? size_t(sel[b_off + b]) * buf_stride : 0;
-            tile[r][threadIdx.x] = double(src[off + size_t(e) * Bs + b_off + b]);
-        }
+        if (b < B && e < E) tile[r][threadIdx.x] = double(src[size_t(e) * Bs + b_off + b]);
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
@@ -365,14 +377,15 @@ __global__ void k_unpack_rows(const T* __restrict__ src, double* __restrict__ ds
 }
 
 template <typename T>
-int unpack_to_host(Impl<T>* h, const T* src, double* dst, int B, int E, const int* sel, size_t buf_stride) {
+int unpack_to_host(Impl<T>* h, const T* src, double* dst, int B, int E, size_t stride = 0) {
     if (!dst || E == 0 || B == 0) return 0;
+    if (stride == 0) stride = h->Bs;
     size_t per = size_t(E) * sizeof(double);
     int chunk = int(std::min<size_t>(size_t(B), std::max<size_t>(h->stage_bytes / per, 1)));
     for (int b0 = 0; b0 < B; b0 += chunk) {
         int nb = std::min(chunk, B - b0);
         dim3 g((E + 31) / 32, (nb + 31) / 32), blk(32, 8);
-        k_unpack_rows<T><<<g, blk, 0, h->stream>>>(src, h->stage, nb, E, h->Bs, sel, buf_stride, b0);
+        k_unpack_rows<T><<<g, blk, 0, h->stream>>>(src, h->stage, nb, E, stride, b0);
         h->launches++;
         CK(cudaMemcpyAsync(dst + size_t(b0) * E, h->stage, size_t(nb) * per, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -452,14 +465,13 @@ int do_upload(Impl<T>* h, int B, const double* x0, const double* ref_velo, const
     return 0;
 }
 
-// cost of the trajectory in buffer `which` (0 current / 1 trial): waypoint match + per-step costs
+// waypoint match + per-step costs of a set of trajectories (0: current, 1: the trial pool)
 template <typename T>
-void launch_cost(Impl<T>* h, int B, int which, int need_phase) {
+void launch_cost(Impl<T>* h, int B, int trial) {
     constexpr int G = 8;
-    int threads = 128;
-    int per_block = threads / G;
-    LAUNCH(h, k_ref_match<T, G>, dim3((B + per_block - 1) / per_block), threads, h->D, B, which, need_phase);
-    LAUNCH(h, k_cost<T>, grid2(B, h->N + 1), 128, h->D, B, which, need_phase);
+    const int cap = trial ? h->D.Vs : B;
+    LAUNCH(h, k_ref_match<T, G>, gs1(cap * G), 128, h->D, B, trial);
+    LAUNCH(h, k_cost<T>, gs2(cap, h->N + 1), 128, h->D, B, trial);
 }
 
 template <typename T>
@@ -468,33 +480,41 @@ int do_solve_resident(Impl<T>* h, int B) {
     if (B == 0) return 0;
     const int N = h->N;
     h->launches = 0;
-    CK(cudaMemsetAsync(h->D.active, 0, size_t(h->max_rounds) * sizeof(int), h->stream));
-    LAUNCH(h, k_init<T>, grid1(B), 128, h->D, B, -1, 1);
-    launch_cost(h, B, 0, -1);
-    LAUNCH(h, k_sum_cost<T>, grid1(B), 128, h->D, B);
-    int rounds = 0;
-    for (int r = 0; r < h->max_rounds; ++r) {
+    CK(cudaStreamSynchronize(h->stream));
+    h->h_ctl[0] = 0;
+    h->h_ctl[1] = B;
+    CK(cudaMemsetAsync(h->D.ctl, 0, CTL_WORDS * sizeof(int), h->stream));
+    LAUNCH(h, k_init<T>, gs1(B), 128, h->D, B, -1, 1);
+    launch_cost(h, B, 0);
+    LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 0);
+    // One round = one line-search step for every running instance.  The verdict kernel publishes
+    // (rounds completed, instances still running) into mapped host memory; the host keeps at most
+    // run_ahead rounds queued beyond the last count it has seen and stops at zero.
+    int launched = 0;
+    const int trial_cap = h->D.Vs;
+    while (launched < h->max_rounds) {
+        int done = h->h_ctl[0];
+        if (done > 0 && h->h_ctl[1] == 0) break;
+        if (launched - done > h->run_ahead) continue;  // spin on the mapped words
+        LAUNCH(h, k_derivs<T>, gs2(B, N + 1), 128, h->D, B, 1);
         if (h->any_alm) {
-            LAUNCH(h, k_cost<T>, grid2(B, N + 1), 128, h->D, B, 0, int(PH_BACKWARD));
-            LAUNCH(h, k_refresh_cost<T>, grid1(B), 128, h->D, B);
+            LAUNCH(h, k_cost<T>, gs2(B, N + 1), 128, h->D, B, 0);
+            LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
-        LAUNCH(h, k_derivs<T>, grid2(B, N + 1), 128, h->D, B, 1);
-        LAUNCH(h, k_backward<T>, grid1(B), 128, h->D, B, 1);
-        LAUNCH(h, k_forward<T>, grid1(B), 128, h->D, B, 1);
-        launch_cost(h, B, 1, int(PH_SEARCH));
-        LAUNCH(h, k_decide<T>, grid1(B), 128, h->D, B, r);
-        CK(cudaMemcpyAsync(&h->h_active[r], &h->D.active[r], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaEventRecord(h->ev[r % (kRunAhead + 1)], h->stream));
-        rounds = r + 1;
-        if (r >= kRunAhead) {
-            int q = r - kRunAhead;
-            CK(cudaEventSynchronize(h->ev[q % (kRunAhead + 1)]));
-            if (h->h_active[q] == 0) break;
-        }
+        LAUNCH(h, k_backward<T>, gs1(B), 128, h->D, B, 1);
+        LAUNCH(h, k_forward<T>, gs1(trial_cap), 128, h->D, B, 1);
+        launch_cost(h, B, 1);
+        LAUNCH(h, k_decide<T>, gs1(B), 128, h->D, B);
+        ++launched;
     }
-    LAUNCH(h, k_store_last_u<T>, grid2(B, N), 128, h->D, B);
+    LAUNCH(h, k_derivs<T>, gs2(B, N + 1), 128, h->D, B, 1);  // commit a step accepted in the last round
+    LAUNCH(h, k_store_last_u<T>, gs2(B, N), 128, h->D, B);
     CK(cudaGetLastError());
-    h->counters.rounds = rounds;
+    CK(cudaStreamSynchronize(h->stream));
+    int ctl[CTL_WORDS];
+    CK(cudaMemcpy(ctl, h->D.ctl, sizeof ctl, cudaMemcpyDeviceToHost));
+    h->counters.rounds = ctl[CTL_ROUND];
+    h->counters.total_trials = ctl[CTL_TRIALS];
     h->counters.launches = h->launches;
     return 0;
 }
@@ -504,13 +524,12 @@ int do_download(Impl<T>* h, int B, double* u_out, double* x_out, double* J_out, 
                 double* step_cost_out, int32_t* status_out, int32_t* iters_out, int32_t* exit_out) {
     CK(cudaSetDevice(h->device));
     const int N = h->N;
-    const size_t Bs = h->Bs;
     int rc;
-    if ((rc = unpack_to_host(h, h->D.U, u_out, B, N * 2, h->D.cur, size_t(N) * 2 * Bs))) return rc;
-    if ((rc = unpack_to_host(h, h->D.X, x_out, B, (N + 1) * 4, h->D.cur, size_t(N + 1) * 4 * Bs))) return rc;
-    if ((rc = unpack_to_host(h, h->D.Kg, K_out, B, N * 8, nullptr, 0))) return rc;
-    if ((rc = unpack_to_host(h, h->D.dg, d_out, B, N * 2, nullptr, 0))) return rc;
-    if ((rc = unpack_to_host(h, h->D.sc, step_cost_out, B, N + 1, h->D.cur, size_t(N + 1) * Bs))) return rc;
+    if ((rc = unpack_to_host(h, h->D.U, u_out, B, N * 2))) return rc;
+    if ((rc = unpack_to_host(h, h->D.X, x_out, B, (N + 1) * 4))) return rc;
+    if ((rc = unpack_to_host(h, h->D.Kg, K_out, B, N * 8))) return rc;
+    if ((rc = unpack_to_host(h, h->D.dg, d_out, B, N * 2))) return rc;
+    if ((rc = unpack_to_host(h, h->D.sc, step_cost_out, B, N + 1))) return rc;
     if (J_out) {
         // J_init and J_cur are two [Bs] arrays; emit [B][2]
         std::vector<double> tmp(size_t(B) * 2);
@@ -553,9 +572,9 @@ int stage_init(Impl<T>* h, int B, const double* x0, const int32_t* tmpl, int war
     if (warm) {
         if ((rc = pack_to_device(h, last_u, h->D.last_u, B, 1, N * 2, N * 2, 1))) return rc;
     }
-    LAUNCH(h, k_init<T>, grid1(B), 128, h->D, B, warm ? 1 : 0, 0);
-    if ((rc = unpack_to_host(h, h->D.U, u_out, B, N * 2, nullptr, 0))) return rc;
-    if ((rc = unpack_to_host(h, h->D.X, x_out, B, (N + 1) * 4, nullptr, 0))) return rc;
+    LAUNCH(h, k_init<T>, gs1(B), 128, h->D, B, warm ? 1 : 0, 0);
+    if ((rc = unpack_to_host(h, h->D.U, u_out, B, N * 2))) return rc;
+    if ((rc = unpack_to_host(h, h->D.X, x_out, B, (N + 1) * 4))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -564,7 +583,6 @@ template <typename T>
 int load_traj(Impl<T>* h, int B, const double* u, const double* x) {
     int rc;
     const int N = h->N;
-    CK(cudaMemsetAsync(h->D.cur, 0, size_t(h->Bs) * sizeof(int), h->stream));
     if (u && (rc = pack_to_device(h, u, h->D.U, B, 1, N * 2, N * 2, 1))) return rc;
     if (x && (rc = pack_to_device(h, x, h->D.X, B, 1, (N + 1) * 4, (N + 1) * 4, 1))) return rc;
     return 0;
@@ -578,7 +596,7 @@ int stage_ref_match(Impl<T>* h, int B, const double* x, const int32_t* tmpl, int
     if ((rc = upload_ints(h, tmpl, h->D.tmpl, B, 0))) return rc;
     if ((rc = load_traj(h, B, nullptr, x))) return rc;
     constexpr int G = 8;
-    LAUNCH(h, k_ref_match<T, G>, dim3((B + 15) / 16), 128, h->D, B, 0, -1);
+    LAUNCH(h, k_ref_match<T, G>, gs1(B * G), 128, h->D, B, 0);
     // ridx is [N+1][Bs] ints: transpose on the host (test path only)
     const int N = h->N;
     std::vector<int> tmp(size_t(N + 1) * h->Bs);
@@ -608,10 +626,10 @@ int stage_cost(Impl<T>* h, int B, const double* u, const double* x, const double
     if ((rc = upload_problem_data(h, B, ref_velo, borders, tmpl, n_obs, obs, obs_len))) return rc;
     if ((rc = load_traj(h, B, u, x))) return rc;
     if ((rc = load_alm(h, B, alm_mu, alm_rho))) return rc;
-    launch_cost(h, B, 0, -1);
-    LAUNCH(h, k_sum_cost<T>, grid1(B), 128, h->D, B);
-    if ((rc = unpack_to_host(h, h->D.J_cur, J_out, B, 1, nullptr, 0))) return rc;
-    if ((rc = unpack_to_host(h, h->D.sc, step_cost_out, B, h->N + 1, nullptr, 0))) return rc;
+    launch_cost(h, B, 0);
+    LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 0);
+    if ((rc = unpack_to_host(h, h->D.J_cur, J_out, B, 1))) return rc;
+    if ((rc = unpack_to_host(h, h->D.sc, step_cost_out, B, h->N + 1))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -629,8 +647,8 @@ int stage_derivs(Impl<T>* h, int B, const double* u, const double* x, const doub
     if ((rc = load_traj(h, B, u, x))) return rc;
     if ((rc = load_alm(h, B, alm_mu, alm_rho))) return rc;
     constexpr int G = 8;
-    LAUNCH(h, k_ref_match<T, G>, dim3((B + 15) / 16), 128, h->D, B, 0, -1);
-    LAUNCH(h, k_derivs<T>, grid2(B, N + 1), 128, h->D, B, 0);
+    LAUNCH(h, k_ref_match<T, G>, gs1(B * G), 128, h->D, B, 0);
+    LAUNCH(h, k_derivs<T>, gs2(B, N + 1), 128, h->D, B, 0);
     // dense conversion on device into a temporary allocation (test path; not part of create-time budget)
     size_t n_lx = size_t(B) * (N + 1) * 4, n_lu = size_t(B) * N * 2, n_lxx = size_t(B) * (N + 1) * 16,
            n_luu = size_t(B) * N * 4, n_A = size_t(B) * N * 16, n_B = size_t(B) * N * 8;
@@ -654,7 +672,7 @@ int stage_derivs(Impl<T>* h, int B, const double* u, const double* x, const doub
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(CILQR_ERR_CUDA, "stage_derivs download: %s", cudaGetErrorString(e));
     if (h->any_alm && alm_mu_next) {
-        if ((rc = unpack_to_host(h, h->D.mu_next, alm_mu_next, B, N * h->D.alm_cols, nullptr, 0))) return rc;
+        if ((rc = unpack_to_host(h, h->D.mu_next, alm_mu_next, B, N * h->D.alm_cols))) return rc;
         CK(cudaStreamSynchronize(h->stream));
     }
     return 0;
@@ -693,13 +711,13 @@ int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const 
         cudaFree(tmp);
         return rc;
     }
-    LAUNCH(h, k_backward<T>, grid1(B), 128, h->D, B, 0);
+    LAUNCH(h, k_backward<T>, gs1(B), 128, h->D, B, 0);
     e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(CILQR_ERR_CUDA, "stage_backward: %s", cudaGetErrorString(e));
-    if ((rc = unpack_to_host(h, h->D.dg, d_out, B, N * 2, nullptr, 0))) return rc;
-    if ((rc = unpack_to_host(h, h->D.Kg, K_out, B, N * 8, nullptr, 0))) return rc;
-    if ((rc = unpack_to_host(h, h->D.dV, dV_out, B, 2, nullptr, 0))) return rc;
+    if ((rc = unpack_to_host(h, h->D.dg, d_out, B, N * 2))) return rc;
+    if ((rc = unpack_to_host(h, h->D.Kg, K_out, B, N * 8))) return rc;
+    if ((rc = unpack_to_host(h, h->D.dV, dV_out, B, 2))) return rc;
     if ((rc = download_ints(h, h->D.status, status_out, B))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -716,9 +734,9 @@ int stage_forward(Impl<T>* h, int B, const double* u, const double* x, const dou
     if ((rc = pack_to_device(h, d, h->D.dg, B, 1, N * 2, N * 2, 1))) return rc;
     if ((rc = pack_to_device(h, K, h->D.Kg, B, 1, N * 8, N * 8, 1))) return rc;
     if ((rc = pack_to_device(h, alpha, h->D.alpha, B, 1, 1, 1, 1))) return rc;
-    LAUNCH(h, k_forward<T>, grid1(B), 128, h->D, B, 0);
-    if ((rc = unpack_to_host(h, h->D.U + size_t(N) * 2 * h->Bs, new_u, B, N * 2, nullptr, 0))) return rc;
-    if ((rc = unpack_to_host(h, h->D.X + size_t(N + 1) * 4 * h->Bs, new_x, B, (N + 1) * 4, nullptr, 0))) return rc;
+    LAUNCH(h, k_forward<T>, gs1(B), 128, h->D, B, 0);
+    if ((rc = unpack_to_host(h, h->D.Ut, new_u, B, N * 2, size_t(h->D.Vs)))) return rc;
+    if ((rc = unpack_to_host(h, h->D.Xt, new_x, B, (N + 1) * 4, size_t(h->D.Vs)))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -740,7 +758,7 @@ int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float
             k_flush_l2<<<148 * 8, 256, 0, h->stream>>>(h->flush, h->flush_n);
         }
         CK(cudaEventRecord(h->t0, h->stream));
-        LAUNCH(h, k_backward<T>, grid1(B), 128, h->D, B, 0);
+        LAUNCH(h, k_backward<T>, gs1(B), 128, h->D, B, 0);
         CK(cudaEventRecord(h->t1, h->stream));
         CK(cudaEventSynchronize(h->t1));
         float ms = 0;
@@ -817,13 +835,60 @@ int do_set_template(Impl<T>* h, int t, const cilqr_params_t* params, const doubl
 }
 
 template <typename T>
+int do_set_option(Impl<T>* h, int option, int value) {
+    switch (option) {
+        case CILQR_OPT_WIDE_SEARCH:
+            h->D.wide_mode = value ? 1 : 0;
+            return 0;
+        case CILQR_OPT_RUN_AHEAD:
+            if (value < 0 || value > 64) return fail(CILQR_ERR_INVALID, "run-ahead must be in [0, 64]");
+            h->run_ahead = value;
+            return 0;
+        default:
+            return fail(CILQR_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
+template <typename T>
+int do_enable_trace(Impl<T>* h, int cap) {
+    CK(cudaSetDevice(h->device));
+    if (cap < 0 || cap > 100000) return fail(CILQR_ERR_INVALID, "trace capacity out of range");
+    if (cap > 0 && cap != h->D.trace_cap) {
+        int rc;
+        if ((rc = dalloc(h, &h->D.tr_status, size_t(cap) * h->Bs))) return rc;
+        if ((rc = dalloc(h, &h->D.tr_alpha, size_t(cap) * h->Bs))) return rc;
+        if ((rc = dalloc(h, &h->D.tr_cost, size_t(cap) * h->Bs))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->D.trace_cap = cap;
+    return 0;
+}
+
+template <typename T>
+int do_get_trace(Impl<T>* h, int B, int32_t* status, int32_t* alpha, double* cost) {
+    CK(cudaSetDevice(h->device));
+    const int cap = h->D.trace_cap;
+    if (cap <= 0) return fail(CILQR_ERR_INVALID, "trace is not enabled");
+    std::vector<int> a(size_t(cap) * h->Bs), c(size_t(cap) * h->Bs);
+    CK(cudaMemcpyAsync(a.data(), h->D.tr_status, a.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(c.data(), h->D.tr_alpha, c.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int rc;
+    if ((rc = unpack_to_host(h, h->D.tr_cost, cost, B, cap))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < cap; ++i) {
+            if (status) status[size_t(b) * cap + i] = a[size_t(i) * h->Bs + b];
+            if (alpha) alpha[size_t(b) * cap + i] = c[size_t(i) * h->Bs + b];
+        }
+    return 0;
+}
+
+template <typename T>
 int do_destroy(Impl<T>* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->h_active) cudaFreeHost(h->h_active);
-    for (auto& e : h->ev)
-        if (e) cudaEventDestroy(e);
+    if (h->h_ctl) cudaFreeHost(const_cast<int*>(h->h_ctl));
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -936,6 +1001,23 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out) {
     if (!h || !out) return fail(CILQR_ERR_INVALID, "NULL argument");
     *out = base(h)->counters;
     return 0;
+}
+
+int cilqr_b200_set_option(cilqr_handle_t* h, int option, int value) {
+    if (!h) return fail(CILQR_ERR_INVALID, "handle is NULL");
+    return DISPATCH(h, do_set_option, option, value);
+}
+
+int cilqr_b200_enable_trace(cilqr_handle_t* h, int cap) {
+    if (!h) return fail(CILQR_ERR_INVALID, "handle is NULL");
+    return DISPATCH(h, do_enable_trace, cap);
+}
+
+int cilqr_b200_get_trace(cilqr_handle_t* h, int B, int32_t* status, int32_t* alpha, double* cost) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    return DISPATCH(h, do_get_trace, B, status, alpha, cost);
 }
 
 int cilqr_b200_stage_init(cilqr_handle_t* h, int B, const double* x0, const int32_t* tmpl, int warm,

@@ -1,17 +1,28 @@
 // Batched CILQR kernels for sm_100a.
 //
 // Memory layout ("step-major SoA"): every per-trajectory array is stored as
-// [step][field][batch] with the batch index innermost and a batch stride Bs
-// (multiple of 128).  Consecutive lanes of a warp own consecutive
-// trajectories, so every global access below is a fully coalesced 128-byte
-// (fp32) or 256-byte (fp64) row, whichever stage is running:
+// [step][field][batch] with the batch index innermost and a batch stride that is
+// a multiple of 128.  Consecutive lanes of a warp own consecutive trajectories,
+// so every global access below is a fully coalesced 128-byte (fp32) or 256-byte
+// (fp64) row, whichever stage is running:
 //   * step-parallel stages (cost, derivatives): one thread per (trajectory, step);
-//   * serial chains (rollouts, Riccati recursion): one thread per trajectory,
-//     the 4x4 / 4x2 / 2x2 blocks held in registers, A and B in their sparse
-//     form (5 + 4 non-trivial entries), V_xx / l_xx symmetric (10 entries);
+//   * serial chains (rollouts, Riccati recursion): one thread per trajectory, the
+//     4x4 / 4x2 / 2x2 blocks held in registers, A and B in their sparse form
+//     (5 + 4 non-trivial entries), V_xx / l_xx symmetric (10 entries);
 //   * waypoint matching: G lanes per trajectory scan a G-wide window of the
 //     reference line per probe and pick the first local minimum by ballot.
 // No tensor cores: the largest contraction is 4x4x4.
+//
+// Line search as a trial pool.  The reference tries alpha = 1, 1/2, ... one after
+// the other and keeps the first that passes (cpp:354-372).  Here every searching
+// instance claims `count` consecutive slots of a trial pool per round — one slot
+// normally, all remaining alphas while it is in a streak of rejected steps — the
+// pool is rolled out / matched / costed in bulk, and the verdict kernel walks the
+// instance's slots in alpha order and takes the first that passes: same decision,
+// up to 20x fewer dependent rounds for the stragglers.
+//
+// All kernels are grid-stride over device-side counts, so one launch shape serves
+// every round (grids are sized in multiples of the 148 SMs by the host).
 #pragma once
 
 #include "cilqr_model.cuh"
@@ -25,36 +36,48 @@ constexpr int kRecLu = 14;      // l_u   [2]
 constexpr int kRecLuu = 16;     // l_uu  sym: 00 01 11
 constexpr int kRecA = 19;       // A     a02 a03 a12 a13 a32
 constexpr int kRecB = 24;       // B     b01 b11 b20 b31
-constexpr int kRecTerminal = 14;  // the terminal record holds l_x and l_xx only
 
 constexpr int kNumAlphas = 20;  // alpha = 2^0 .. 2^-19  (cpp:354)
 
 enum Phase : int { PH_BACKWARD = 0, PH_SEARCH = 1, PH_DONE = 2 };
 enum Status : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BWD_FAIL = 2, ST_FWD_FAIL = 3, ST_SMALL_STEP = 4 };
 enum ExitReason : int { EX_MAX_ITER = 0, EX_CONVERGED = 1, EX_MAX_LAMB = 2 };
+// device-side loop control words
+enum Ctl : int { CTL_NV = 0, CTL_ACTIVE = 1, CTL_TICKET = 2, CTL_ROUND = 3, CTL_TRIALS = 4, CTL_WORDS = 8 };
 
 // Everything a kernel needs, passed by value.
 template <typename T>
 struct Dev {
-    int N, Bs, max_obs, alm_cols;
+    int N, Bs, Vs, max_obs, alm_cols;
+    int wide_mode;     // 0: one alpha per round; 1: adaptive (all remaining alphas while in a rejection streak)
+    int trace_cap;     // iterations recorded per instance (0 = off)
     const DevParams<T>* P;  // [CILQR_B200_MAX_TEMPLATES]
     const T* wx;
     const T* wy;
     const T* wyaw;
-    // problem data
+    // problem data, stride Bs
     T* ref_velo;  // [Bs]
     T* borders;   // [2][Bs]
     int* tmpl;    // [Bs]
     int* n_obs;   // [Bs]
     T* obs;       // [max_obs][N+1][3][Bs]
     T* x0;        // [4][Bs]
-    // trajectories and what is derived from them, ping-pong pairs selected by cur[b]
-    T* X;       // [2][N+1][4][Bs]
-    T* U;       // [2][N][2][Bs]
-    int* ridx;  // [2][N+1][Bs]   matched waypoint per step
-    T* sc;      // [2][N+1][Bs]   per-step cost
-    int* cur;   // [Bs]
-    // derivative records and gains
+    // current trajectory of every instance, stride Bs
+    T* X;       // [N+1][4][Bs]
+    T* U;       // [N][2][Bs]
+    int* ridx;  // [N+1][Bs]   matched waypoint per step
+    T* sc;      // [N+1][Bs]   per-step cost
+    // trial pool, stride Vs
+    T* Xt;
+    T* Ut;
+    int* ridx_t;
+    T* sc_t;
+    int* t_inst;  // [Vs] owning instance
+    int* t_aidx;  // [Vs] alpha index
+    int* t_first;     // [Bs] first slot claimed this round
+    int* t_count;     // [Bs] slots claimed this round
+    int* commit_src;  // [Bs] trial slot to copy into the current trajectory, -1 = none
+    // derivative records and gains, stride Bs
     T* rec;  // [N+1][28][Bs]
     T* Kg;   // [N][8][Bs]
     T* dg;   // [N][2][Bs]
@@ -70,25 +93,52 @@ struct Dev {
     int* iters;
     int* exit_reason;
     int* rec_valid;
-    T* last_u;  // [N][2][Bs]
-    int* first; // [Bs]
+    int* wide;
+    T* last_u;   // [N][2][Bs]
+    int* first;  // [Bs]
     // augmented-Lagrangian state (allocated only when a template asks for it)
     T* mu;       // [N][alm_cols][Bs]
     T* mu_next;  // [N][alm_cols][Bs]
     T* rho;      // [Bs]
-    int* active; // [max_rounds] instances still running after each round
+    // loop control
+    int* ctl;             // [CTL_WORDS]
+    volatile int* h_ctl;  // mapped pinned host words: [0] rounds completed, [1] active after that round
+    // optional per-iteration trace, [trace_cap][Bs]
+    int* tr_status;
+    int* tr_alpha;
+    T* tr_cost;
 };
 
+// A set of trajectories: either the instances' current ones or the trial pool.
 template <typename T>
-__device__ __forceinline__ size_t at(const Dev<T>& D, int step, int field, int nfields, int b) {
-    return (size_t(step) * nfields + field) * D.Bs + b;
+struct View {
+    T* X;
+    T* U;
+    int* ridx;
+    T* sc;
+    size_t stride;
+    const int* inst;  // trial slot -> instance, nullptr for identity
+};
+template <typename T>
+__device__ __forceinline__ View<T> view_of(const Dev<T>& D, int trial) {
+    View<T> v;
+    if (trial) {
+        v.X = D.Xt; v.U = D.Ut; v.ridx = D.ridx_t; v.sc = D.sc_t; v.stride = size_t(D.Vs); v.inst = D.t_inst;
+    } else {
+        v.X = D.X; v.U = D.U; v.ridx = D.ridx; v.sc = D.sc; v.stride = size_t(D.Bs); v.inst = nullptr;
+    }
+    return v;
 }
 template <typename T>
-__device__ __forceinline__ size_t xbuf(const Dev<T>& D, int buf) { return size_t(buf) * (D.N + 1) * 4 * D.Bs; }
-template <typename T>
-__device__ __forceinline__ size_t ubuf(const Dev<T>& D, int buf) { return size_t(buf) * D.N * 2 * D.Bs; }
-template <typename T>
-__device__ __forceinline__ size_t sbuf(const Dev<T>& D, int buf) { return size_t(buf) * (D.N + 1) * D.Bs; }
+__device__ __forceinline__ int view_count(const Dev<T>& D, int trial, int B) {
+    if (!trial) return B;
+    int nv = D.ctl[CTL_NV];
+    return nv < D.Vs ? nv : D.Vs;
+}
+
+__device__ __forceinline__ size_t at(size_t stride, int step, int field, int nfields, int i) {
+    return (size_t(step) * nfields + field) * stride + i;
+}
 
 // ---------------------------------------------------------------------------
 // K0  initial trajectory: get_init_traj (cpp:155-161, :182-197) or the shifted
@@ -97,55 +147,56 @@ __device__ __forceinline__ size_t sbuf(const Dev<T>& D, int buf) { return size_t
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, int reset_state) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const DevParams<T>& P = D.P[D.tmpl[b]];
+    const size_t Bs = D.Bs;
     const int N = D.N;
-    bool warm = force_warm > 0 || (force_warm < 0 && P.use_last && !D.first[b]);
-    T* X = D.X;  // buffer 0
-    T* U = D.U;
-    T x[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        x[c] = D.x0[size_t(c) * D.Bs + b];
-        X[at(D, 0, c, 4, b)] = x[c];
-    }
-    for (int i = 0; i < N; ++i) {
-        T a = 0, s = 0;
-        if (warm) {
-            int src = (i + 1 < N) ? i + 1 : N - 1;
-            a = D.last_u[at(D, src, 0, 2, b)];
-            s = D.last_u[at(D, src, 1, 2, b)];
-        }
-        U[at(D, i, 0, 2, b)] = a;
-        U[at(D, i, 1, 2, b)] = s;
-        T nx[4];
-        propagate(x, a, s, P.dt, P.wheelbase, P.ref_point, nx);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const DevParams<T>& P = D.P[D.tmpl[b]];
+        bool warm = force_warm > 0 || (force_warm < 0 && P.use_last && !D.first[b]);
+        T x[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            x[c] = nx[c];
-            X[at(D, i + 1, c, 4, b)] = nx[c];
+            x[c] = D.x0[size_t(c) * Bs + b];
+            D.X[at(Bs, 0, c, 4, b)] = x[c];
         }
-    }
-    D.cur[b] = 0;
-    if (reset_state) {
-        if (P.solve_type == 1 && D.mu && (!P.use_last || D.first[b])) {  // cpp:88-93
-            D.rho[b] = P.alm_rho_init;
-            for (int i = 0; i < N * D.alm_cols; ++i) {
-                D.mu[size_t(i) * D.Bs + b] = 0;
-                D.mu_next[size_t(i) * D.Bs + b] = 0;
+        for (int i = 0; i < N; ++i) {
+            T a = 0, s = 0;
+            if (warm) {
+                int src = (i + 1 < N) ? i + 1 : N - 1;
+                a = D.last_u[at(Bs, src, 0, 2, b)];
+                s = D.last_u[at(Bs, src, 1, 2, b)];
+            }
+            D.U[at(Bs, i, 0, 2, b)] = a;
+            D.U[at(Bs, i, 1, 2, b)] = s;
+            T nx[4];
+            propagate(x, a, s, P.dt, P.wheelbase, P.ref_point, nx);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                x[c] = nx[c];
+                D.X[at(Bs, i + 1, c, 4, b)] = nx[c];
             }
         }
-        D.first[b] = 0;
-        D.status[b] = ST_RUNNING;
-        D.lamb[b] = P.init_lamb;
-        D.iters[b] = 0;
-        D.phase[b] = PH_BACKWARD;
-        D.aidx[b] = 0;
-        D.rec_valid[b] = 0;
-        D.exit_reason[b] = EX_MAX_ITER;
-        D.dV[b] = 0;
-        D.dV[D.Bs + b] = 0;
+        if (reset_state) {
+            if (P.solve_type == 1 && D.mu && (!P.use_last || D.first[b])) {  // cpp:88-93
+                D.rho[b] = P.alm_rho_init;
+                for (int i = 0; i < N * D.alm_cols; ++i) {
+                    D.mu[size_t(i) * Bs + b] = 0;
+                    D.mu_next[size_t(i) * Bs + b] = 0;
+                }
+            }
+            D.first[b] = 0;
+            D.status[b] = ST_RUNNING;
+            D.lamb[b] = P.init_lamb;
+            D.iters[b] = 0;
+            D.phase[b] = P.max_iter > 0 ? PH_BACKWARD : PH_DONE;
+            D.aidx[b] = 0;
+            D.rec_valid[b] = 0;
+            D.wide[b] = 0;
+            D.exit_reason[b] = EX_MAX_ITER;
+            D.commit_src[b] = -1;
+            D.t_count[b] = 0;
+            D.dV[b] = 0;
+            D.dV[Bs + b] = 0;
+        }
     }
 }
 
@@ -156,58 +207,59 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
 //     Equivalent formulation used here: first j >= start with
 //     !(dist[j+1] < dist[j]) (NaN stops the scan, as in the reference).
 //     G lanes per trajectory evaluate a window of G waypoints per probe.
-//     `which` = 0: the current trajectory, 1: the line-search trial.
 // ---------------------------------------------------------------------------
 template <typename T, int G>
-__global__ void __launch_bounds__(128) k_ref_match(Dev<T> D, int B, int which, int need_phase) {
+__global__ void __launch_bounds__(128) k_ref_match(Dev<T> D, int B, int trial) {
+    const View<T> V = view_of(D, trial);
+    const int count = view_count(D, trial, B);
     const int lane = threadIdx.x & 31;
     const int sub = lane % G;
     const int grp_shift = lane - sub;  // first lane of my group inside the warp
-    int b = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    bool live = b < B;
-    if (live && need_phase >= 0) live = D.phase[b] == need_phase;
-    int bb = b < B ? b : B - 1;  // keep addresses valid for idle groups
-    const DevParams<T>& P = D.P[D.tmpl[bb]];
-    const int M = P.wp_len;
-    const T* wx = D.wx + P.wp_off;
-    const T* wy = D.wy + P.wp_off;
-    const int buf = which ? 1 - D.cur[bb] : D.cur[bb];
-    const T* X = D.X + xbuf(D, buf);
-    int* R = D.ridx + sbuf(D, buf);
     const unsigned grp_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << grp_shift);
-    int start = 0;
-    for (int k = 0; k <= D.N; ++k) {
-        T px = X[at(D, k, 0, 4, bb)];
-        T py = X[at(D, k, 1, 4, bb)];
-        int found = -1;
-        bool done = !live;
-        // all groups of the warp iterate together; finished groups idle
-        while (!__all_sync(0xffffffffu, done)) {
-            int j = start + sub;
-            int jc = j < M ? j : M - 1;
-            T dj = m_hypot(px - wx[jc], py - wy[jc]);
-            T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
-            bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
-            unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
-            if (!done) {
-                if (m) {
-                    found = start + (__ffs(m) - 1 - grp_shift);
-                    done = true;
-                } else {
-                    start += G - 1;
+    const int groups_per_warp = 32 / G;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * groups_per_warp; base < count; base += n_warps * groups_per_warp) {
+        const int v = base + lane / G;
+        const bool live = v < count;
+        const int vv = live ? v : count - 1;  // keep addresses valid for idle groups
+        const int b = V.inst ? V.inst[vv] : vv;
+        const DevParams<T>& P = D.P[D.tmpl[b]];
+        const int M = P.wp_len;
+        const T* wx = D.wx + P.wp_off;
+        const T* wy = D.wy + P.wp_off;
+        int start = 0;
+        for (int k = 0; k <= D.N; ++k) {
+            const T px = V.X[at(V.stride, k, 0, 4, vv)];
+            const T py = V.X[at(V.stride, k, 1, 4, vv)];
+            int found = -1;
+            bool done = !live;
+            // all groups of the warp iterate together; finished groups idle
+            while (!__all_sync(0xffffffffu, done)) {
+                int j = start + sub;
+                int jc = j < M ? j : M - 1;
+                T dj = m_hypot(px - wx[jc], py - wy[jc]);
+                T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
+                bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
+                unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
+                if (!done) {
+                    if (m) {
+                        found = start + (__ffs(m) - 1 - grp_shift);
+                        done = true;
+                    } else {
+                        start += G - 1;
+                    }
                 }
             }
-        }
-        if (live) {
-            if (found > M - 1) found = M - 1;
-            if (sub == 0) R[size_t(k) * D.Bs + b] = found;
-            start = found;
+            if (live) {
+                if (sub == 0) V.ridx[size_t(k) * V.stride + v] = found;
+                start = found;
+            }
         }
     }
 }
 
-// The eight box constraints of one step in the reference's order
-// (cpp:222-241): acc up/lo, steer up/lo, velocity up/lo, lateral up/lo.
+// acc up/lo, steer up/lo in the reference's order (cpp:222-228)
 template <typename T>
 __device__ __forceinline__ void ctrl_constraints(const DevParams<T>& P, T acc, T steer, T c[4]) {
     c[0] = acc - P.acc_max;
@@ -222,89 +274,91 @@ __device__ __forceinline__ void ctrl_constraints(const DevParams<T>& P, T acc, T
 //     step k (k >= 1: u_{k-1}, x_k, ref_k, obstacles at tick k).
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) k_cost(Dev<T> D, int B, int which, int need_phase) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y;
-    if (b >= B) return;
-    if (need_phase >= 0 && D.phase[b] != need_phase) return;
-    const DevParams<T>& P = D.P[D.tmpl[b]];
+__global__ void __launch_bounds__(128) k_cost(Dev<T> D, int B, int trial) {
+    const View<T> V = view_of(D, trial);
+    const int count = view_count(D, trial, B);
     const int N = D.N;
-    const int buf = which ? 1 - D.cur[b] : D.cur[b];
-    const T* X = D.X + xbuf(D, buf);
-    const T* U = D.U + ubuf(D, buf);
-    const int ri = D.ridx[sbuf(D, buf) + size_t(k) * D.Bs + b];
-    T x[4];
+    const size_t Bs = D.Bs;
+    const int k = blockIdx.y;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += gridDim.x * blockDim.x) {
+        const int b = V.inst ? V.inst[v] : v;
+        const DevParams<T>& P = D.P[D.tmpl[b]];
+        const int ri = V.ridx[size_t(k) * V.stride + v];
+        T x[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) x[c] = X[at(D, k, c, 4, b)];
-    const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
-    const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
-    T cost = 0;
+        for (int c = 0; c < 4; ++c) x[c] = V.X[at(V.stride, k, c, 4, v)];
+        const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
+        const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
+        T cost = 0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        T e = x[c] - ref[c];
-        cost += e * P.Q[c] * e;
-    }
-    if (k < N) {
-        T a = U[at(D, k, 0, 2, b)], s = U[at(D, k, 1, 2, b)];
-        T ce = a * P.R[0] * a;
-        ce += s * P.R[1] * s;
-        cost += ce;
-    }
-    if (k >= 1) {
-        T a = U[at(D, k - 1, 0, 2, b)], s = U[at(D, k - 1, 1, 2, b)];
-        T c[8];
-        ctrl_constraints(P, a, s, c);
-        c[4] = x[2] - P.velo_max;
-        c[5] = P.velo_min - x[2];
-        T d_sign, hyp;
-        T cur_d = lateral_offset(x[0], x[1], rx, ry, ryaw, &d_sign, &hyp);
-        c[6] = cur_d - (D.borders[b] - P.width / 2);
-        c[7] = (D.borders[D.Bs + b] + P.width / 2) - cur_d;
-        T Jk = 0;
-        const bool alm = P.solve_type == 1;
-        const T rho = alm ? D.rho[b] : T(0);
-        const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * D.Bs + b : nullptr;
-        if (!alm) {
-#pragma unroll
-            for (int m = 0; m < 8; ++m) Jk += exp_barrier(c[m], P.st_q1, P.st_q2);
-        } else {
-#pragma unroll
-            for (int m = 0; m < 8; ++m) Jk += alm_item(c[m], rho, mu[size_t(m) * D.Bs]);
+        for (int c = 0; c < 4; ++c) {
+            T e = x[c] - ref[c];
+            cost += e * P.Q[c] * e;
         }
-        const int no = D.n_obs[b];
-        if (no > 0) {
-            EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
-            for (int j = 0; j < no; ++j) {
-                const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 3 * D.Bs + b;
-                T ox = ob[0], oy = ob[D.Bs], oyaw = ob[2 * size_t(D.Bs)];
-                T so, co;
-                m_sincos(oyaw, &so, &co);
-                T cf = ellipse_margin<T, false>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
-                T cr = ellipse_margin<T, false>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
-                if (!alm) {
-                    Jk += exp_barrier(cf, P.obs_q1, P.obs_q2);
-                    Jk += exp_barrier(cr, P.obs_q1, P.obs_q2);
-                } else {
-                    Jk += alm_item(cf, rho, mu[size_t(8 + 2 * j) * D.Bs]);
-                    Jk += alm_item(cr, rho, mu[size_t(9 + 2 * j) * D.Bs]);
+        if (k < N) {
+            T a = V.U[at(V.stride, k, 0, 2, v)], s = V.U[at(V.stride, k, 1, 2, v)];
+            T ce = a * P.R[0] * a;
+            ce += s * P.R[1] * s;
+            cost += ce;
+        }
+        if (k >= 1) {
+            T a = V.U[at(V.stride, k - 1, 0, 2, v)], s = V.U[at(V.stride, k - 1, 1, 2, v)];
+            T c[8];
+            ctrl_constraints(P, a, s, c);
+            c[4] = x[2] - P.velo_max;
+            c[5] = P.velo_min - x[2];
+            T d_sign, hyp;
+            T cur_d = lateral_offset(x[0], x[1], rx, ry, ryaw, &d_sign, &hyp);
+            c[6] = cur_d - (D.borders[b] - P.width / 2);
+            c[7] = (D.borders[Bs + b] + P.width / 2) - cur_d;
+            T Jk = 0;
+            const bool alm = P.solve_type == 1;
+            const T rho = alm ? D.rho[b] : T(0);
+            const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+            if (!alm) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) Jk += exp_barrier(c[m], P.st_q1, P.st_q2);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) Jk += alm_item(c[m], rho, mu[size_t(m) * Bs]);
+            }
+            const int no = D.n_obs[b];
+            if (no > 0) {
+                EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
+                for (int j = 0; j < no; ++j) {
+                    const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 3 * Bs + b;
+                    T ox = ob[0], oy = ob[Bs], oyaw = ob[2 * Bs];
+                    T so, co;
+                    m_sincos(oyaw, &so, &co);
+                    T cf = ellipse_margin<T, false>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
+                    T cr = ellipse_margin<T, false>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
+                    if (!alm) {
+                        Jk += exp_barrier(cf, P.obs_q1, P.obs_q2);
+                        Jk += exp_barrier(cr, P.obs_q1, P.obs_q2);
+                    } else {
+                        Jk += alm_item(cf, rho, mu[size_t(8 + 2 * j) * Bs]);
+                        Jk += alm_item(cr, rho, mu[size_t(9 + 2 * j) * Bs]);
+                    }
                 }
             }
+            cost += Jk;
         }
-        cost += Jk;
+        V.sc[size_t(k) * V.stride + v] = cost;
     }
-    D.sc[sbuf(D, buf) + size_t(k) * D.Bs + b] = cost;
 }
 
-// J = sum of the step costs of the current trajectory (used once after init).
+// J = sum of the step costs of the current trajectory.  mode 0: every instance,
+// sets J_cur and J_init (after the initial rollout); mode 1: instances whose
+// multipliers just changed (ALM, cpp:342 recomputes ori_cost every iter_step).
 template <typename T>
-__global__ void __launch_bounds__(128) k_sum_cost(Dev<T> D, int B) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const T* sc = D.sc + sbuf(D, D.cur[b]);
-    T J = 0;
-    for (int k = 0; k <= D.N; ++k) J += sc[size_t(k) * D.Bs + b];
-    D.J_cur[b] = J;
-    D.J_init[b] = J;
+__global__ void __launch_bounds__(128) k_sum_cost(Dev<T> D, int B, int mode) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        if (mode == 1 && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) continue;
+        T J = 0;
+        for (int k = 0; k <= D.N; ++k) J += D.sc[size_t(k) * D.Bs + b];
+        D.J_cur[b] = J;
+        if (mode == 0) D.J_init[b] = J;
+    }
 }
 
 // One constraint's gradient / Gauss-Newton Hessian weight: returns (g, h) with
@@ -327,156 +381,182 @@ __device__ __forceinline__ void constraint_weights(bool alm, T c, T q1, T q2, T 
 // ---------------------------------------------------------------------------
 // K3 + K4  get_total_cost_derivatives_and_Hessians (cpp:463-690) and
 //     get_kinematic_model_derivatives (src/utils.cpp:285-342), one thread per
-//     (trajectory, step k), writing the compact record of step k:
+//     (instance, step k), writing the compact record of step k:
 //     l_x[k], l_xx[k] (constraints of x_k if k >= 1), and for k < N
 //     l_u[k], l_uu[k] (constraints of u_k, i.e. the reference's step k+1), A_k, B_k.
+//     In the solver (masked != 0) the same thread first commits an accepted
+//     trial into the current trajectory ("x = new_x; u = new_u", cpp:113-116),
+//     then differentiates only where the record is stale — the reference's
+//     cache rule for rejected steps (cpp:469-474).
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y;
-    if (b >= B) return;
-    if (masked && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) return;
-    const DevParams<T>& P = D.P[D.tmpl[b]];
     const int N = D.N;
-    const int buf = D.cur[b];
-    const T* X = D.X + xbuf(D, buf);
-    const T* U = D.U + ubuf(D, buf);
-    const int ri = D.ridx[sbuf(D, buf) + size_t(k) * D.Bs + b];
-    const bool alm = P.solve_type == 1;
-    const T rho = alm ? D.rho[b] : T(0);
-    T x[4];
+    const size_t Bs = D.Bs, Vs = D.Vs;
+    const int k = blockIdx.y;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        T x[4], ua = 0, us = 0;
+        int ri;
+        const int src = masked ? D.commit_src[b] : -1;
+        if (src >= 0) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) x[c] = X[at(D, k, c, 4, b)];
-    const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
-    const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
+            for (int c = 0; c < 4; ++c) {
+                x[c] = D.Xt[at(Vs, k, c, 4, src)];
+                D.X[at(Bs, k, c, 4, b)] = x[c];
+            }
+            if (k < N) {
+                ua = D.Ut[at(Vs, k, 0, 2, src)];
+                us = D.Ut[at(Vs, k, 1, 2, src)];
+                D.U[at(Bs, k, 0, 2, b)] = ua;
+                D.U[at(Bs, k, 1, 2, b)] = us;
+            }
+            ri = D.ridx_t[size_t(k) * Vs + src];
+            D.ridx[size_t(k) * Bs + b] = ri;
+            D.sc[size_t(k) * Bs + b] = D.sc_t[size_t(k) * Vs + src];
+        }
+        if (masked && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) continue;
+        if (src < 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) x[c] = D.X[at(Bs, k, c, 4, b)];
+            if (k < N) {
+                ua = D.U[at(Bs, k, 0, 2, b)];
+                us = D.U[at(Bs, k, 1, 2, b)];
+            }
+            ri = D.ridx[size_t(k) * Bs + b];
+        }
+        const DevParams<T>& P = D.P[D.tmpl[b]];
+        const bool alm = P.solve_type == 1;
+        const T rho = alm ? D.rho[b] : T(0);
+        const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
+        const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
 
-    T gx[4] = {0, 0, 0, 0};
-    T H[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
-    if (k >= 1) {
-        const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * D.Bs + b : nullptr;
-        T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * D.Bs + b : nullptr;
-        // velocity bounds: c_dot = (0,0,+-1,0)
-        T cv[2] = {x[2] - P.velo_max, P.velo_min - x[2]};
-        T g, h;
-        constraint_weights(alm, cv[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4) * D.Bs] : T(0), &g, &h);
-        gx[2] += g;
-        H[7] += h;
-        constraint_weights(alm, cv[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(5) * D.Bs] : T(0), &g, &h);
-        gx[2] += -g;
-        H[7] += h;
-        // road borders: c_dot = +-(px-rx, py-ry)/hypot, flipped when d_sign < 0 (cpp:527-533)
-        T d_sign, hyp;
-        T cur_d = lateral_offset(x[0], x[1], rx, ry, ryaw, &d_sign, &hyp);
-        T cp[2] = {cur_d - (D.borders[b] - P.width / 2), (D.borders[D.Bs + b] + P.width / 2) - cur_d};
-        T n0 = (x[0] - rx) / hyp, n1 = (x[1] - ry) / hyp;
-        if (d_sign < 0) {
-            n0 = -n0;
-            n1 = -n1;
-        }
-        constraint_weights(alm, cp[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(6) * D.Bs] : T(0), &g, &h);
-        gx[0] += g * n0;
-        gx[1] += g * n1;
-        H[0] += h * (n0 * n0);
-        H[1] += h * (n0 * n1);
-        H[4] += h * (n1 * n1);
-        constraint_weights(alm, cp[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(7) * D.Bs] : T(0), &g, &h);
-        gx[0] += g * (-n0);
-        gx[1] += g * (-n1);
-        H[0] += h * (n0 * n0);
-        H[1] += h * (n0 * n1);
-        H[4] += h * (n1 * n1);
-        if (alm) {
-            mun[size_t(4) * D.Bs] = std_min(std_max(mu[size_t(4) * D.Bs] + rho * cv[0], T(0)), P.max_mu);
-            mun[size_t(5) * D.Bs] = std_min(std_max(mu[size_t(5) * D.Bs] + rho * cv[1], T(0)), P.max_mu);
-            mun[size_t(6) * D.Bs] = std_min(std_max(mu[size_t(6) * D.Bs] + rho * cp[0], T(0)), P.max_mu);
-            mun[size_t(7) * D.Bs] = std_min(std_max(mu[size_t(7) * D.Bs] + rho * cp[1], T(0)), P.max_mu);
-        }
-        // obstacles: front and rear circle against each ellipse (cpp:648-664)
-        const int no = D.n_obs[b];
-        if (no > 0) {
-            EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
-            for (int j = 0; j < no; ++j) {
-                const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 3 * D.Bs + b;
-                T ox = ob[0], oy = ob[D.Bs], oyaw = ob[2 * size_t(D.Bs)];
-                T so, co;
-                m_sincos(oyaw, &so, &co);
-                T gfx, gfy, grx, gry;
-                T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
-                T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
-                // chain through the 4x2 centre Jacobians: (gx, gy, 0, yaw row)
-                T f3 = e.jf0 * gfx + e.jf1 * gfy;
-                T r3 = e.jr0 * grx + e.jr1 * gry;
-                T gf, hf, gr, hr;
-                constraint_weights(alm, cf, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(8 + 2 * j) * D.Bs] : T(0), &gf, &hf);
-                constraint_weights(alm, cr, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(9 + 2 * j) * D.Bs] : T(0), &gr, &hr);
-                // front + rear first, then into the row (cpp:662-664)
-                gx[0] += gf * gfx + gr * grx;
-                gx[1] += gf * gfy + gr * gry;
-                gx[3] += gf * f3 + gr * r3;
-                H[0] += hf * (gfx * gfx) + hr * (grx * grx);
-                H[1] += hf * (gfx * gfy) + hr * (grx * gry);
-                H[3] += hf * (gfx * f3) + hr * (grx * r3);
-                H[4] += hf * (gfy * gfy) + hr * (gry * gry);
-                H[6] += hf * (gfy * f3) + hr * (gry * r3);
-                H[9] += hf * (f3 * f3) + hr * (r3 * r3);
-                if (alm) {
-                    mun[size_t(8 + 2 * j) * D.Bs] =
-                        std_min(std_max(mu[size_t(8 + 2 * j) * D.Bs] + rho * cf, T(0)), P.max_mu);
-                    mun[size_t(9 + 2 * j) * D.Bs] =
-                        std_min(std_max(mu[size_t(9 + 2 * j) * D.Bs] + rho * cr, T(0)), P.max_mu);
+        T gx[4] = {0, 0, 0, 0};
+        T H[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
+        if (k >= 1) {
+            const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+            T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+            // velocity bounds: c_dot = (0,0,+-1,0)
+            T cv[2] = {x[2] - P.velo_max, P.velo_min - x[2]};
+            T g, h;
+            constraint_weights(alm, cv[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4) * Bs] : T(0), &g, &h);
+            gx[2] += g;
+            H[7] += h;
+            constraint_weights(alm, cv[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(5) * Bs] : T(0), &g, &h);
+            gx[2] += -g;
+            H[7] += h;
+            // road borders: c_dot = +-(px-rx, py-ry)/hypot, flipped when d_sign < 0 (cpp:527-533)
+            T d_sign, hyp;
+            T cur_d = lateral_offset(x[0], x[1], rx, ry, ryaw, &d_sign, &hyp);
+            T cp[2] = {cur_d - (D.borders[b] - P.width / 2), (D.borders[Bs + b] + P.width / 2) - cur_d};
+            T n0 = (x[0] - rx) / hyp, n1 = (x[1] - ry) / hyp;
+            if (d_sign < 0) {
+                n0 = -n0;
+                n1 = -n1;
+            }
+            constraint_weights(alm, cp[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(6) * Bs] : T(0), &g, &h);
+            gx[0] += g * n0;
+            gx[1] += g * n1;
+            H[0] += h * (n0 * n0);
+            H[1] += h * (n0 * n1);
+            H[4] += h * (n1 * n1);
+            constraint_weights(alm, cp[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(7) * Bs] : T(0), &g, &h);
+            gx[0] += g * (-n0);
+            gx[1] += g * (-n1);
+            H[0] += h * (n0 * n0);
+            H[1] += h * (n0 * n1);
+            H[4] += h * (n1 * n1);
+            if (alm) {
+                mun[size_t(4) * Bs] = std_min(std_max(mu[size_t(4) * Bs] + rho * cv[0], T(0)), P.max_mu);
+                mun[size_t(5) * Bs] = std_min(std_max(mu[size_t(5) * Bs] + rho * cv[1], T(0)), P.max_mu);
+                mun[size_t(6) * Bs] = std_min(std_max(mu[size_t(6) * Bs] + rho * cp[0], T(0)), P.max_mu);
+                mun[size_t(7) * Bs] = std_min(std_max(mu[size_t(7) * Bs] + rho * cp[1], T(0)), P.max_mu);
+            }
+            // obstacles: front and rear circle against each ellipse (cpp:648-664)
+            const int no = D.n_obs[b];
+            if (no > 0) {
+                EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
+                for (int j = 0; j < no; ++j) {
+                    const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 3 * Bs + b;
+                    T ox = ob[0], oy = ob[Bs], oyaw = ob[2 * Bs];
+                    T so, co;
+                    m_sincos(oyaw, &so, &co);
+                    T gfx, gfy, grx, gry;
+                    T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
+                    T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
+                    // chain through the 4x2 centre Jacobians: (gx, gy, 0, yaw row)
+                    T f3 = e.jf0 * gfx + e.jf1 * gfy;
+                    T r3 = e.jr0 * grx + e.jr1 * gry;
+                    T gf, hf, gr, hr;
+                    constraint_weights(alm, cf, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(8 + 2 * j) * Bs] : T(0), &gf, &hf);
+                    constraint_weights(alm, cr, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(9 + 2 * j) * Bs] : T(0), &gr, &hr);
+                    // front + rear first, then into the row (cpp:662-664)
+                    gx[0] += gf * gfx + gr * grx;
+                    gx[1] += gf * gfy + gr * gry;
+                    gx[3] += gf * f3 + gr * r3;
+                    H[0] += hf * (gfx * gfx) + hr * (grx * grx);
+                    H[1] += hf * (gfx * gfy) + hr * (grx * gry);
+                    H[3] += hf * (gfx * f3) + hr * (grx * r3);
+                    H[4] += hf * (gfy * gfy) + hr * (gry * gry);
+                    H[6] += hf * (gfy * f3) + hr * (gry * r3);
+                    H[9] += hf * (f3 * f3) + hr * (r3 * r3);
+                    if (alm) {
+                        mun[size_t(8 + 2 * j) * Bs] =
+                            std_min(std_max(mu[size_t(8 + 2 * j) * Bs] + rho * cf, T(0)), P.max_mu);
+                        mun[size_t(9 + 2 * j) * Bs] =
+                            std_min(std_max(mu[size_t(9 + 2 * j) * Bs] + rho * cr, T(0)), P.max_mu);
+                    }
                 }
             }
         }
-    }
-    // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
-    T* rec = D.rec + size_t(k) * kRecFields * D.Bs + b;
+        // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
+        T* rec = D.rec + size_t(k) * kRecFields * Bs + b;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) rec[size_t(kRecLx + c) * D.Bs] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
-    H[0] += 2 * P.Q[0];
-    H[4] += 2 * P.Q[1];
-    H[7] += 2 * P.Q[2];
-    H[9] += 2 * P.Q[3];
+        for (int c = 0; c < 4; ++c) rec[size_t(kRecLx + c) * Bs] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
+        H[0] += 2 * P.Q[0];
+        H[4] += 2 * P.Q[1];
+        H[7] += 2 * P.Q[2];
+        H[9] += 2 * P.Q[3];
 #pragma unroll
-    for (int c = 0; c < 10; ++c) rec[size_t(kRecLxx + c) * D.Bs] = H[c];
+        for (int c = 0; c < 10; ++c) rec[size_t(kRecLxx + c) * Bs] = H[c];
 
-    if (k < N) {
-        T a = U[at(D, k, 0, 2, b)], s = U[at(D, k, 1, 2, b)];
-        T c[4];
-        ctrl_constraints(P, a, s, c);
-        const T* mu = alm ? D.mu + size_t(k) * D.alm_cols * D.Bs + b : nullptr;
-        T g[4], h[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-            constraint_weights(alm, c[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * D.Bs] : T(0), &g[m], &h[m]);
-        T gu0 = g[0] + (-g[1]);
-        T gu1 = g[2] + (-g[3]);
-        T hu0 = h[0] + h[1];
-        T hu1 = h[2] + h[3];
-        if (alm) {
-            T* mun = D.mu_next + size_t(k) * D.alm_cols * D.Bs + b;
+        if (k < N) {
+            T c[4];
+            ctrl_constraints(P, ua, us, c);
+            const T* mu = alm ? D.mu + size_t(k) * D.alm_cols * Bs + b : nullptr;
+            T g[4], h[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m)
-                mun[size_t(m) * D.Bs] = std_min(std_max(mu[size_t(m) * D.Bs] + rho * c[m], T(0)), P.max_mu);
+                constraint_weights(alm, c[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * Bs] : T(0), &g[m], &h[m]);
+            T gu0 = g[0] + (-g[1]);
+            T gu1 = g[2] + (-g[3]);
+            T hu0 = h[0] + h[1];
+            T hu1 = h[2] + h[3];
+            if (alm) {
+                T* mun = D.mu_next + size_t(k) * D.alm_cols * Bs + b;
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    mun[size_t(m) * Bs] = std_min(std_max(mu[size_t(m) * Bs] + rho * c[m], T(0)), P.max_mu);
+            }
+            rec[size_t(kRecLu + 0) * Bs] = 2 * (ua * P.R[0]) + gu0;
+            rec[size_t(kRecLu + 1) * Bs] = 2 * (us * P.R[1]) + gu1;
+            rec[size_t(kRecLuu + 0) * Bs] = 2 * P.R[0] + hu0;
+            rec[size_t(kRecLuu + 1) * Bs] = 0;
+            rec[size_t(kRecLuu + 2) * Bs] = 2 * P.R[1] + hu1;
+            T ja[5], jb[4];
+            model_jacobians(x[2], x[3], us, P.dt, P.wheelbase, P.ref_point, ja, jb);
+#pragma unroll
+            for (int c2 = 0; c2 < 5; ++c2) rec[size_t(kRecA + c2) * Bs] = ja[c2];
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) rec[size_t(kRecB + c2) * Bs] = jb[c2];
         }
-        rec[size_t(kRecLu + 0) * D.Bs] = 2 * (a * P.R[0]) + gu0;
-        rec[size_t(kRecLu + 1) * D.Bs] = 2 * (s * P.R[1]) + gu1;
-        rec[size_t(kRecLuu + 0) * D.Bs] = 2 * P.R[0] + hu0;
-        rec[size_t(kRecLuu + 1) * D.Bs] = 0;
-        rec[size_t(kRecLuu + 2) * D.Bs] = 2 * P.R[1] + hu1;
-        T ja[5], jb[4];
-        model_jacobians(x[2], x[3], s, P.dt, P.wheelbase, P.ref_point, ja, jb);
-#pragma unroll
-        for (int c2 = 0; c2 < 5; ++c2) rec[size_t(kRecA + c2) * D.Bs] = ja[c2];
-#pragma unroll
-        for (int c2 = 0; c2 < 4; ++c2) rec[size_t(kRecB + c2) * D.Bs] = jb[c2];
     }
 }
 
 // solve()'s bookkeeping after an iter_step (cpp:113-141): lambda schedule,
-// iteration count, the three exits.
+// iteration count, the three exits.  alpha_idx / cost feed the optional trace.
 template <typename T>
-__device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T>& P, int b, int status) {
+__device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T>& P, int b, int status,
+                                              int alpha_idx, T cost) {
     T lamb = D.lamb[b];
     if (status == ST_BWD_FAIL || status == ST_FWD_FAIL) {
         lamb = std_max(P.lamb_amplify, lamb * P.lamb_amplify);
@@ -485,8 +565,13 @@ __device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T
     }
     D.lamb[b] = lamb;
     D.status[b] = status;
-    int it = D.iters[b] + 1;
-    D.iters[b] = it;
+    const int it = D.iters[b];
+    if (it < D.trace_cap) {
+        D.tr_status[size_t(it) * D.Bs + b] = status;
+        D.tr_alpha[size_t(it) * D.Bs + b] = alpha_idx;
+        D.tr_cost[size_t(it) * D.Bs + b] = cost;
+    }
+    D.iters[b] = it + 1;
     D.aidx[b] = 0;
     if (lamb > P.max_lamb) {
         D.phase[b] = PH_DONE;
@@ -494,7 +579,7 @@ __device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T
     } else if (status == ST_CONVERGED) {
         D.phase[b] = PH_DONE;
         D.exit_reason[b] = EX_CONVERGED;
-    } else if (it >= P.max_iter) {
+    } else if (it + 1 >= P.max_iter) {
         D.phase[b] = PH_DONE;
         D.exit_reason[b] = EX_MAX_ITER;
     } else {
@@ -502,24 +587,16 @@ __device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T
     }
 }
 
-// ---------------------------------------------------------------------------
-// K5  backward_pass (cpp:391-439): the Riccati recursion, one thread per
-//     trajectory.  Per step it streams the 28-scalar record (l_x 4, l_xx 10,
-//     l_u 2, l_uu 3, A 5, B 4) and writes K (8) and d (2):
-//     (38 N + 18) * sizeof(T) algorithmic bytes per trajectory.
-//     Q_uu + lambda*I is tested exactly like Eigen::LLT (lower, unblocked):
-//     fail iff a pivot <= 0, NaN passes (cpp:415-420); the inverse is the
-//     adjugate times 1/det (cpp:421).  `solver` != 0: act on instances in
-//     PH_BACKWARD, drive the state machine; 0: standalone stage.
-// ---------------------------------------------------------------------------
+// The Riccati recursion of one trajectory.  Streams the 28-scalar record of each
+// step (l_x 4, l_xx 10, l_u 2, l_uu 3, A 5, B 4) and writes K (8) and d (2):
+// (38 N + 18) * sizeof(T) algorithmic bytes per trajectory.  Q_uu + lambda*I is
+// tested exactly like Eigen::LLT (lower, unblocked): fail iff a pivot <= 0, NaN
+// passes (cpp:415-420); the inverse is the adjugate times 1/det (cpp:421).
+// Returns false on a non-PD Q_uu (d, K rows not reached are zeroed, as in the reference).
 template <typename T>
-__global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    if (solver && D.phase[b] != PH_BACKWARD) return;
+__device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
     const int N = D.N;
     const size_t Bs = D.Bs;
-    const T lamb = D.lamb[b];
     const T* rec = D.rec + size_t(N) * kRecFields * Bs + b;
     T Vx[4], V[10];
 #pragma unroll
@@ -611,10 +688,10 @@ __global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver) {
             K[c] = (-i00) * Qux[c] + (-i01) * Qux[4 + c];
             K[4 + c] = (-i10) * Qux[c] + (-i11) * Qux[4 + c];
         }
-        D.dg[at(D, i, 0, 2, b)] = d0;
-        D.dg[at(D, i, 1, 2, b)] = d1;
+        D.dg[at(Bs, i, 0, 2, b)] = d0;
+        D.dg[at(Bs, i, 1, 2, b)] = d1;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) D.Kg[at(D, i, c, 8, b)] = K[c];
+        for (int c = 0; c < 8; ++c) D.Kg[at(Bs, i, c, 8, b)] = K[c];
         // value function update (cpp:427-432), regularised Q_uu
         T M0[4], M1[4];  // K^T Q_uu, columns 0 and 1
 #pragma unroll
@@ -647,149 +724,244 @@ __global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver) {
         dV1 += d0 * Qu0 + d1 * Qu1;
     }
     if (failed) {
-        // the reference returns freshly zeroed d, K rows for the steps it never reached
         for (; i >= 0; --i) {
-            D.dg[at(D, i, 0, 2, b)] = 0;
-            D.dg[at(D, i, 1, 2, b)] = 0;
+            D.dg[at(Bs, i, 0, 2, b)] = 0;
+            D.dg[at(Bs, i, 1, 2, b)] = 0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) D.Kg[at(D, i, c, 8, b)] = 0;
+            for (int c = 0; c < 8; ++c) D.Kg[at(Bs, i, c, 8, b)] = 0;
         }
     }
     D.dV[b] = dV0;
     D.dV[Bs + b] = dV1;
-    if (solver) {
-        D.rec_valid[b] = 1;
-        if (failed) {
-            end_iteration(D, D.P[D.tmpl[b]], b, ST_BWD_FAIL);  // cpp:345-347, :118-120
-        } else {
-            D.status[b] = ST_RUNNING;  // set by the derivative stage (cpp:472/475)
-            D.phase[b] = PH_SEARCH;
-            D.aidx[b] = 0;
+    return !failed;
+}
+
+// ---------------------------------------------------------------------------
+// K5  backward_pass (cpp:383-440), one thread per trajectory.
+//     solver == 0: the stand-alone operator (roofline leg, stage tests).
+//     solver != 0: instances in PH_BACKWARD run the recursion and start their
+//     line search; then every searching instance claims its trial-pool slots
+//     for this round (warp-aggregated, one atomic per warp).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver) {
+    const int lane = threadIdx.x & 31;
+    const int n_threads = gridDim.x * blockDim.x;
+    const int rounds = (B + n_threads - 1) / n_threads;
+    for (int it = 0, b = blockIdx.x * blockDim.x + threadIdx.x; it < rounds; ++it, b += n_threads) {
+        const bool in = b < B;
+        int want = 0, a0 = 0;
+        if (in) {
+            if (!solver) {
+                bool ok = riccati(D, b, D.lamb[b]);
+                D.status[b] = ok ? ST_RUNNING : ST_BWD_FAIL;
+            } else {
+                D.commit_src[b] = -1;  // consumed by the derivative stage just before
+                D.t_count[b] = 0;
+                int ph = D.phase[b];
+                if (ph == PH_BACKWARD) {
+                    bool ok = riccati(D, b, D.lamb[b]);
+                    D.rec_valid[b] = 1;
+                    if (!ok) {
+                        end_iteration(D, D.P[D.tmpl[b]], b, ST_BWD_FAIL, -1, D.J_cur[b]);  // cpp:345-347, :118-120
+                        ph = D.phase[b];
+                    } else {
+                        D.status[b] = ST_RUNNING;  // set by the derivative stage (cpp:472/475)
+                        D.phase[b] = ph = PH_SEARCH;
+                        D.aidx[b] = 0;
+                    }
+                }
+                if (ph == PH_SEARCH) {
+                    a0 = D.aidx[b];
+                    want = (D.wide_mode && D.wide[b]) ? kNumAlphas - a0 : 1;
+                }
+            }
         }
-    } else {
-        D.status[b] = failed ? ST_BWD_FAIL : ST_RUNNING;
+        if (solver) {
+            // exclusive prefix sum of `want` over the warp, one atomic for the warp's total
+            int incl = want;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int total = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0;
+            if (lane == 31 && total > 0) base = atomicAdd(&D.ctl[CTL_NV], total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            if (want > 0) {
+                int v0 = base + incl - want;
+                int room = D.Vs - v0;
+                int cnt = room <= 0 ? 0 : (want < room ? want : room);
+                D.t_first[b] = v0;
+                D.t_count[b] = cnt;
+                for (int i = 0; i < cnt; ++i) {
+                    D.t_inst[v0 + i] = b;
+                    D.t_aidx[v0 + i] = a0 + i;
+                }
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
 // K6  forward_pass (cpp:442-461): u' = u + K (x' - x) + alpha d, x' = f(x', u'),
-//     one thread per trajectory, written to the trial buffer.  In the solver
-//     alpha = 2^-aidx; the stage operator passes explicit alphas.
+//     one thread per trial slot.  In the solver alpha = 2^-aidx of the slot;
+//     the stage operator passes explicit alphas (slot v = instance v).
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    if (solver && D.phase[b] != PH_SEARCH) return;
-    const DevParams<T>& P = D.P[D.tmpl[b]];
     const int N = D.N;
-    const int buf = D.cur[b];
-    const T* X = D.X + xbuf(D, buf);
-    const T* U = D.U + ubuf(D, buf);
-    T* Xn = D.X + xbuf(D, 1 - buf);
-    T* Un = D.U + ubuf(D, 1 - buf);
-    const T alpha = solver ? T(1) / T(1 << D.aidx[b]) : D.alpha[b];
-    T xn[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        xn[c] = X[at(D, 0, c, 4, b)];
-        Xn[at(D, 0, c, 4, b)] = xn[c];
-    }
-    for (int i = 0; i < N; ++i) {
-        T dx[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dx[c] = xn[c] - X[at(D, i, c, 4, b)];
-        T un[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            T s = 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) s += D.Kg[at(D, i, r * 4 + c, 8, b)] * dx[c];
-            un[r] = (U[at(D, i, r, 2, b)] + s) + alpha * D.dg[at(D, i, r, 2, b)];
-            Un[at(D, i, r, 2, b)] = un[r];
-        }
-        T nx[4];
-        propagate(xn, un[0], un[1], P.dt, P.wheelbase, P.ref_point, nx);
+    const size_t Bs = D.Bs, Vs = D.Vs;
+    const int count = solver ? view_count(D, 1, B) : B;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += gridDim.x * blockDim.x) {
+        const int b = solver ? D.t_inst[v] : v;
+        const DevParams<T>& P = D.P[D.tmpl[b]];
+        const T alpha = solver ? T(1) / T(1 << D.t_aidx[v]) : D.alpha[b];
+        T xn[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            xn[c] = nx[c];
-            Xn[at(D, i + 1, c, 4, b)] = nx[c];
+            xn[c] = D.X[at(Bs, 0, c, 4, b)];
+            D.Xt[at(Vs, 0, c, 4, v)] = xn[c];
+        }
+        for (int i = 0; i < N; ++i) {
+            T dx[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dx[c] = xn[c] - D.X[at(Bs, i, c, 4, b)];
+            T un[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                T s = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s += D.Kg[at(Bs, i, r * 4 + c, 8, b)] * dx[c];
+                un[r] = (D.U[at(Bs, i, r, 2, b)] + s) + alpha * D.dg[at(Bs, i, r, 2, b)];
+                D.Ut[at(Vs, i, r, 2, v)] = un[r];
+            }
+            T nx[4];
+            propagate(xn, un[0], un[1], P.dt, P.wheelbase, P.ref_point, nx);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                xn[c] = nx[c];
+                D.Xt[at(Vs, i + 1, c, 4, v)] = nx[c];
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// K7  the line-search verdict of iter_step (cpp:356-380) for the trial each
-//     searching instance just evaluated, then solve()'s bookkeeping.  Also
-//     counts the instances still running after this round.
+// K7  the line-search verdict of iter_step (cpp:356-380) over the slots each
+//     searching instance evaluated this round, in alpha order, then solve()'s
+//     bookkeeping.  The last block to finish publishes the number of instances
+//     still running to the host and re-arms the round counters.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int round) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    bool running = false;
-    if (b < B) {
+__global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B) {
+    const size_t Bs = D.Bs, Vs = D.Vs;
+    int my_active = 0, my_trials = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         int ph = D.phase[b];
-        if (ph == PH_SEARCH) {
+        const int cnt = D.t_count[b];
+        if (ph == PH_SEARCH && cnt > 0) {
             const DevParams<T>& P = D.P[D.tmpl[b]];
-            const int cur = D.cur[b];
-            const T* sc = D.sc + sbuf(D, 1 - cur);
-            T new_J = 0;
-            for (int k = 0; k <= D.N; ++k) new_J += sc[size_t(k) * D.Bs + b];
-            const int a = D.aidx[b];
-            const T alpha = T(1) / T(1 << a);
-            const T actual = D.J_cur[b] - new_J;
-            if (a == 0 && m_fabs(actual) < P.conv_thr) {
-                end_iteration(D, P, b, ST_CONVERGED);  // trial discarded (cpp:358-361)
-            } else {
-                const T approx = -(alpha * alpha * D.dV[b] + alpha * D.dV[D.Bs + b]);
-                if (actual > T(0) && (approx < T(0) || actual / approx > P.accept_thr)) {
-                    D.cur[b] = 1 - cur;  // x, u <- new (cpp:113-116)
-                    D.J_cur[b] = new_J;
-                    D.rec_valid[b] = 0;
-                    end_iteration(D, P, b, a == 0 ? ST_RUNNING : ST_SMALL_STEP);
-                } else if (a + 1 >= kNumAlphas) {
+            const int v0 = D.t_first[b];
+            const int a0 = D.aidx[b];
+            const T J_cur = D.J_cur[b];
+            const T dV0 = D.dV[b], dV1 = D.dV[Bs + b];
+            bool ended = false;
+            my_trials += cnt;
+            for (int i = 0; i < cnt && !ended; ++i) {
+                const int v = v0 + i, a = a0 + i;
+                T new_J = 0;
+                for (int k = 0; k <= D.N; ++k) new_J += D.sc_t[size_t(k) * Vs + v];
+                const T alpha = T(1) / T(1 << a);
+                const T actual = J_cur - new_J;
+                if (a == 0 && m_fabs(actual) < P.conv_thr) {
+                    D.wide[b] = 0;
+                    end_iteration(D, P, b, ST_CONVERGED, a, new_J);  // trial discarded (cpp:358-361)
+                    ended = true;
+                } else {
+                    const T approx = -(alpha * alpha * dV0 + alpha * dV1);
+                    if (actual > T(0) && (approx < T(0) || actual / approx > P.accept_thr)) {
+                        D.commit_src[b] = v;  // x, u <- new (cpp:113-116), copied by the next derivative stage
+                        D.J_cur[b] = new_J;
+                        D.rec_valid[b] = 0;
+                        D.wide[b] = a > 0;
+                        end_iteration(D, P, b, a == 0 ? ST_RUNNING : ST_SMALL_STEP, a, new_J);
+                        ended = true;
+                    }
+                }
+            }
+            if (!ended) {
+                if (a0 + cnt >= kNumAlphas) {
                     if (P.solve_type == 1 && D.mu) {  // cpp:377-378
                         for (int i = 0; i < D.N * D.alm_cols; ++i)
-                            D.mu[size_t(i) * D.Bs + b] = D.mu_next[size_t(i) * D.Bs + b];
+                            D.mu[size_t(i) * Bs + b] = D.mu_next[size_t(i) * Bs + b];
                         D.rho[b] = std_min((1 + P.alm_gamma) * D.rho[b], P.max_rho);
                         D.rec_valid[b] = 0;
                     }
-                    end_iteration(D, P, b, ST_FWD_FAIL);
+                    D.wide[b] = 1;
+                    end_iteration(D, P, b, ST_FWD_FAIL, -1, J_cur);
                 } else {
-                    D.aidx[b] = a + 1;
+                    D.aidx[b] = a0 + cnt;
+                    D.wide[b] = 1;  // alpha = 1 was rejected: evaluate the remaining alphas together
                 }
             }
             ph = D.phase[b];
         }
-        running = ph != PH_DONE;
+        my_active += ph != PH_DONE;
     }
-    unsigned m = __ballot_sync(0xffffffffu, running);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&D.active[round], __popc(m));
-}
-
-// In ALM mode the multipliers changed after a failed line search, so the cost of
-// the unchanged trajectory must be re-evaluated (the reference recomputes ori_cost
-// at every iter_step, cpp:342).  Barrier mode never needs this.
-template <typename T>
-__global__ void __launch_bounds__(128) k_refresh_cost(Dev<T> D, int B) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    if (D.phase[b] != PH_BACKWARD || D.rec_valid[b]) return;
-    const T* sc = D.sc + sbuf(D, D.cur[b]);
-    T J = 0;
-    for (int k = 0; k <= D.N; ++k) J += sc[size_t(k) * D.Bs + b];
-    D.J_cur[b] = J;
+    // block-level count, then one atomic per block
+    __shared__ int s_active, s_trials;
+    if (threadIdx.x == 0) s_active = s_trials = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_active += __shfl_down_sync(0xffffffffu, my_active, o);
+        my_trials += __shfl_down_sync(0xffffffffu, my_trials, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_active, my_active);
+        atomicAdd(&s_trials, my_trials);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&D.ctl[CTL_ACTIVE], s_active);
+        atomicAdd(&D.ctl[CTL_TRIALS], s_trials);
+        __threadfence();
+        int ticket = atomicAdd(&D.ctl[CTL_TICKET], 1);
+        if (ticket == int(gridDim.x) - 1) {
+            __threadfence();
+            int active = atomicAdd(&D.ctl[CTL_ACTIVE], 0);
+            int round = D.ctl[CTL_ROUND] + 1;
+            D.ctl[CTL_ROUND] = round;
+            D.ctl[CTL_ACTIVE] = 0;
+            D.ctl[CTL_NV] = 0;
+            D.ctl[CTL_TICKET] = 0;
+            D.h_ctl[1] = active;
+            __threadfence_system();
+            D.h_ctl[0] = round;
+            __threadfence_system();
+        }
+    }
 }
 
 // last_solve_u = u (cpp:144)
 template <typename T>
 __global__ void __launch_bounds__(128) k_store_last_u(Dev<T> D, int B) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
-    if (b >= B) return;
-    const T* U = D.U + ubuf(D, D.cur[b]);
-    D.last_u[at(D, i, 0, 2, b)] = U[at(D, i, 0, 2, b)];
-    D.last_u[at(D, i, 1, 2, b)] = U[at(D, i, 1, 2, b)];
+    const int i = blockIdx.y;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        D.last_u[at(D.Bs, i, 0, 2, b)] = D.U[at(D.Bs, i, 0, 2, b)];
+        D.last_u[at(D.Bs, i, 1, 2, b)] = D.U[at(D.Bs, i, 1, 2, b)];
+    }
+}
+
+// Stage-operator helper: slot v = instance v for the first B slots of the trial pool.
+template <typename T>
+__global__ void k_identity_slots(Dev<T> D, int B) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        D.t_inst[b] = b;
+        D.t_aidx[b] = 0;
+    }
 }
 
 __global__ void k_pack_int(const int* __restrict__ src, int* __restrict__ dst, int B, int fill) {
@@ -806,32 +978,33 @@ __global__ void k_records_from_dense(Dev<T> D, int B, const double* lx, const do
     int k = blockIdx.y;
     if (b >= B) return;
     const int N = D.N;
-    T* rec = D.rec + size_t(k) * kRecFields * D.Bs + b;
+    const size_t Bs = D.Bs;
+    T* rec = D.rec + size_t(k) * kRecFields * Bs + b;
     const double* px = lx + (size_t(b) * (N + 1) + k) * 4;
     const double* pxx = lxx + (size_t(b) * (N + 1) + k) * 16;
-    for (int c = 0; c < 4; ++c) rec[size_t(kRecLx + c) * D.Bs] = T(px[c]);
+    for (int c = 0; c < 4; ++c) rec[size_t(kRecLx + c) * Bs] = T(px[c]);
     int e = 0;
     for (int r = 0; r < 4; ++r)
-        for (int c = r; c < 4; ++c, ++e) rec[size_t(kRecLxx + e) * D.Bs] = T(pxx[r * 4 + c]);
+        for (int c = r; c < 4; ++c, ++e) rec[size_t(kRecLxx + e) * Bs] = T(pxx[r * 4 + c]);
     if (k < N) {
         const double* pu = lu + (size_t(b) * N + k) * 2;
         const double* puu = luu + (size_t(b) * N + k) * 4;
         const double* pa = A + (size_t(b) * N + k) * 16;
         const double* pb = Bm + (size_t(b) * N + k) * 8;
-        rec[size_t(kRecLu + 0) * D.Bs] = T(pu[0]);
-        rec[size_t(kRecLu + 1) * D.Bs] = T(pu[1]);
-        rec[size_t(kRecLuu + 0) * D.Bs] = T(puu[0]);
-        rec[size_t(kRecLuu + 1) * D.Bs] = T(puu[1]);
-        rec[size_t(kRecLuu + 2) * D.Bs] = T(puu[3]);
-        rec[size_t(kRecA + 0) * D.Bs] = T(pa[0 * 4 + 2]);
-        rec[size_t(kRecA + 1) * D.Bs] = T(pa[0 * 4 + 3]);
-        rec[size_t(kRecA + 2) * D.Bs] = T(pa[1 * 4 + 2]);
-        rec[size_t(kRecA + 3) * D.Bs] = T(pa[1 * 4 + 3]);
-        rec[size_t(kRecA + 4) * D.Bs] = T(pa[3 * 4 + 2]);
-        rec[size_t(kRecB + 0) * D.Bs] = T(pb[0 * 2 + 1]);
-        rec[size_t(kRecB + 1) * D.Bs] = T(pb[1 * 2 + 1]);
-        rec[size_t(kRecB + 2) * D.Bs] = T(pb[2 * 2 + 0]);
-        rec[size_t(kRecB + 3) * D.Bs] = T(pb[3 * 2 + 1]);
+        rec[size_t(kRecLu + 0) * Bs] = T(pu[0]);
+        rec[size_t(kRecLu + 1) * Bs] = T(pu[1]);
+        rec[size_t(kRecLuu + 0) * Bs] = T(puu[0]);
+        rec[size_t(kRecLuu + 1) * Bs] = T(puu[1]);
+        rec[size_t(kRecLuu + 2) * Bs] = T(puu[3]);
+        rec[size_t(kRecA + 0) * Bs] = T(pa[0 * 4 + 2]);
+        rec[size_t(kRecA + 1) * Bs] = T(pa[0 * 4 + 3]);
+        rec[size_t(kRecA + 2) * Bs] = T(pa[1 * 4 + 2]);
+        rec[size_t(kRecA + 3) * Bs] = T(pa[1 * 4 + 3]);
+        rec[size_t(kRecA + 4) * Bs] = T(pa[3 * 4 + 2]);
+        rec[size_t(kRecB + 0) * Bs] = T(pb[0 * 2 + 1]);
+        rec[size_t(kRecB + 1) * Bs] = T(pb[1 * 2 + 1]);
+        rec[size_t(kRecB + 2) * Bs] = T(pb[2 * 2 + 0]);
+        rec[size_t(kRecB + 3) * Bs] = T(pb[3 * 2 + 1]);
     }
 }
 
@@ -842,14 +1015,15 @@ __global__ void k_records_to_dense(Dev<T> D, int B, double* lx, double* lu, doub
     int k = blockIdx.y;
     if (b >= B) return;
     const int N = D.N;
-    const T* rec = D.rec + size_t(k) * kRecFields * D.Bs + b;
+    const size_t Bs = D.Bs;
+    const T* rec = D.rec + size_t(k) * kRecFields * Bs + b;
     double* px = lx + (size_t(b) * (N + 1) + k) * 4;
     double* pxx = lxx + (size_t(b) * (N + 1) + k) * 16;
-    for (int c = 0; c < 4; ++c) px[c] = double(rec[size_t(kRecLx + c) * D.Bs]);
+    for (int c = 0; c < 4; ++c) px[c] = double(rec[size_t(kRecLx + c) * Bs]);
     int e = 0;
     for (int r = 0; r < 4; ++r)
         for (int c = r; c < 4; ++c, ++e) {
-            double v = double(rec[size_t(kRecLxx + e) * D.Bs]);
+            double v = double(rec[size_t(kRecLxx + e) * Bs]);
             pxx[r * 4 + c] = v;
             pxx[c * 4 + r] = v;
         }
@@ -858,23 +1032,23 @@ __global__ void k_records_to_dense(Dev<T> D, int B, double* lx, double* lu, doub
         double* puu = luu + (size_t(b) * N + k) * 4;
         double* pa = A + (size_t(b) * N + k) * 16;
         double* pb = Bm + (size_t(b) * N + k) * 8;
-        pu[0] = double(rec[size_t(kRecLu + 0) * D.Bs]);
-        pu[1] = double(rec[size_t(kRecLu + 1) * D.Bs]);
-        puu[0] = double(rec[size_t(kRecLuu + 0) * D.Bs]);
-        puu[1] = puu[2] = double(rec[size_t(kRecLuu + 1) * D.Bs]);
-        puu[3] = double(rec[size_t(kRecLuu + 2) * D.Bs]);
+        pu[0] = double(rec[size_t(kRecLu + 0) * Bs]);
+        pu[1] = double(rec[size_t(kRecLu + 1) * Bs]);
+        puu[0] = double(rec[size_t(kRecLuu + 0) * Bs]);
+        puu[1] = puu[2] = double(rec[size_t(kRecLuu + 1) * Bs]);
+        puu[3] = double(rec[size_t(kRecLuu + 2) * Bs]);
         for (int r = 0; r < 4; ++r)
             for (int c = 0; c < 4; ++c) pa[r * 4 + c] = (r == c) ? 1.0 : 0.0;
-        pa[0 * 4 + 2] = double(rec[size_t(kRecA + 0) * D.Bs]);
-        pa[0 * 4 + 3] = double(rec[size_t(kRecA + 1) * D.Bs]);
-        pa[1 * 4 + 2] = double(rec[size_t(kRecA + 2) * D.Bs]);
-        pa[1 * 4 + 3] = double(rec[size_t(kRecA + 3) * D.Bs]);
-        pa[3 * 4 + 2] = double(rec[size_t(kRecA + 4) * D.Bs]);
+        pa[0 * 4 + 2] = double(rec[size_t(kRecA + 0) * Bs]);
+        pa[0 * 4 + 3] = double(rec[size_t(kRecA + 1) * Bs]);
+        pa[1 * 4 + 2] = double(rec[size_t(kRecA + 2) * Bs]);
+        pa[1 * 4 + 3] = double(rec[size_t(kRecA + 3) * Bs]);
+        pa[3 * 4 + 2] = double(rec[size_t(kRecA + 4) * Bs]);
         for (int c = 0; c < 8; ++c) pb[c] = 0.0;
-        pb[0 * 2 + 1] = double(rec[size_t(kRecB + 0) * D.Bs]);
-        pb[1 * 2 + 1] = double(rec[size_t(kRecB + 1) * D.Bs]);
-        pb[2 * 2 + 0] = double(rec[size_t(kRecB + 2) * D.Bs]);
-        pb[3 * 2 + 1] = double(rec[size_t(kRecB + 3) * D.Bs]);
+        pb[0 * 2 + 1] = double(rec[size_t(kRecB + 0) * Bs]);
+        pb[1 * 2 + 1] = double(rec[size_t(kRecB + 1) * Bs]);
+        pb[2 * 2 + 0] = double(rec[size_t(kRecB + 2) * Bs]);
+        pb[3 * 2 + 1] = double(rec[size_t(kRecB + 3) * Bs]);
     }
 }
 
