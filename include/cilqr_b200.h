@@ -143,8 +143,17 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *      remaining alphas of iter_step's line search (cpp:354-372) in one device round and
  *      keep the first that passes; 0 evaluates one alpha per round.
  *  CILQR_OPT_RUN_AHEAD (default 3): device rounds the host may queue beyond the last one
- *      whose active count it has seen. */
-typedef enum cilqr_option_t { CILQR_OPT_WIDE_SEARCH = 0, CILQR_OPT_RUN_AHEAD = 1 } cilqr_option_t;
+ *      whose active count it has seen.
+ *  CILQR_OPT_PREFETCH_BELOW (default 32768): batches up to this size run the backward pass
+ *      with next-step operands prefetched into registers (latency-bound regime); larger
+ *      batches use the leaner streaming variant (bandwidth-bound regime).
+ *  CILQR_OPT_BENCH_PREFETCH (default 0): which of the two cilqr_b200_bench_backward times. */
+typedef enum cilqr_option_t {
+    CILQR_OPT_WIDE_SEARCH = 0,
+    CILQR_OPT_RUN_AHEAD = 1,
+    CILQR_OPT_PREFETCH_BELOW = 2,
+    CILQR_OPT_BENCH_PREFETCH = 3
+} cilqr_option_t;
 int cilqr_b200_set_option(cilqr_handle_t* h, int option, int value);
 
 /* Per-iteration decision trace (lockstep tests): record the first `cap` iter_step outcomes of

@@ -13,12 +13,14 @@ def run(cfg, B, N, dtype):
             c = s.counters()
             print("%s B=%d N=%d %s: %.1f ms  iters %d (mean %.1f) rounds %d launches %d exits %s -> %.2f M iter/s"
                   % (cfg, B, N, dtype, dt * 1e3, c["total_iters"], out.iters.mean(), c["rounds"], c["launches"], c["exits"], c["total_iters"] / dt / 1e6))
-        for Bk in (B,):
-            ms, nbytes = s.bench_backward(Bk, 0.0, 10, True)
-            print("  backward B=%d: median %.3f ms -> %.0f GB/s" % (Bk, np.median(ms), nbytes / np.median(ms) / 1e6))
+        for pf in (0, 1):
+            s.set_option(s.OPT_BENCH_PREFETCH, pf)
+            ms, nbytes = s.bench_backward(B, 0.0, 10, True)
+            print("  backward B=%d prefetch=%d: median %.3f ms -> %.0f GB/s" % (B, pf, np.median(ms), nbytes / np.median(ms) / 1e6))
 
 if __name__ == "__main__":
     run("C1", 4096, 50, "f64")
     run("C1", 4096, 50, "f32")
     run("C1", 65536, 50, "f64")
     run("C1", 65536, 50, "f32")
+    run("C1", 262144, 50, "f64")

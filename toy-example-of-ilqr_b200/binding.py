@@ -157,7 +157,7 @@ class BatchSolver:
         return {"total_iters": int(c.total_iters), "total_trials": int(c.total_trials), "rounds": int(c.rounds),
                 "launches": int(c.launches), "exits": dict(zip(EXIT_NAMES, list(c.exits)))}
 
-    OPT_WIDE_SEARCH, OPT_RUN_AHEAD = 0, 1
+    OPT_WIDE_SEARCH, OPT_RUN_AHEAD, OPT_PREFETCH_BELOW, OPT_BENCH_PREFETCH = 0, 1, 2, 3
 
     def set_option(self, option, value):
         self._ck(self.lib.cilqr_b200_set_option(self.h, int(option), int(value)))

@@ -48,6 +48,8 @@ struct Base {
     bool any_alm = false;
     int max_rounds = 0;
     int run_ahead = 3;
+    int prefetch_below = 32768;  // batches up to this size use the operand-prefetching Riccati kernel
+    int bench_prefetch = 0;
     volatile int* h_ctl = nullptr;  // mapped pinned: [0] rounds completed, [1] instances active after it
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     double* stage = nullptr;  // device staging in host layout
@@ -249,6 +251,8 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.sc_t, size_t(N + 1) * Vs))) return r;
         if ((r = dalloc(h, &D.t_inst, Vs))) return r;
         if ((r = dalloc(h, &D.t_aidx, Vs))) return r;
+        if ((r = dalloc(h, &D.t_done, Vs))) return r;
+        if ((r = dalloc(h, &D.J_t, Vs))) return r;
         if ((r = dalloc(h, &D.t_first, Bs))) return r;
         if ((r = dalloc(h, &D.t_count, Bs))) return r;
         if ((r = dalloc(h, &D.commit_src, Bs))) return r;
@@ -501,7 +505,11 @@ int do_solve_resident(Impl<T>* h, int B) {
             LAUNCH(h, k_cost<T>, gs2(B, N + 1), 128, h->D, B, 0);
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
-        LAUNCH(h, k_backward<T>, gs1(B), 128, h->D, B, 1);
+        if (B <= h->prefetch_below) {
+            LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 1);
+        } else {
+            LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 1);
+        }
         LAUNCH(h, k_forward<T>, gs1(trial_cap), 128, h->D, B, 1);
         launch_cost(h, B, 1);
         LAUNCH(h, k_decide<T>, gs1(B), 128, h->D, B);
@@ -711,7 +719,7 @@ int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const 
         cudaFree(tmp);
         return rc;
     }
-    LAUNCH(h, k_backward<T>, gs1(B), 128, h->D, B, 0);
+    LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0);
     e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(CILQR_ERR_CUDA, "stage_backward: %s", cudaGetErrorString(e));
@@ -758,7 +766,11 @@ int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float
             k_flush_l2<<<148 * 8, 256, 0, h->stream>>>(h->flush, h->flush_n);
         }
         CK(cudaEventRecord(h->t0, h->stream));
-        LAUNCH(h, k_backward<T>, gs1(B), 128, h->D, B, 0);
+        if (h->bench_prefetch) {
+            LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0);
+        } else {
+            LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0);
+        }
         CK(cudaEventRecord(h->t1, h->stream));
         CK(cudaEventSynchronize(h->t1));
         float ms = 0;
@@ -843,6 +855,12 @@ int do_set_option(Impl<T>* h, int option, int value) {
         case CILQR_OPT_RUN_AHEAD:
             if (value < 0 || value > 64) return fail(CILQR_ERR_INVALID, "run-ahead must be in [0, 64]");
             h->run_ahead = value;
+            return 0;
+        case CILQR_OPT_PREFETCH_BELOW:
+            h->prefetch_below = value;
+            return 0;
+        case CILQR_OPT_BENCH_PREFETCH:
+            h->bench_prefetch = value ? 1 : 0;
             return 0;
         default:
             return fail(CILQR_ERR_INVALID, "unknown option %d", option);

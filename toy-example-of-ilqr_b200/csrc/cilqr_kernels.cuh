@@ -74,6 +74,8 @@ struct Dev {
     T* sc_t;
     int* t_inst;  // [Vs] owning instance
     int* t_aidx;  // [Vs] alpha index
+    int* t_done;  // [Vs] step costs stored so far (self-resetting)
+    T* J_t;       // [Vs] total cost of the trial
     int* t_first;     // [Bs] first slot claimed this round
     int* t_count;     // [Bs] slots claimed this round
     int* commit_src;  // [Bs] trial slot to copy into the current trajectory, -1 = none
@@ -205,7 +207,9 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
 //     j = start, start+1, ... and stops at the first j whose successor is not
 //     strictly closer (or at the last waypoint); the next step starts there.
 //     Equivalent formulation used here: first j >= start with
-//     !(dist[j+1] < dist[j]) (NaN stops the scan, as in the reference).
+//     !(dist[j+1] < dist[j]) (NaN stops the scan, as in the reference); distances
+//     are compared squared (no hypot on the serial chain; the two orderings can
+//     differ only for waypoints equidistant to within an ulp).
 //     G lanes per trajectory evaluate a window of G waypoints per probe.
 // ---------------------------------------------------------------------------
 template <typename T, int G>
@@ -229,16 +233,25 @@ __global__ void __launch_bounds__(128) k_ref_match(Dev<T> D, int B, int trial) {
         const T* wx = D.wx + P.wp_off;
         const T* wy = D.wy + P.wp_off;
         int start = 0;
+        // the position of step k+1 is fetched while step k scans (the scan is a serial chain)
+        T npx = V.X[at(V.stride, 0, 0, 4, vv)];
+        T npy = V.X[at(V.stride, 0, 1, 4, vv)];
         for (int k = 0; k <= D.N; ++k) {
-            const T px = V.X[at(V.stride, k, 0, 4, vv)];
-            const T py = V.X[at(V.stride, k, 1, 4, vv)];
+            const T px = npx, py = npy;
+            {
+                const int kn = k < D.N ? k + 1 : k;
+                npx = V.X[at(V.stride, kn, 0, 4, vv)];
+                npy = V.X[at(V.stride, kn, 1, 4, vv)];
+            }
             int found = -1;
             bool done = !live;
             // all groups of the warp iterate together; finished groups idle
             while (!__all_sync(0xffffffffu, done)) {
                 int j = start + sub;
                 int jc = j < M ? j : M - 1;
-                T dj = m_hypot(px - wx[jc], py - wy[jc]);
+                // squared distance: the scan only compares distances, and x -> sqrt(x) is monotone
+                const T ex = px - __ldg(wx + jc), ey = py - __ldg(wy + jc);
+                T dj = ex * ex + ey * ey;
                 T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
                 bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
                 unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
@@ -344,6 +357,18 @@ __global__ void __launch_bounds__(128) k_cost(Dev<T> D, int B, int trial) {
             cost += Jk;
         }
         V.sc[size_t(k) * V.stride + v] = cost;
+        if (trial) {
+            // the thread that stores the last step cost of a trial sums them in step order (fixed
+            // order: the total is deterministic whichever thread ends up doing it)
+            __threadfence();
+            if (atomicAdd(&D.t_done[v], 1) == N) {
+                __threadfence();
+                T J = 0;
+                for (int kk = 0; kk <= N; ++kk) J += __ldcg(&V.sc[size_t(kk) * V.stride + v]);
+                D.J_t[v] = J;
+                D.t_done[v] = 0;
+            }
+        }
     }
 }
 
@@ -593,7 +618,7 @@ __device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T
 // tested exactly like Eigen::LLT (lower, unblocked): fail iff a pivot <= 0, NaN
 // passes (cpp:415-420); the inverse is the adjugate times 1/det (cpp:421).
 // Returns false on a non-PD Q_uu (d, K rows not reached are zeroed, as in the reference).
-template <typename T>
+template <typename T, bool kPrefetch>
 __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
     const int N = D.N;
     const size_t Bs = D.Bs;
@@ -606,11 +631,26 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
     T dV0 = 0, dV1 = 0;
     bool failed = false;
     int i = N - 1;
+    T nxt[kRecFields];
+    if (kPrefetch) {
+        const T* p = rec - size_t(kRecFields) * Bs;
+#pragma unroll
+        for (int c = 0; c < kRecFields; ++c) nxt[c] = p[size_t(c) * Bs];
+    }
     for (; i >= 0; --i) {
         rec -= size_t(kRecFields) * Bs;
         T r[kRecFields];
+        if (kPrefetch) {
+            // record of step i was fetched during step i+1; fetch step i-1 now (latency-bound batches)
 #pragma unroll
-        for (int c = 0; c < kRecFields; ++c) r[c] = rec[size_t(c) * Bs];
+            for (int c = 0; c < kRecFields; ++c) r[c] = nxt[c];
+            const T* p = rec - size_t(i > 0 ? kRecFields : 0) * Bs;
+#pragma unroll
+            for (int c = 0; c < kRecFields; ++c) nxt[c] = p[size_t(c) * Bs];
+        } else {
+#pragma unroll
+            for (int c = 0; c < kRecFields; ++c) r[c] = rec[size_t(c) * Bs];
+        }
         const T a02 = r[kRecA + 0], a03 = r[kRecA + 1], a12 = r[kRecA + 2], a13 = r[kRecA + 3], a32 = r[kRecA + 4];
         const T b01 = r[kRecB + 0], b11 = r[kRecB + 1], b20 = r[kRecB + 2], b31 = r[kRecB + 3];
         // symmetric V: 00 01 02 03 11 12 13 22 23 33
@@ -666,18 +706,10 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
         const T Quu01 = r[kRecLuu + 1] + (G00 * b01 + G01 * b11 + G03 * b31);
         const T Quu10 = r[kRecLuu + 1] + G12 * b20;
         const T Quu11 = (r[kRecLuu + 2] + (G10 * b01 + G11 * b11 + G13 * b31)) + lamb;
-        // LLT positive-definiteness test
-        if (Quu00 <= T(0)) {
-            failed = true;
-            break;
-        }
-        {
-            const T l10 = Quu10 / m_sqrt(Quu00);
-            if (Quu11 - l10 * l10 <= T(0)) {
-                failed = true;
-                break;
-            }
-        }
+        // LLT positive-definiteness test, as a predicate: the sqrt/divide chain then overlaps the
+        // 1/det chain below instead of serialising in front of it; nothing is stored when it fails
+        const T l10 = Quu10 / m_sqrt(Quu00);
+        const bool not_pd = (Quu00 <= T(0)) || (Quu11 - l10 * l10 <= T(0));
         const T invdet = T(1) / (Quu00 * Quu11 - Quu10 * Quu01);
         const T i00 = Quu11 * invdet, i01 = -Quu01 * invdet, i10 = -Quu10 * invdet, i11 = Quu00 * invdet;
         const T d0 = (-i00) * Qu0 + (-i01) * Qu1;
@@ -687,6 +719,10 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
         for (int c = 0; c < 4; ++c) {
             K[c] = (-i00) * Qux[c] + (-i01) * Qux[4 + c];
             K[4 + c] = (-i10) * Qux[c] + (-i11) * Qux[4 + c];
+        }
+        if (not_pd) {
+            failed = true;
+            break;
         }
         D.dg[at(Bs, i, 0, 2, b)] = d0;
         D.dg[at(Bs, i, 1, 2, b)] = d1;
@@ -743,7 +779,7 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
 //     line search; then every searching instance claims its trial-pool slots
 //     for this round (warp-aggregated, one atomic per warp).
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool kPrefetch>
 __global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver) {
     const int lane = threadIdx.x & 31;
     const int n_threads = gridDim.x * blockDim.x;
@@ -753,14 +789,14 @@ __global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver) {
         int want = 0, a0 = 0;
         if (in) {
             if (!solver) {
-                bool ok = riccati(D, b, D.lamb[b]);
+                bool ok = riccati<T, kPrefetch>(D, b, D.lamb[b]);
                 D.status[b] = ok ? ST_RUNNING : ST_BWD_FAIL;
             } else {
                 D.commit_src[b] = -1;  // consumed by the derivative stage just before
                 D.t_count[b] = 0;
                 int ph = D.phase[b];
                 if (ph == PH_BACKWARD) {
-                    bool ok = riccati(D, b, D.lamb[b]);
+                    bool ok = riccati<T, kPrefetch>(D, b, D.lamb[b]);
                     D.rec_valid[b] = 1;
                     if (!ok) {
                         end_iteration(D, D.P[D.tmpl[b]], b, ST_BWD_FAIL, -1, D.J_cur[b]);  // cpp:345-347, :118-120
@@ -819,22 +855,44 @@ __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
         const DevParams<T>& P = D.P[D.tmpl[b]];
         const T alpha = solver ? T(1) / T(1 << D.t_aidx[v]) : D.alpha[b];
         T xn[4];
+        // operands of step i+1 are fetched while step i computes: the rollout is one serial
+        // dependency chain, so load latency must stay off it
+        T cx[4], cu[2], cd[2], cK[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            xn[c] = D.X[at(Bs, 0, c, 4, b)];
+            cx[c] = D.X[at(Bs, 0, c, 4, b)];
+            xn[c] = cx[c];
             D.Xt[at(Vs, 0, c, 4, v)] = xn[c];
         }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            cu[r] = D.U[at(Bs, 0, r, 2, b)];
+            cd[r] = D.dg[at(Bs, 0, r, 2, b)];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cK[c] = D.Kg[at(Bs, 0, c, 8, b)];
         for (int i = 0; i < N; ++i) {
+            T nxx[4], nxu[2], nxd[2], nxK[8];
+            const int ip = i + 1 < N ? i + 1 : i;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) nxx[c] = D.X[at(Bs, ip, c, 4, b)];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                nxu[r] = D.U[at(Bs, ip, r, 2, b)];
+                nxd[r] = D.dg[at(Bs, ip, r, 2, b)];
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) nxK[c] = D.Kg[at(Bs, ip, c, 8, b)];
             T dx[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dx[c] = xn[c] - D.X[at(Bs, i, c, 4, b)];
+            for (int c = 0; c < 4; ++c) dx[c] = xn[c] - cx[c];
             T un[2];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 T s = 0;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) s += D.Kg[at(Bs, i, r * 4 + c, 8, b)] * dx[c];
-                un[r] = (D.U[at(Bs, i, r, 2, b)] + s) + alpha * D.dg[at(Bs, i, r, 2, b)];
+                for (int c = 0; c < 4; ++c) s += cK[r * 4 + c] * dx[c];
+                un[r] = (cu[r] + s) + alpha * cd[r];
                 D.Ut[at(Vs, i, r, 2, v)] = un[r];
             }
             T nx[4];
@@ -843,7 +901,15 @@ __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
             for (int c = 0; c < 4; ++c) {
                 xn[c] = nx[c];
                 D.Xt[at(Vs, i + 1, c, 4, v)] = nx[c];
+                cx[c] = nxx[c];
             }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                cu[r] = nxu[r];
+                cd[r] = nxd[r];
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cK[c] = nxK[c];
         }
     }
 }
@@ -871,8 +937,7 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B) {
             my_trials += cnt;
             for (int i = 0; i < cnt && !ended; ++i) {
                 const int v = v0 + i, a = a0 + i;
-                T new_J = 0;
-                for (int k = 0; k <= D.N; ++k) new_J += D.sc_t[size_t(k) * Vs + v];
+                const T new_J = D.J_t[v];
                 const T alpha = T(1) / T(1 << a);
                 const T actual = J_cur - new_J;
                 if (a == 0 && m_fabs(actual) < P.conv_thr) {
