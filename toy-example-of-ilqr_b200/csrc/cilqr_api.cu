@@ -155,7 +155,7 @@ int upload_templates(Impl<T>* h) {
     if (total > h->wp_cap) {
         size_t cap = std::max<size_t>(total, 4096);
         T* q = nullptr;
-        CK(cudaMalloc(&q, cap * 3 * sizeof(T)));
+        CK(cudaMalloc(&q, cap * 5 * sizeof(T)));
         h->allocs.push_back(q);
         h->d_wp = q;
         h->wp_cap = cap;
@@ -173,6 +173,14 @@ int upload_templates(Impl<T>* h) {
     h->D.wx = h->d_wp;
     h->D.wy = h->d_wp + h->wp_cap;
     h->D.wyaw = h->d_wp + 2 * h->wp_cap;
+    h->D.wsin = h->d_wp + 3 * h->wp_cap;
+    h->D.wcos = h->d_wp + 4 * h->wp_cap;
+    if (total) {
+        k_wp_sincos<T><<<(unsigned(total) + 127) / 128, 128, 0, h->stream>>>(
+            h->d_wp + 2 * h->wp_cap, h->d_wp + 3 * h->wp_cap, h->d_wp + 4 * h->wp_cap, int(total));
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));
+    }
     std::vector<DevParams<T>> hp(CILQR_B200_MAX_TEMPLATES);
     h->any_alm = false;
     int max_iter = 0;
@@ -239,7 +247,7 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.borders, 2 * Bs))) return r;
         if ((r = dalloc(h, &D.tmpl, Bs))) return r;
         if ((r = dalloc(h, &D.n_obs, Bs))) return r;
-        if ((r = dalloc(h, &D.obs, size_t(max_obs) * (N + 1) * 3 * Bs))) return r;
+        if ((r = dalloc(h, &D.obs, size_t(max_obs) * (N + 1) * 4 * Bs))) return r;
         if ((r = dalloc(h, &D.x0, 4 * Bs))) return r;
         if ((r = dalloc(h, &D.X, size_t(N + 1) * 4 * Bs))) return r;
         if ((r = dalloc(h, &D.U, size_t(N) * 2 * Bs))) return r;
@@ -325,7 +333,7 @@ inline void launch_kernel(Base* h, void (*kernel)(KArgs...), dim3 grid, dim3 blo
 // (obstacle tracks longer than N+1), only the first rows_dst rows of each block are kept.
 template <typename T>
 __global__ void k_pack_rows(const double* __restrict__ src, T* __restrict__ dst, int B, int blocks, int rows_src,
-                            int rows_dst, int inner, size_t Bs, int b_off) {
+                            int rows_dst, int inner, int inner_dst, size_t Bs, int b_off) {
     __shared__ double tile[32][33];
     const int E = blocks * rows_src * inner;
     int e0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
@@ -340,13 +348,16 @@ __global__ void k_pack_rows(const double* __restrict__ src, T* __restrict__ dst,
             int c = e % inner;
             int row = (e / inner) % rows_src;
             int blk = e / (inner * rows_src);
-            if (row < rows_dst) dst[(size_t(blk) * rows_dst + row) * inner * Bs + size_t(c) * Bs + b_off + b] = T(tile[threadIdx.x][r]);
+            if (row < rows_dst)
+                dst[(size_t(blk) * rows_dst + row) * inner_dst * Bs + size_t(c) * Bs + b_off + b] = T(tile[threadIdx.x][r]);
         }
     }
 }
 
 template <typename T>
-int pack_to_device(Impl<T>* h, const double* src, T* dst, int B, int blocks, int rows_src, int rows_dst, int inner) {
+int pack_to_device(Impl<T>* h, const double* src, T* dst, int B, int blocks, int rows_src, int rows_dst, int inner,
+                   int inner_dst = 0) {
+    if (inner_dst == 0) inner_dst = inner;
     if (!src) return fail(CILQR_ERR_INVALID, "NULL input array");
     const size_t E = size_t(blocks) * rows_src * inner;
     if (E == 0 || B == 0) return 0;
@@ -357,7 +368,7 @@ int pack_to_device(Impl<T>* h, const double* src, T* dst, int B, int blocks, int
         int nb = std::min(chunk, B - b0);
         CK(cudaMemcpyAsync(h->stage, src + size_t(b0) * E, size_t(nb) * per, cudaMemcpyHostToDevice, h->stream));
         dim3 g((unsigned(E) + 31) / 32, (nb + 31) / 32), blk(32, 8);
-        k_pack_rows<T><<<g, blk, 0, h->stream>>>(h->stage, dst, nb, blocks, rows_src, rows_dst, inner, h->Bs, b0);
+        k_pack_rows<T><<<g, blk, 0, h->stream>>>(h->stage, dst, nb, blocks, rows_src, rows_dst, inner, inner_dst, h->Bs, b0);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -454,7 +465,8 @@ int upload_problem_data(Impl<T>* h, int B, const double* ref_velo, const double*
     if (n_obs)
         for (int b = 0; b < B && !any; ++b) any = n_obs[b] > 0;
     if (any && h->max_obs > 0) {
-        if ((rc = pack_to_device(h, obs, h->D.obs, B, h->max_obs, obs_len, h->N + 1, 3))) return rc;
+        if ((rc = pack_to_device(h, obs, h->D.obs, B, h->max_obs, obs_len, h->N + 1, 3, 4))) return rc;
+        LAUNCH(h, k_obs_sincos<T>, gs2(B, h->max_obs * (h->N + 1)), 128, h->D.obs, B, size_t(h->Bs));
     }
     return 0;
 }

@@ -55,12 +55,14 @@ struct Dev {
     const T* wx;
     const T* wy;
     const T* wyaw;
+    const T* wsin;  // sin / cos of the waypoint yaws, evaluated once per template
+    const T* wcos;
     // problem data, stride Bs
     T* ref_velo;  // [Bs]
     T* borders;   // [2][Bs]
     int* tmpl;    // [Bs]
     int* n_obs;   // [Bs]
-    T* obs;       // [max_obs][N+1][3][Bs]
+    T* obs;       // [max_obs][N+1][4][Bs]  (x, y, sin yaw, cos yaw)
     T* x0;        // [4][Bs]
     // current trajectory of every instance, stride Bs
     T* X;       // [N+1][4][Bs]
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(128) k_cost(Dev<T> D, int B, int trial) {
             c[4] = x[2] - P.velo_max;
             c[5] = P.velo_min - x[2];
             T d_sign, hyp;
-            T cur_d = lateral_offset(x[0], x[1], rx, ry, ryaw, &d_sign, &hyp);
+            T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
             c[6] = cur_d - (D.borders[b] - P.width / 2);
             c[7] = (D.borders[Bs + b] + P.width / 2) - cur_d;
             T Jk = 0;
@@ -339,10 +341,10 @@ __global__ void __launch_bounds__(128) k_cost(Dev<T> D, int B, int trial) {
             if (no > 0) {
                 EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
                 for (int j = 0; j < no; ++j) {
-                    const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 3 * Bs + b;
-                    T ox = ob[0], oy = ob[Bs], oyaw = ob[2 * Bs];
-                    T so, co;
-                    m_sincos(oyaw, &so, &co);
+                    // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
+                    // evaluated once per upload (k_obs_sincos), not once per cost evaluation
+                    const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 4 * Bs + b;
+                    const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
                     T cf = ellipse_margin<T, false>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
                     T cr = ellipse_margin<T, false>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
                     if (!alm) {
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
             H[7] += h;
             // road borders: c_dot = +-(px-rx, py-ry)/hypot, flipped when d_sign < 0 (cpp:527-533)
             T d_sign, hyp;
-            T cur_d = lateral_offset(x[0], x[1], rx, ry, ryaw, &d_sign, &hyp);
+            T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
             T cp[2] = {cur_d - (D.borders[b] - P.width / 2), (D.borders[Bs + b] + P.width / 2) - cur_d};
             T n0 = (x[0] - rx) / hyp, n1 = (x[1] - ry) / hyp;
             if (d_sign < 0) {
@@ -501,10 +503,10 @@ __global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
             if (no > 0) {
                 EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
                 for (int j = 0; j < no; ++j) {
-                    const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 3 * Bs + b;
-                    T ox = ob[0], oy = ob[Bs], oyaw = ob[2 * Bs];
-                    T so, co;
-                    m_sincos(oyaw, &so, &co);
+                    // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
+                    // evaluated once per upload (k_obs_sincos), not once per cost evaluation
+                    const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 4 * Bs + b;
+                    const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
                     T gfx, gfy, grx, gry;
                     T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
                     T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
@@ -1020,12 +1022,28 @@ __global__ void __launch_bounds__(128) k_store_last_u(Dev<T> D, int B) {
     }
 }
 
-// Stage-operator helper: slot v = instance v for the first B slots of the trial pool.
+// Obstacle samples arrive as (x, y, yaw); replace the yaw by (sin yaw, cos yaw) in place
+// (fields 2 and 3), once per upload.  rows = max_obs * (N+1).
 template <typename T>
-__global__ void k_identity_slots(Dev<T> D, int B) {
+__global__ void k_obs_sincos(T* obs, int B, size_t Bs) {
+    const size_t row = blockIdx.y;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-        D.t_inst[b] = b;
-        D.t_aidx[b] = 0;
+        T* p = obs + row * 4 * Bs + b;
+        T s, c;
+        m_sincos(p[2 * Bs], &s, &c);
+        p[2 * Bs] = s;
+        p[3 * Bs] = c;
+    }
+}
+
+// sin / cos of the waypoint yaws of all templates, once per cilqr_b200_set_template.
+template <typename T>
+__global__ void k_wp_sincos(const T* wyaw, T* wsin, T* wcos, int M) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        T s, c;
+        m_sincos(wyaw[i], &s, &c);
+        wsin[i] = s;
+        wcos[i] = c;
     }
 }
 

@@ -172,9 +172,8 @@ __device__ __forceinline__ T ellipse_margin(T px, T py, T ox, T oy, T so, T co, 
 // Lateral offset to the matched waypoint (cpp:235-241): signed *distance to the
 // waypoint*, sign from the cross product; sign(0) = +1 (include/utils.hpp:110-117).
 template <typename T>
-__device__ __forceinline__ T lateral_offset(T px, T py, T rx, T ry, T ryaw, T* d_sign, T* hyp) {
-    T s, c;
-    m_sincos(ryaw, &s, &c);
+__device__ __forceinline__ T lateral_offset(T px, T py, T rx, T ry, T s, T c, T* d_sign, T* hyp) {
+    // s, c = sin / cos of the matched waypoint's yaw (tabulated once per template)
     T ds = (py - ry) * c - (px - rx) * s;
     T h = m_hypot(px - rx, py - ry);
     *d_sign = ds;
