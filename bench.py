@@ -38,9 +38,10 @@ METRIC = "ilqr_iterations_per_sec"
 UNIT = "iterations/s"
 WORKLOAD = "C1: batch=4096 randomized scenario_two_straight instances per GPU, N=50, nx=4, nu=2"
 ROOFLINE_BATCH = 262144
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_backward<double,false> at B=262144, N=50
-# from the committed ncu capture (profiles/), or None when no capture of this build exists
-ROOFLINE_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_backward<double,false> at B=262144, N=50,
+# from the committed `ncu --set full` capture (profiles/r01_ncu_full_summary.txt): 2.9675 GB read +
+# 1.0303 GB written = 0.994 x the algorithmic 4.0223 GB.  Only valid for that dtype / batch.
+ROOFLINE_TRAFFIC_BYTES = {"f64": 2.967507e9 + 1.030318e9}
 
 
 def measured_peak():
@@ -287,7 +288,7 @@ def main():
         achieved = nbytes / (float(np.mean(ms)) * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_backward (backward_pass Riccati recursion, cpp:383-440)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ROOFLINE_TRAFFIC_BYTES, "peak_source": peak_src,
+                    "traffic": ROOFLINE_TRAFFIC_BYTES.get(args.dtype), "peak_source": peak_src,
                     "bytes_per_launch": nbytes, "ms_per_launch": float(np.mean(ms)),
                     "batch": Br, "layout": "compact record, (38*N+18)*sizeof(T) bytes per trajectory",
                     "frac_of_nominal_8000": achieved / 8000.0}

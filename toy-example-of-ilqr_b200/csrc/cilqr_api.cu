@@ -96,8 +96,8 @@ DevParams<T> convert_params(const cilqr_params_t& p) {
     T radius = T(0.5) * T(p.width);
     T a = T(0.5) * T(p.length) + T(p.d_safe) * 6 + radius;
     T b = T(0.5) * T(p.width) + T(p.d_safe) + radius;
-    d.ell_a2 = a * a;
-    d.ell_b2 = b * b;
+    d.ell_a2 = T(1) / (a * a);
+    d.ell_b2 = T(1) / (b * b);
     d.alm_rho_init = T(p.alm_rho_init);
     d.alm_gamma = T(p.alm_gamma);
     d.max_rho = T(p.max_rho);

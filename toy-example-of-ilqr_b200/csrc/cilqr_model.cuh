@@ -46,7 +46,7 @@ struct DevParams {
     T R[2];  // diag(w_acc, w_stl)                (cpp:28-30)
     T obs_q1, obs_q2, st_q1, st_q2;
     T acc_max, acc_min, stl_lim, velo_max, velo_min;
-    T ell_a2, ell_b2;  // squared semi-axes
+    T ell_a2, ell_b2;  // reciprocals of the squared semi-axes, 1/a^2 and 1/b^2
     T alm_rho_init, alm_gamma, max_rho, max_mu;
     T init_lamb, lamb_decay, lamb_amplify, max_lamb, conv_thr, accept_thr;
     int max_iter, solve_type, ref_point, use_last;
@@ -156,13 +156,15 @@ __device__ __forceinline__ EgoCircles<T> ego_circles(const T x[4], T wheelbase, 
 // obstacle sample (ox, oy, sin/cos of its yaw): margin c = 1 - (xs^2/a^2 + ys^2/b^2)
 // and, when wanted, its gradient w.r.t. the point.
 template <typename T, bool kGrad>
-__device__ __forceinline__ T ellipse_margin(T px, T py, T ox, T oy, T so, T co, T a2, T b2, T* gx, T* gy) {
+__device__ __forceinline__ T ellipse_margin(T px, T py, T ox, T oy, T so, T co, T inv_a2, T inv_b2, T* gx, T* gy) {
+    // inv_a2 = 1/a^2, inv_b2 = 1/b^2 are per-template constants: the reference's divisions by a^2, b^2
+    // become multiplications (<= 1 ulp apart; fp64 division costs ~30 issue slots on the SM)
     T dx = px - ox, dy = py - oy;
     T xs = co * dx + so * dy;
     T ys = -so * dx + co * dy;
-    T margin = 1 - ((xs * xs) / a2 + (ys * ys) / b2);
+    T margin = 1 - ((xs * xs) * inv_a2 + (ys * ys) * inv_b2);
     if (kGrad) {
-        T g0 = -2 * xs / a2, g1 = -2 * ys / b2;
+        T g0 = -2 * xs * inv_a2, g1 = -2 * ys * inv_b2;
         *gx = co * g0 + (-so) * g1;
         *gy = so * g0 + co * g1;
     }
