@@ -188,7 +188,8 @@ def main():
     B, N = args.batch, 50
 
     # this rank's slice of the global instance-id range (no cross-rank data on the solve path)
-    pb = cb.synthetic_batch("C1", B, N=N, first_id=rank * B)
+    lo, hi = cb.shard.weak_range(B, rank)
+    pb = cb.synthetic_batch("C1", hi - lo, N=N, first_id=lo)
     solver = cb.BatchSolver(pb.templates, B, N, pb.max_obs, args.dtype, device=local)
     solver.set_stream(stream.cuda_stream)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MiB > L2
@@ -261,15 +262,8 @@ def main():
     t_e2e_local = sum(e2e_ms) / 1e3
 
     # ---- reduce over ranks: max time, summed work --------------------------------------------------
-    if dist is not None:
-        tt = torch.tensor([t_local, t_e2e_local], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ii = torch.tensor([iters_total, e2e_iters, launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(ii, op=dist.ReduceOp.SUM)
-        t_max, t_e2e = tt.tolist()
-        iters_total, e2e_iters, launches = [int(v) for v in ii.tolist()]
-    else:
-        t_max, t_e2e = t_local, t_e2e_local
+    (t_max, t_e2e), (iters_total, e2e_iters, launches) = cb.shard.reduce_max_sum(
+        dist, dev, [t_local, t_e2e_local], [iters_total, e2e_iters, launches])
     solver.close()
 
     # ---- roofline: K5 alone at a batch larger than L2 (rank 0) ---------------------------------------

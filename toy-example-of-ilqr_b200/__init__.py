@@ -5,7 +5,7 @@ host-side mirror used by tests and bench.py:  binding (ctypes), scenario (YAML t
 arrays, synthetic batches), templates (the reference's four scenarios).
 The directory name carries a hyphen, so import it through the top-level `cilqr_b200` module.
 """
-from . import scenario, templates  # noqa: F401
+from . import scenario, shard, templates  # noqa: F401
 from .binding import (  # noqa: F401
     BatchSolver, CILQRSolver, CilqrError, CilqrParams, SolveResult, EXPORTS, LIB_PATH, STATUS_NAMES,
     EXIT_NAMES, load_library,
