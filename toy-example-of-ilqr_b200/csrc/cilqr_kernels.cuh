@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
     const int N = D.N;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         const DevParams<T>& P = D.P[D.tmpl[b]];
+        const T p_dt = P.dt, p_wb = P.wheelbase;
+        const int p_ref = P.ref_point;
         bool warm = force_warm > 0 || (force_warm < 0 && P.use_last && !D.first[b]);
         T x[4];
 #pragma unroll
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
             D.U[at(Bs, i, 0, 2, b)] = a;
             D.U[at(Bs, i, 1, 2, b)] = s;
             T nx[4];
-            propagate(x, a, s, P.dt, P.wheelbase, P.ref_point, nx);
+            propagate(x, a, s, p_dt, p_wb, p_ref, nx);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 x[c] = nx[c];
@@ -242,8 +244,8 @@ __global__ void __launch_bounds__(128) k_ref_match(Dev<T> D, int B, int trial) {
             const T px = npx, py = npy;
             {
                 const int kn = k < D.N ? k + 1 : k;
-                npx = V.X[at(V.stride, kn, 0, 4, vv)];
-                npy = V.X[at(V.stride, kn, 1, 4, vv)];
+                npx = ld_early(V.X + at(V.stride, kn, 0, 4, vv));
+                npy = ld_early(V.X + at(V.stride, kn, 1, 4, vv));
             }
             int found = -1;
             bool done = !live;
@@ -420,40 +422,48 @@ template <typename T>
 __global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
-    const int k = blockIdx.y;
+    // two independent halves per (instance, step), one thread each (grid.y = 2 (N+1)):
+    // part 0 = state terms (l_x, l_xx), part 1 = control terms and model Jacobians (l_u, l_uu, A, B)
+    const int k = blockIdx.y >> 1;
+    const int part = blockIdx.y & 1;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         T x[4], ua = 0, us = 0;
-        int ri;
+        int ri = 0;
         const int src = masked ? D.commit_src[b] : -1;
         if (src >= 0) {
+            // the accepted trial becomes the current trajectory; part 1 reads the state from the
+            // trial slot too, so it never races with part 0's copy
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                x[c] = D.Xt[at(Vs, k, c, 4, src)];
-                D.X[at(Bs, k, c, 4, b)] = x[c];
-            }
-            if (k < N) {
+            for (int c = 0; c < 4; ++c) x[c] = D.Xt[at(Vs, k, c, 4, src)];
+            if (part == 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) D.X[at(Bs, k, c, 4, b)] = x[c];
+                ri = D.ridx_t[size_t(k) * Vs + src];
+                D.ridx[size_t(k) * Bs + b] = ri;
+                D.sc[size_t(k) * Bs + b] = D.sc_t[size_t(k) * Vs + src];
+            } else if (k < N) {
                 ua = D.Ut[at(Vs, k, 0, 2, src)];
                 us = D.Ut[at(Vs, k, 1, 2, src)];
                 D.U[at(Bs, k, 0, 2, b)] = ua;
                 D.U[at(Bs, k, 1, 2, b)] = us;
             }
-            ri = D.ridx_t[size_t(k) * Vs + src];
-            D.ridx[size_t(k) * Bs + b] = ri;
-            D.sc[size_t(k) * Bs + b] = D.sc_t[size_t(k) * Vs + src];
         }
         if (masked && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) continue;
         if (src < 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) x[c] = D.X[at(Bs, k, c, 4, b)];
-            if (k < N) {
+            if (part == 0) {
+                ri = D.ridx[size_t(k) * Bs + b];
+            } else if (k < N) {
                 ua = D.U[at(Bs, k, 0, 2, b)];
                 us = D.U[at(Bs, k, 1, 2, b)];
             }
-            ri = D.ridx[size_t(k) * Bs + b];
         }
         const DevParams<T>& P = D.P[D.tmpl[b]];
         const bool alm = P.solve_type == 1;
         const T rho = alm ? D.rho[b] : T(0);
+        T* rec = D.rec + size_t(k) * kRecFields * Bs + b;
+        if (part == 0) {
         const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
         const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
 
@@ -536,7 +546,6 @@ __global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
             }
         }
         // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
-        T* rec = D.rec + size_t(k) * kRecFields * Bs + b;
 #pragma unroll
         for (int c = 0; c < 4; ++c) rec[size_t(kRecLx + c) * Bs] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
         H[0] += 2 * P.Q[0];
@@ -545,8 +554,9 @@ __global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
         H[9] += 2 * P.Q[3];
 #pragma unroll
         for (int c = 0; c < 10; ++c) rec[size_t(kRecLxx + c) * Bs] = H[c];
+        }  // part 0
 
-        if (k < N) {
+        if (part == 1 && k < N) {
             T c[4];
             ctrl_constraints(P, ua, us, c);
             const T* mu = alm ? D.mu + size_t(k) * D.alm_cols * Bs + b : nullptr;
@@ -637,7 +647,7 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
     if (kPrefetch) {
         const T* p = rec - size_t(kRecFields) * Bs;
 #pragma unroll
-        for (int c = 0; c < kRecFields; ++c) nxt[c] = p[size_t(c) * Bs];
+        for (int c = 0; c < kRecFields; ++c) nxt[c] = ld_early(p + size_t(c) * Bs);
     }
     for (; i >= 0; --i) {
         rec -= size_t(kRecFields) * Bs;
@@ -648,7 +658,7 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
             for (int c = 0; c < kRecFields; ++c) r[c] = nxt[c];
             const T* p = rec - size_t(i > 0 ? kRecFields : 0) * Bs;
 #pragma unroll
-            for (int c = 0; c < kRecFields; ++c) nxt[c] = p[size_t(c) * Bs];
+            for (int c = 0; c < kRecFields; ++c) nxt[c] = ld_early(p + size_t(c) * Bs);
         } else {
 #pragma unroll
             for (int c = 0; c < kRecFields; ++c) r[c] = rec[size_t(c) * Bs];
@@ -854,7 +864,11 @@ __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
     const int count = solver ? view_count(D, 1, B) : B;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += gridDim.x * blockDim.x) {
         const int b = solver ? D.t_inst[v] : v;
-        const DevParams<T>& P = D.P[D.tmpl[b]];
+        // solver scalars into registers: the stores below could alias *P as far as the compiler knows,
+        // and a reload per step puts a memory latency on the serial chain
+        const DevParams<T>* Pp = D.P + D.tmpl[b];
+        const T p_dt = Pp->dt, p_wb = Pp->wheelbase;
+        const int p_ref = Pp->ref_point;
         const T alpha = solver ? T(1) / T(1 << D.t_aidx[v]) : D.alpha[b];
         T xn[4];
         // operands of step i+1 are fetched while step i computes: the rollout is one serial
@@ -877,14 +891,14 @@ __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
             T nxx[4], nxu[2], nxd[2], nxK[8];
             const int ip = i + 1 < N ? i + 1 : i;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) nxx[c] = D.X[at(Bs, ip, c, 4, b)];
+            for (int c = 0; c < 4; ++c) nxx[c] = ld_early(D.X + at(Bs, ip, c, 4, b));
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                nxu[r] = D.U[at(Bs, ip, r, 2, b)];
-                nxd[r] = D.dg[at(Bs, ip, r, 2, b)];
+                nxu[r] = ld_early(D.U + at(Bs, ip, r, 2, b));
+                nxd[r] = ld_early(D.dg + at(Bs, ip, r, 2, b));
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) nxK[c] = D.Kg[at(Bs, ip, c, 8, b)];
+            for (int c = 0; c < 8; ++c) nxK[c] = ld_early(D.Kg + at(Bs, ip, c, 8, b));
             T dx[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) dx[c] = xn[c] - cx[c];
@@ -898,7 +912,7 @@ __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
                 D.Ut[at(Vs, i, r, 2, v)] = un[r];
             }
             T nx[4];
-            propagate(xn, un[0], un[1], P.dt, P.wheelbase, P.ref_point, nx);
+            propagate(xn, un[0], un[1], p_dt, p_wb, p_ref, nx);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 xn[c] = nx[c];

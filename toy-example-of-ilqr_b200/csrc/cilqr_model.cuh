@@ -29,6 +29,20 @@ __device__ __forceinline__ double m_sqrt(double v) { return sqrt(v); }
 __device__ __forceinline__ float m_sqrt(float v) { return sqrtf(v); }
 __device__ __forceinline__ double m_fabs(double v) { return fabs(v); }
 __device__ __forceinline__ float m_fabs(float v) { return fabsf(v); }
+// Loads that must be ISSUED where they are written: the compiler otherwise sinks a software
+// prefetch down to its first use (seen in the ncu source view: the serial Riccati / rollout
+// chains then stall a full memory latency per step).  volatile asm keeps program order.
+__device__ __forceinline__ double ld_early(const double* p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_early(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // std::max / std::min semantics (NaN in the first argument is kept), as the
 // reference uses them (cpp:82, :120, :378, :623).
 template <typename T>
