@@ -125,6 +125,19 @@ int cilqr_b200_download(cilqr_handle_t* h, int B, double* u_out, double* x_out, 
                         double* d_out, double* step_cost_out, int32_t* status_out, int32_t* iters_out,
                         int32_t* exit_out);
 
+/* The step after the path: the receding-horizon loop of src/motion_planning.cpp:180-197
+ * for B independent scenarios, entirely on the device.  Per tick t = 0 .. ticks-1:
+ *     (u, x) = solve(ego_state, ref line, ref_velo, get_sub_routing_lines(tracks, t), borders);
+ *     ego_state = x.row(1);
+ * with the warm start of lqr/use_last_solution carried between ticks.  tracks [B][max_obs][track_len][3]
+ * are the full obstacle tracks (tick t reads samples t .. t+N; track_len < ticks + N is
+ * CILQR_ERR_RANGE, the reference's std::out_of_range).  ego_out [B][ticks+1][4] (ego_out[.][0] = x0),
+ * iters_out / status_out [B][ticks] may be NULL.  Track and history buffers are (re)allocated here when a
+ * longer simulation than any before is requested. */
+int cilqr_b200_simulate(cilqr_handle_t* h, int B, const double* x0, const double* ref_velo, const double* borders,
+                        const int32_t* tmpl, const int32_t* n_obs, const double* tracks, int track_len, int ticks,
+                        double* ego_out, int32_t* iters_out, int32_t* status_out);
+
 /* Counters of the last solve: total iter_step calls over the batch, line-search
  * trials (forward pass + cost) evaluated, device rounds run, kernels launched,
  * instances per exit reason. */

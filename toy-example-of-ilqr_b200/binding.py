@@ -31,7 +31,7 @@ EXPORTS = [
     "cilqr_b200_last_error", "cilqr_b200_version", "cilqr_b200_create", "cilqr_b200_destroy",
     "cilqr_b200_set_stream", "cilqr_b200_set_template", "cilqr_b200_reset", "cilqr_b200_solve_batch",
     "cilqr_b200_upload", "cilqr_b200_solve_resident", "cilqr_b200_download", "cilqr_b200_counters",
-    "cilqr_b200_set_option", "cilqr_b200_enable_trace", "cilqr_b200_get_trace",
+    "cilqr_b200_set_option", "cilqr_b200_enable_trace", "cilqr_b200_get_trace", "cilqr_b200_simulate",
     "cilqr_b200_stage_init", "cilqr_b200_stage_ref_match", "cilqr_b200_stage_cost", "cilqr_b200_stage_derivs",
     "cilqr_b200_stage_backward", "cilqr_b200_stage_forward", "cilqr_b200_bench_backward",
     "cilqr_b200_bench_tile_records",
@@ -210,6 +210,19 @@ class BatchSolver:
             _dp(out.J), _dp(out.K), _dp(out.d), _dp(out.step_cost), _ip(out.status), _ip(out.iters),
             _ip(out.exit_reason)))
         return out
+
+    def simulate(self, x0, ref_velo, borders, tmpl, n_obs, tracks, ticks):
+        """Closed receding-horizon loop on the device (motion_planning.cpp:180-197): returns the ego state
+        at every tick [B][ticks+1][4], iter_step counts and final status per tick [B][ticks]."""
+        x0, ref_velo, borders, tracks = _f64(x0), _f64(ref_velo), _f64(borders), _f64(tracks)
+        tmpl, n_obs = _i32(tmpl), _i32(n_obs)
+        B = x0.shape[0]
+        ego = np.empty((B, ticks + 1, 4))
+        iters, status = np.empty((B, ticks), np.int32), np.empty((B, ticks), np.int32)
+        self._ck(self.lib.cilqr_b200_simulate(self.h, B, _dp(x0), _dp(ref_velo), _dp(borders), _ip(tmpl), _ip(n_obs),
+                                              _dp(tracks), int(tracks.shape[2]), int(ticks), _dp(ego), _ip(iters),
+                                              _ip(status)))
+        return ego, iters, status
 
     # -- stage operators -----------------------------------------------------
     def stage_init(self, x0, tmpl=None, warm=False, last_u=None):

@@ -65,6 +65,13 @@ struct Base {
 template <typename T>
 struct Impl : Base {
     Dev<T> D{};
+    T* obs_plain = nullptr;   // [max_obs][N+1][4][Bs], the obstacle window of a plain solve
+    T* obs_tracks = nullptr;  // [max_obs][track_cap][4][Bs], full tracks of the simulation
+    int track_cap = 0;
+    T* hist_x = nullptr;
+    int* hist_iters = nullptr;
+    int* hist_status = nullptr;
+    int hist_cap = 0;
     DevParams<T>* dP = nullptr;
     T* d_wp = nullptr;  // wx | wy | wyaw, each kMaxWaypoints? (sized on demand)
     size_t wp_cap = 0;
@@ -247,7 +254,10 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.borders, 2 * Bs))) return r;
         if ((r = dalloc(h, &D.tmpl, Bs))) return r;
         if ((r = dalloc(h, &D.n_obs, Bs))) return r;
-        if ((r = dalloc(h, &D.obs, size_t(max_obs) * (N + 1) * 4 * Bs))) return r;
+        if ((r = dalloc(h, &h->obs_plain, size_t(max_obs) * (N + 1) * 4 * Bs))) return r;
+        D.obs = h->obs_plain;
+        D.obs_len = N + 1;
+        D.obs_off = 0;
         if ((r = dalloc(h, &D.x0, 4 * Bs))) return r;
         if ((r = dalloc(h, &D.X, size_t(N + 1) * 4 * Bs))) return r;
         if ((r = dalloc(h, &D.U, size_t(N) * 2 * Bs))) return r;
@@ -456,6 +466,9 @@ template <typename T>
 int upload_problem_data(Impl<T>* h, int B, const double* ref_velo, const double* borders, const int32_t* tmpl,
                         const int32_t* n_obs, const double* obs, int obs_len) {
     int rc;
+    h->D.obs = h->obs_plain;
+    h->D.obs_len = h->N + 1;
+    h->D.obs_off = 0;
     if ((rc = check_tmpl_nobs(h, B, tmpl, n_obs, obs_len))) return rc;
     if ((rc = upload_ints(h, tmpl, h->D.tmpl, B, 0))) return rc;
     if ((rc = upload_ints(h, n_obs, h->D.n_obs, B, 0))) return rc;
@@ -465,8 +478,8 @@ int upload_problem_data(Impl<T>* h, int B, const double* ref_velo, const double*
     if (n_obs)
         for (int b = 0; b < B && !any; ++b) any = n_obs[b] > 0;
     if (any && h->max_obs > 0) {
-        if ((rc = pack_to_device(h, obs, h->D.obs, B, h->max_obs, obs_len, h->N + 1, 3, 4))) return rc;
-        LAUNCH(h, k_obs_sincos<T>, gs2(B, h->max_obs * (h->N + 1)), 128, h->D.obs, B, size_t(h->Bs));
+        if ((rc = pack_to_device(h, obs, h->obs_plain, B, h->max_obs, obs_len, h->N + 1, 3, 4))) return rc;
+        LAUNCH(h, k_obs_sincos<T>, gs2(B, h->max_obs * (h->N + 1)), 128, h->obs_plain, B, size_t(h->Bs));
     }
     return 0;
 }
@@ -817,6 +830,79 @@ int do_reset(Impl<T>* h) {
     return 0;
 }
 
+// Receding-horizon closed loop of src/motion_planning.cpp:180-197 for B scenarios, on the device.
+template <typename T>
+int do_simulate(Impl<T>* h, int B, const double* x0, const double* ref_velo, const double* borders,
+                const int32_t* tmpl, const int32_t* n_obs, const double* tracks, int track_len, int ticks,
+                double* ego_out, int32_t* iters_out, int32_t* status_out) {
+    CK(cudaSetDevice(h->device));
+    const int N = h->N;
+    if (ticks < 1) return fail(CILQR_ERR_INVALID, "ticks must be >= 1");
+    bool any = false;
+    if (n_obs)
+        for (int b = 0; b < B && !any; ++b) any = n_obs[b] > 0;
+    if (any && track_len < ticks + N)
+        return fail(CILQR_ERR_RANGE, "obstacle tracks hold %d samples, the last tick needs %d (RoutingLine index out of range)",
+                    track_len, ticks + N);
+    int rc;
+    if ((rc = check_tmpl_nobs(h, B, tmpl, n_obs, track_len))) return rc;
+    // set-up allocations (grow-only): full tracks and the per-tick history
+    if (track_len > h->track_cap) {
+        if ((rc = dalloc(h, &h->obs_tracks, size_t(h->max_obs) * track_len * 4 * h->Bs))) return rc;
+        h->track_cap = track_len;
+    }
+    if (ticks > h->hist_cap) {
+        if ((rc = dalloc(h, &h->hist_x, size_t(ticks + 1) * 4 * h->Bs))) return rc;
+        if ((rc = dalloc(h, &h->hist_iters, size_t(ticks) * h->Bs))) return rc;
+        if ((rc = dalloc(h, &h->hist_status, size_t(ticks) * h->Bs))) return rc;
+        h->hist_cap = ticks;
+    }
+    if ((rc = upload_ints(h, tmpl, h->D.tmpl, B, 0))) return rc;
+    if ((rc = upload_ints(h, n_obs, h->D.n_obs, B, 0))) return rc;
+    if ((rc = pack_to_device(h, ref_velo, h->D.ref_velo, B, 1, 1, 1, 1))) return rc;
+    if ((rc = pack_to_device(h, borders, h->D.borders, B, 1, 2, 2, 1))) return rc;
+    if ((rc = pack_to_device(h, x0, h->D.x0, B, 1, 4, 4, 1))) return rc;
+    if (any && h->max_obs > 0) {
+        if ((rc = pack_to_device(h, tracks, h->obs_tracks, B, h->max_obs, track_len, track_len, 3, 4))) return rc;
+        LAUNCH(h, k_obs_sincos<T>, gs2(B, h->max_obs * track_len), 128, h->obs_tracks, B, size_t(h->Bs));
+    }
+    if ((rc = do_reset(h))) return rc;  // a new simulation starts with is_first_solve == true
+    h->D.obs = h->obs_tracks;
+    h->D.obs_len = track_len;
+    int64_t total_iters = 0, total_trials = 0;
+    int rounds = 0, launches = 0;
+    for (int t = 0; t < ticks; ++t) {
+        h->D.obs_off = t;
+        if ((rc = do_solve_resident(h, B))) break;
+        LAUNCH(h, k_advance<T>, gs1(B), 128, h->D, B, t, h->hist_x, h->hist_iters, h->hist_status);
+        total_trials += h->counters.total_trials;
+        rounds += h->counters.rounds;
+        launches += h->launches;
+    }
+    h->D.obs = h->obs_plain;
+    h->D.obs_len = N + 1;
+    h->D.obs_off = 0;
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    // history back in host layout: ego [B][ticks+1][4], iters / status [B][ticks]
+    if ((rc = unpack_to_host(h, h->hist_x, ego_out, B, (ticks + 1) * 4))) return rc;
+    std::vector<int> hi(size_t(ticks) * h->Bs), hs(size_t(ticks) * h->Bs);
+    CK(cudaMemcpyAsync(hi.data(), h->hist_iters, hi.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hs.data(), h->hist_status, hs.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < B; ++b)
+        for (int t = 0; t < ticks; ++t) {
+            total_iters += hi[size_t(t) * h->Bs + b];
+            if (iters_out) iters_out[size_t(b) * ticks + t] = hi[size_t(t) * h->Bs + b];
+            if (status_out) status_out[size_t(b) * ticks + t] = hs[size_t(t) * h->Bs + b];
+        }
+    h->counters.total_iters = total_iters;
+    h->counters.total_trials = total_trials;
+    h->counters.rounds = rounds;
+    h->counters.launches = launches;
+    return 0;
+}
+
 template <typename T>
 int do_set_template(Impl<T>* h, int t, const cilqr_params_t* params, const double* wx, const double* wy,
                     const double* wyaw, int M) {
@@ -1030,6 +1116,16 @@ int cilqr_b200_solve_batch(cilqr_handle_t* h, int B, const double* x0, const dou
     if (rc) return rc;
     CK(cudaStreamSynchronize(base(h)->stream));
     return 0;
+}
+
+int cilqr_b200_simulate(cilqr_handle_t* h, int B, const double* x0, const double* ref_velo, const double* borders,
+                        const int32_t* tmpl, const int32_t* n_obs, const double* tracks, int track_len, int ticks,
+                        double* ego_out, int32_t* iters_out, int32_t* status_out) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    return DISPATCH(h, do_simulate, B, x0, ref_velo, borders, tmpl, n_obs, tracks, track_len, ticks, ego_out,
+                    iters_out, status_out);
 }
 
 int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out) {

@@ -62,7 +62,9 @@ struct Dev {
     T* borders;   // [2][Bs]
     int* tmpl;    // [Bs]
     int* n_obs;   // [Bs]
-    T* obs;       // [max_obs][N+1][4][Bs]  (x, y, sin yaw, cos yaw)
+    T* obs;       // [max_obs][obs_len][4][Bs]  (x, y, sin yaw, cos yaw); step k reads sample obs_off + k
+    int obs_len;  // N+1 for a plain solve, the track length in the receding-horizon simulation
+    int obs_off;  // simulation tick (utils::get_sub_routing_lines, src/utils.cpp:88-103)
     T* x0;        // [4][Bs]
     // current trajectory of every instance, stride Bs
     T* X;       // [N+1][4][Bs]
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(128) k_cost(Dev<T> D, int B, int trial) {
                 for (int j = 0; j < no; ++j) {
                     // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
                     // evaluated once per upload (k_obs_sincos), not once per cost evaluation
-                    const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 4 * Bs + b;
+                    const T* ob = D.obs + (size_t(j) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
                     const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
                     T cf = ellipse_margin<T, false>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
                     T cr = ellipse_margin<T, false>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
                 for (int j = 0; j < no; ++j) {
                     // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
                     // evaluated once per upload (k_obs_sincos), not once per cost evaluation
-                    const T* ob = D.obs + (size_t(j) * (N + 1) + k) * 4 * Bs + b;
+                    const T* ob = D.obs + (size_t(j) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
                     const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
                     T gfx, gfy, grx, gry;
                     T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
@@ -1023,6 +1025,24 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B) {
             D.h_ctl[0] = round;
             __threadfence_system();
         }
+    }
+}
+
+// Receding-horizon step (src/motion_planning.cpp:197): ego_state = new_x.row(1); also logs the
+// tick's outcome.  hist_x [ticks+1][4][Bs], hist_iters / hist_status [ticks][Bs].
+template <typename T>
+__global__ void k_advance(Dev<T> D, int B, int tick, T* hist_x, int* hist_iters, int* hist_status) {
+    const size_t Bs = D.Bs;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (tick == 0) hist_x[size_t(c) * Bs + b] = D.x0[size_t(c) * Bs + b];
+            T v = D.X[at(Bs, 1, c, 4, b)];
+            D.x0[size_t(c) * Bs + b] = v;
+            hist_x[(size_t(tick + 1) * 4 + c) * Bs + b] = v;
+        }
+        hist_iters[size_t(tick) * Bs + b] = D.iters[b];
+        hist_status[size_t(tick) * Bs + b] = D.status[b];
     }
 }
 
