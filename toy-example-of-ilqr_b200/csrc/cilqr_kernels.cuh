@@ -953,9 +953,15 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B) {
             const T dV0 = D.dV[b], dV1 = D.dV[Bs + b];
             bool ended = false;
             my_trials += cnt;
-            for (int i = 0; i < cnt && !ended; ++i) {
+            // all trial costs first (independent loads), then the verdicts in alpha order
+            T Jt[kNumAlphas];
+#pragma unroll
+            for (int i = 0; i < kNumAlphas; ++i) Jt[i] = i < cnt ? D.J_t[v0 + i] : T(0);
+#pragma unroll
+            for (int i = 0; i < kNumAlphas; ++i) {
+                if (i >= cnt || ended) break;
                 const int v = v0 + i, a = a0 + i;
-                const T new_J = D.J_t[v];
+                const T new_J = Jt[i];
                 const T alpha = T(1) / T(1 << a);
                 const T actual = J_cur - new_J;
                 if (a == 0 && m_fabs(actual) < P.conv_thr) {
