@@ -540,7 +540,11 @@ int do_solve_resident(Impl<T>* h, int B) {
         } else {
             LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 1);
         }
-        LAUNCH(h, k_forward<T>, gs1(trial_cap), 128, h->D, B, 1);
+        if (B <= h->prefetch_below) {
+            LAUNCH(h, k_forward2<T>, gs1(2 * trial_cap), 128, h->D, B);  // two lanes per trial slot
+        } else {
+            LAUNCH(h, k_forward<T>, gs1(trial_cap), 128, h->D, B, 1);
+        }
         launch_cost(h, B, 1);
         LAUNCH(h, k_decide<T>, gs1(B), 128, h->D, B);
         ++launched;

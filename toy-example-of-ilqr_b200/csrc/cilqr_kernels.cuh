@@ -932,6 +932,106 @@ __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
     }
 }
 
+// K6 on two lanes per trial slot (latency-bound batches).  A rollout step holds two independent
+// sin/cos evaluations (~220 clk each on B200) on an otherwise short dependency chain; lane 0 of a
+// pair takes the heading, lane 1 the steering side, they swap results by shuffle and both apply the
+// same algebra (step_from_trig), so the state stays replicated and the bits equal k_forward's.
+template <typename T>
+__global__ void __launch_bounds__(128) k_forward2(Dev<T> D, int B) {
+    const int N = D.N;
+    const size_t Bs = D.Bs, Vs = D.Vs;
+    const int count = view_count(D, 1, B);
+    const int role = threadIdx.x & 1;
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const int n_pairs = (gridDim.x * blockDim.x) >> 1;
+    const int warp_first = pair - ((threadIdx.x & 31) >> 1);
+    for (int base = warp_first; base < count; base += n_pairs) {
+        const int v = base + ((threadIdx.x & 31) >> 1);
+        const bool live = v < count;
+        const int vv = live ? v : count - 1;
+        const int b = D.t_inst[vv];
+        const DevParams<T>* Pp = D.P + D.tmpl[b];
+        const T p_dt = Pp->dt, p_wb = Pp->wheelbase;
+        const int p_ref = Pp->ref_point;
+        const T alpha = T(1) / T(1 << D.t_aidx[vv]);
+        T xn[4], cx[4], cu[2], cd[2], cK[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            cx[c] = D.X[at(Bs, 0, c, 4, b)];
+            xn[c] = cx[c];
+            if (live && role == 0) D.Xt[at(Vs, 0, c, 4, v)] = xn[c];
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            cu[r] = D.U[at(Bs, 0, r, 2, b)];
+            cd[r] = D.dg[at(Bs, 0, r, 2, b)];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cK[c] = D.Kg[at(Bs, 0, c, 8, b)];
+        for (int i = 0; i < N; ++i) {
+            T nxx[4], nxu[2], nxd[2], nxK[8];
+            const int ip = i + 1 < N ? i + 1 : i;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) nxx[c] = ld_early(D.X + at(Bs, ip, c, 4, b));
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                nxu[r] = ld_early(D.U + at(Bs, ip, r, 2, b));
+                nxd[r] = ld_early(D.dg + at(Bs, ip, r, 2, b));
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) nxK[c] = ld_early(D.Kg + at(Bs, ip, c, 8, b));
+            T dx[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dx[c] = xn[c] - cx[c];
+            T un[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                T s = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s += cK[r * 4 + c] * dx[c];
+                un[r] = (cu[r] + s) + alpha * cd[r];
+            }
+            if (live && role == 0) {
+                D.Ut[at(Vs, i, 0, 2, v)] = un[0];
+                D.Ut[at(Vs, i, 1, 2, v)] = un[1];
+            }
+            // the two sin/cos pairs of the step, one per lane, then swapped
+            T s_head, c_head, turn;
+            if (p_ref == 0) {
+                T s, c;
+                m_sincos(role ? un[1] : xn[3], &s, &c);
+                const T os = __shfl_xor_sync(0xffffffffu, s, 1), oc = __shfl_xor_sync(0xffffffffu, c, 1);
+                s_head = role ? os : s;
+                c_head = role ? oc : c;
+                turn = (role ? s : os) / (role ? c : oc);
+            } else {
+                const T beta = m_atan(tan_sc(un[1]) / 2);
+                T s, c;
+                m_sincos(role ? beta : beta + xn[3], &s, &c);
+                const T os = __shfl_xor_sync(0xffffffffu, s, 1), oc = __shfl_xor_sync(0xffffffffu, c, 1);
+                s_head = role ? os : s;
+                c_head = role ? oc : c;
+                turn = role ? s : os;
+            }
+            T nx[4];
+            step_from_trig(xn, un[0], p_dt, p_wb, p_ref, s_head, c_head, turn, nx);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                xn[c] = nx[c];
+                if (live && role == 0) D.Xt[at(Vs, i + 1, c, 4, v)] = nx[c];
+                cx[c] = nxx[c];
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                cu[r] = nxu[r];
+                cd[r] = nxd[r];
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cK[c] = nxK[c];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K7  the line-search verdict of iter_step (cpp:356-380) over the slots each
 //     searching instance evaluated this round, in alpha order, then solve()'s

@@ -67,27 +67,42 @@ struct DevParams {
     int wp_off, wp_len;  // slice of the handle's waypoint table
 };
 
-// src/utils.cpp:262-283 — one Euler step of the rear-axle (ref_point 0) or
-// centre-of-gravity (1) bicycle model; all right-hand sides use the old state.
+// src/utils.cpp:262-283 — one Euler step of the rear-axle (ref_point 0) or centre-of-gravity (1)
+// bicycle model; all right-hand sides use the old state.  The step is split into its
+// transcendental part and its algebra so that the rollout kernels can evaluate the two independent
+// sin/cos pairs of a step on two lanes at once and still produce the bits of the one-lane version:
+//   rear:    heading = sincos(yaw),        turn = tan(steer)
+//   gravity: heading = sincos(beta + yaw), turn = sin(beta),  beta = atan(tan(steer) / 2)
+// tan(v) is taken as sin(v)/cos(v) from one sincos (<= 2 ulp, the accuracy class of CUDA's tan()),
+// which keeps every lane on the same instruction stream.
+template <typename T>
+__device__ __forceinline__ T tan_sc(T v) {
+    T s, c;
+    m_sincos(v, &s, &c);
+    return s / c;
+}
+template <typename T>
+__device__ __forceinline__ void step_from_trig(const T x[4], T acc, T dt, T wheelbase, int ref_point, T s_head,
+                                               T c_head, T turn, T out[4]) {
+    out[0] = x[0] + x[2] * c_head * dt;
+    out[1] = x[1] + x[2] * s_head * dt;
+    out[2] = x[2] + acc * dt;
+    out[3] = ref_point == 0 ? x[3] + x[2] * turn * dt / wheelbase : x[3] + 2 * x[2] * turn * dt / wheelbase;
+}
 template <typename T>
 __device__ __forceinline__ void propagate(const T x[4], T acc, T steer, T dt, T wheelbase,
                                           int ref_point, T out[4]) {
+    T s, c, turn;
     if (ref_point == 0) {
-        T s, c;
         m_sincos(x[3], &s, &c);
-        out[0] = x[0] + x[2] * c * dt;
-        out[1] = x[1] + x[2] * s * dt;
-        out[2] = x[2] + acc * dt;
-        out[3] = x[3] + x[2] * m_tan(steer) * dt / wheelbase;
+        turn = tan_sc(steer);
     } else {
-        T beta = m_atan(m_tan(steer) / 2);
-        T s, c;
+        const T beta = m_atan(tan_sc(steer) / 2);
         m_sincos(beta + x[3], &s, &c);
-        out[0] = x[0] + x[2] * c * dt;
-        out[1] = x[1] + x[2] * s * dt;
-        out[2] = x[2] + acc * dt;
-        out[3] = x[3] + 2 * x[2] * m_sin(beta) * dt / wheelbase;
+        T cb;
+        m_sincos(beta, &turn, &cb);
     }
+    step_from_trig(x, acc, dt, wheelbase, ref_point, s, c, turn, out);
 }
 
 // src/utils.cpp:285-342 — the non-trivial entries of A = df/dx (identity plus
