@@ -530,7 +530,12 @@ int do_solve_resident(Impl<T>* h, int B) {
         int done = h->h_ctl[0];
         if (done > 0 && h->h_ctl[1] == 0) break;
         if (launched - done > h->run_ahead) continue;  // spin on the mapped words
-        LAUNCH(h, k_derivs<T>, gs2(B, 2 * (N + 1)), 128, h->D, B, 1);
+        if (B <= h->prefetch_below) {
+            LAUNCH(h, (k_derivs<T, -1>), gs2(B, 2 * (N + 1)), 128, h->D, B, 1);
+        } else {
+            LAUNCH(h, (k_derivs<T, 0>), gs2(B, N + 1), 128, h->D, B, 1);
+            LAUNCH(h, (k_derivs<T, 1>), gs2(B, N + 1), 128, h->D, B, 1);
+        }
         if (h->any_alm) {
             LAUNCH(h, k_cost<T>, gs2(B, N + 1), 128, h->D, B, 0);
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
@@ -549,7 +554,7 @@ int do_solve_resident(Impl<T>* h, int B) {
         LAUNCH(h, k_decide<T>, gs1(B), 128, h->D, B);
         ++launched;
     }
-    LAUNCH(h, k_derivs<T>, gs2(B, 2 * (N + 1)), 128, h->D, B, 1);  // commit a step accepted in the last round
+    LAUNCH(h, (k_derivs<T, -1>), gs2(B, 2 * (N + 1)), 128, h->D, B, 1);  // commit a step accepted in the last round
     LAUNCH(h, k_store_last_u<T>, gs2(B, N), 128, h->D, B);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -690,7 +695,7 @@ int stage_derivs(Impl<T>* h, int B, const double* u, const double* x, const doub
     if ((rc = load_alm(h, B, alm_mu, alm_rho))) return rc;
     constexpr int G = 8;
     LAUNCH(h, k_ref_match<T, G>, gs1(B * G), 128, h->D, B, 0);
-    LAUNCH(h, k_derivs<T>, gs2(B, 2 * (N + 1)), 128, h->D, B, 0);
+    LAUNCH(h, (k_derivs<T, -1>), gs2(B, 2 * (N + 1)), 128, h->D, B, 0);
     // dense conversion on device into a temporary allocation (test path; not part of create-time budget)
     size_t n_lx = size_t(B) * (N + 1) * 4, n_lu = size_t(B) * N * 2, n_lxx = size_t(B) * (N + 1) * 16,
            n_luu = size_t(B) * N * 4, n_A = size_t(B) * N * 16, n_B = size_t(B) * N * 8;

@@ -420,14 +420,16 @@ __device__ __forceinline__ void constraint_weights(bool alm, T c, T q1, T q2, T 
 //     then differentiates only where the record is stale — the reference's
 //     cache rule for rejected steps (cpp:469-474).
 // ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(128) k_derivs(Dev<T> D, int B, int masked) {
+template <typename T, int kPart>
+__global__ void __launch_bounds__(128, kPart == 0 ? 5 : 4) k_derivs(Dev<T> D, int B, int masked) {
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
-    // two independent halves per (instance, step), one thread each (grid.y = 2 (N+1)):
-    // part 0 = state terms (l_x, l_xx), part 1 = control terms and model Jacobians (l_u, l_uu, A, B)
-    const int k = blockIdx.y >> 1;
-    const int part = blockIdx.y & 1;
+    // two independent halves per (instance, step): part 0 = state terms (l_x, l_xx), part 1 = control
+    // terms and model Jacobians (l_u, l_uu, A, B).  kPart < 0: one launch, the half taken from
+    // blockIdx.y (latency-bound batches: one launch less per round).  kPart = 0 / 1: one launch per
+    // half, so that each half gets its own register budget and occupancy (throughput regime).
+    const int k = kPart < 0 ? int(blockIdx.y >> 1) : int(blockIdx.y);
+    const int part = kPart < 0 ? int(blockIdx.y & 1) : kPart;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         T x[4], ua = 0, us = 0;
         int ri = 0;
