@@ -35,7 +35,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(CILQR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kGridCap = 148 * 8;  // grid-stride kernels: at most 8 CTAs of 128 threads per SM
+constexpr int kGridCap = 148 * 32;  // grid-stride kernels: at most 32 CTAs of 128 threads per SM (queued beyond residency)
 
 // Type-erased part of a handle; the typed buffers live in Impl<T>.
 struct Base {
