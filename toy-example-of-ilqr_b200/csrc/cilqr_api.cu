@@ -505,7 +505,11 @@ void launch_cost(Impl<T>* h, int B, int trial) {
     } else {
         LAUNCH(h, (k_ref_match<T, 8>), gs1(cap * 8), 128, h->D, B, trial);
     }
-    LAUNCH(h, k_cost<T>, gs2(cap, h->N + 1), 128, h->D, B, trial);
+    if (B <= h->prefetch_below) {
+        LAUNCH(h, (k_cost<T, 7>), gs2(cap, h->N + 1), 128, h->D, B, trial);
+    } else {
+        LAUNCH(h, (k_cost<T, 8>), gs2(cap, h->N + 1), 128, h->D, B, trial);
+    }
 }
 
 template <typename T>
@@ -537,7 +541,7 @@ int do_solve_resident(Impl<T>* h, int B) {
             LAUNCH(h, (k_derivs<T, 1>), gs2(B, N + 1), 128, h->D, B, 1);
         }
         if (h->any_alm) {
-            LAUNCH(h, k_cost<T>, gs2(B, N + 1), 128, h->D, B, 0);
+            LAUNCH(h, (k_cost<T, 7>), gs2(B, N + 1), 128, h->D, B, 0);
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
         if (B <= h->prefetch_below) {

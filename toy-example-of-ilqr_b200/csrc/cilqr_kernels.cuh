@@ -292,8 +292,10 @@ __device__ __forceinline__ void ctrl_constraints(const DevParams<T>& P, T acc, T
 //     state term of x_k, control term of u_k (k < N), constraint terms of
 //     step k (k >= 1: u_{k-1}, x_k, ref_k, obstacles at tick k).
 // ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(128) k_cost(Dev<T> D, int B, int trial) {
+// kMinBlocks: 8 CTAs/SM (64 registers, small spills) in the throughput regime, where the kernel is
+// fp64-latency bound and more resident warps pay (+11 % whole-solve at B = 262 144); 7 otherwise.
+template <typename T, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int trial) {
     const View<T> V = view_of(D, trial);
     const int count = view_count(D, trial, B);
     const int N = D.N;
@@ -421,7 +423,7 @@ __device__ __forceinline__ void constraint_weights(bool alm, T c, T q1, T q2, T 
 //     cache rule for rejected steps (cpp:469-474).
 // ---------------------------------------------------------------------------
 template <typename T, int kPart>
-__global__ void __launch_bounds__(128, kPart == 0 ? 5 : 4) k_derivs(Dev<T> D, int B, int masked) {
+__global__ void __launch_bounds__(128, kPart < 0 ? 4 : 8) k_derivs(Dev<T> D, int B, int masked) {
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
     // two independent halves per (instance, step): part 0 = state terms (l_x, l_xx), part 1 = control
