@@ -225,6 +225,28 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     t_local = sum(step_ms) / 1e3
 
+    # one extra, untimed solve with a CUDA event in front of every stage launch: where the step's
+    # device time goes, and the backward-pass kernel's live duration inside the step
+    in_step = None
+    if rank == 0:
+        solver.set_option(solver.OPT_PROFILE_STAGES, 1)
+        with torch.cuda.stream(stream):
+            flush.add_(1.0)
+            solver.solve_resident(B)
+        st = solver.stage_times()
+        solver.set_option(solver.OPT_PROFILE_STAGES, 0)
+        total = sum(v[0] for v in st.values())
+        bw_ms, bw_n = st["backward"]
+        sz = 8 if args.dtype == "f64" else 4
+        in_step = {
+            "stage_ms": {k: round(v[0], 3) for k, v in st.items()}, "rounds": bw_n,
+            "backward_share": bw_ms / total if total else None,
+            "backward_us_per_launch": 1e3 * bw_ms / max(bw_n, 1),
+            "backward_GBps_if_all_instances_ran": (38 * N + 18) * sz * B / (1e6 * bw_ms / max(bw_n, 1)) if bw_ms else None,
+            "note": "B=4096 records (63 MB) are L2-resident and only the running instances take part in a "
+                    "round: the step is latency-bound, the HBM roofline of this kernel is measured at B=262144",
+        }
+
     # ---- e2e: pinned host buffers through cilqr_b200_solve_batch ---------------------------------
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -306,6 +328,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": 1e3 * t_e2e / max(args.steps, 1)},
             "gpu_launches": launches,
             "roofline": roofline,
+            "in_step": in_step,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -160,14 +160,22 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *  CILQR_OPT_PREFETCH_BELOW (default 32768): batches up to this size run the backward pass
  *      with next-step operands prefetched into registers (latency-bound regime); larger
  *      batches use the leaner streaming variant (bandwidth-bound regime).
- *  CILQR_OPT_BENCH_PREFETCH (default 0): which of the two cilqr_b200_bench_backward times. */
+ *  CILQR_OPT_BENCH_PREFETCH (default 0): which of the two cilqr_b200_bench_backward times.
+ *  CILQR_OPT_PROFILE_STAGES (default 0): record a CUDA event in front of every stage launch of the
+ *      following solves (adds a few microseconds per round; not for timed runs). */
 typedef enum cilqr_option_t {
     CILQR_OPT_WIDE_SEARCH = 0,
     CILQR_OPT_RUN_AHEAD = 1,
     CILQR_OPT_PREFETCH_BELOW = 2,
-    CILQR_OPT_BENCH_PREFETCH = 3
+    CILQR_OPT_BENCH_PREFETCH = 3,
+    CILQR_OPT_PROFILE_STAGES = 4
 } cilqr_option_t;
 int cilqr_b200_set_option(cilqr_handle_t* h, int option, int value);
+
+/* Per-stage device time of the last solve run with CILQR_OPT_PROFILE_STAGES: ms_out [6] and
+ * launches_out [6] (may be NULL) for {derivatives, backward pass, forward pass, waypoint match,
+ * cost, verdict}, measured between consecutive stage events on the launch stream. */
+int cilqr_b200_stage_times(cilqr_handle_t* h, double* ms_out, int32_t* launches_out);
 
 /* Per-iteration decision trace (lockstep tests): record the first `cap` iter_step outcomes of
  * every instance of subsequent solves; get_trace returns status [B][cap] (cilqr_status_t after

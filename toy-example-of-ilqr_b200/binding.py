@@ -32,6 +32,7 @@ EXPORTS = [
     "cilqr_b200_set_stream", "cilqr_b200_set_template", "cilqr_b200_reset", "cilqr_b200_solve_batch",
     "cilqr_b200_upload", "cilqr_b200_solve_resident", "cilqr_b200_download", "cilqr_b200_counters",
     "cilqr_b200_set_option", "cilqr_b200_enable_trace", "cilqr_b200_get_trace", "cilqr_b200_simulate",
+    "cilqr_b200_stage_times",
     "cilqr_b200_stage_init", "cilqr_b200_stage_ref_match", "cilqr_b200_stage_cost", "cilqr_b200_stage_derivs",
     "cilqr_b200_stage_backward", "cilqr_b200_stage_forward", "cilqr_b200_bench_backward",
     "cilqr_b200_bench_tile_records",
@@ -157,7 +158,14 @@ class BatchSolver:
         return {"total_iters": int(c.total_iters), "total_trials": int(c.total_trials), "rounds": int(c.rounds),
                 "launches": int(c.launches), "exits": dict(zip(EXIT_NAMES, list(c.exits)))}
 
-    OPT_WIDE_SEARCH, OPT_RUN_AHEAD, OPT_PREFETCH_BELOW, OPT_BENCH_PREFETCH = 0, 1, 2, 3
+    OPT_WIDE_SEARCH, OPT_RUN_AHEAD, OPT_PREFETCH_BELOW, OPT_BENCH_PREFETCH, OPT_PROFILE_STAGES = 0, 1, 2, 3, 4
+    STAGES = ["derivs", "backward", "forward", "ref_match", "cost", "decide"]
+
+    def stage_times(self):
+        ms = np.zeros(6)
+        n = np.zeros(6, np.int32)
+        self._ck(self.lib.cilqr_b200_stage_times(self.h, _dp(ms), _ip(n)))
+        return {k: (float(a), int(b)) for k, a, b in zip(self.STAGES, ms, n)}
 
     def set_option(self, option, value):
         self._ck(self.lib.cilqr_b200_set_option(self.h, int(option), int(value)))

@@ -50,6 +50,12 @@ struct Base {
     int run_ahead = 3;
     int prefetch_below = 32768;  // batches up to this size use the operand-prefetching Riccati kernel
     int bench_prefetch = 0;
+    // optional in-step stage profile: CUDA events around every stage launch of one solve
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_stage;  // stage id that starts at event i (-1 = end marker)
+    double stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    int stage_launches[6] = {0, 0, 0, 0, 0, 0};
     volatile int* h_ctl = nullptr;  // mapped pinned: [0] rounds completed, [1] instances active after it
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     double* stage = nullptr;  // device staging in host layout
@@ -495,9 +501,24 @@ int do_upload(Impl<T>* h, int B, const double* x0, const double* ref_velo, const
 }
 
 // waypoint match + per-step costs of a set of trajectories (0: current, 1: the trial pool)
+// stage profile: an event in front of stage `id` (0 derivs, 1 backward, 2 forward, 3 ref_match, 4 cost,
+// 5 decide; -1 closes the round)
+inline void mark_stage(Base* h, int id) {
+    if (!h->profile) return;
+    size_t i = h->prof_stage.size();
+    if (i >= h->prof_ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->prof_ev.push_back(e);
+    }
+    cudaEventRecord(h->prof_ev[i], h->stream);
+    h->prof_stage.push_back(id);
+}
+
 template <typename T>
 void launch_cost(Impl<T>* h, int B, int trial) {
     const int cap = trial ? h->D.Vs : B;
+    if (trial) mark_stage(h, 3);
     // waypoint scan window: 16 lanes per trajectory while the batch is latency-bound (one probe
     // usually covers a step's advance), 8 lanes in the throughput regime
     if (B <= h->prefetch_below) {
@@ -505,6 +526,7 @@ void launch_cost(Impl<T>* h, int B, int trial) {
     } else {
         LAUNCH(h, (k_ref_match<T, 8>), gs1(cap * 8), 128, h->D, B, trial);
     }
+    if (trial) mark_stage(h, 4);
     if (B <= h->prefetch_below) {
         LAUNCH(h, (k_cost<T, 7>), gs2(cap, h->N + 1), 128, h->D, B, trial);
     } else {
@@ -534,6 +556,7 @@ int do_solve_resident(Impl<T>* h, int B) {
         int done = h->h_ctl[0];
         if (done > 0 && h->h_ctl[1] == 0) break;
         if (launched - done > h->run_ahead) continue;  // spin on the mapped words
+        mark_stage(h, 0);
         if (B <= h->prefetch_below) {
             LAUNCH(h, (k_derivs<T, -1>), gs2(B, 2 * (N + 1)), 128, h->D, B, 1);
         } else {
@@ -544,24 +567,44 @@ int do_solve_resident(Impl<T>* h, int B) {
             LAUNCH(h, (k_cost<T, 7>), gs2(B, N + 1), 128, h->D, B, 0);
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
+        mark_stage(h, 1);
         if (B <= h->prefetch_below) {
             LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 1);
         } else {
             LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 1);
         }
+        mark_stage(h, 2);
         if (B <= h->prefetch_below) {
             LAUNCH(h, k_forward2<T>, gs1(2 * trial_cap), 128, h->D, B);  // two lanes per trial slot
         } else {
             LAUNCH(h, k_forward<T>, gs1(trial_cap), 128, h->D, B, 1);
         }
         launch_cost(h, B, 1);
+        mark_stage(h, 5);
         LAUNCH(h, k_decide<T>, gs1(B), 128, h->D, B);
+        mark_stage(h, -1);
         ++launched;
     }
     LAUNCH(h, (k_derivs<T, -1>), gs2(B, 2 * (N + 1)), 128, h->D, B, 1);  // commit a step accepted in the last round
     LAUNCH(h, k_store_last_u<T>, gs2(B, N), 128, h->D, B);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
+    if (h->profile) {
+        for (int i = 0; i < 6; ++i) {
+            h->stage_ms[i] = 0;
+            h->stage_launches[i] = 0;
+        }
+        for (size_t i = 0; i + 1 < h->prof_stage.size(); ++i) {
+            int id = h->prof_stage[i];
+            if (id < 0) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) {
+                h->stage_ms[id] += ms;
+                h->stage_launches[id] += 1;
+            }
+        }
+        h->prof_stage.clear();
+    }
     int ctl[CTL_WORDS];
     CK(cudaMemcpy(ctl, h->D.ctl, sizeof ctl, cudaMemcpyDeviceToHost));
     h->counters.rounds = ctl[CTL_ROUND];
@@ -975,6 +1018,10 @@ int do_set_option(Impl<T>* h, int option, int value) {
         case CILQR_OPT_PREFETCH_BELOW:
             h->prefetch_below = value;
             return 0;
+        case CILQR_OPT_PROFILE_STAGES:
+            h->profile = value ? 1 : 0;
+            h->prof_stage.clear();
+            return 0;
         case CILQR_OPT_BENCH_PREFETCH:
             h->bench_prefetch = value ? 1 : 0;
             return 0;
@@ -1023,6 +1070,7 @@ int do_destroy(Impl<T>* h) {
     cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_ctl) cudaFreeHost(const_cast<int*>(h->h_ctl));
+    for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1139,6 +1187,15 @@ int cilqr_b200_simulate(cilqr_handle_t* h, int B, const double* x0, const double
     if (B == 0) return 0;
     return DISPATCH(h, do_simulate, B, x0, ref_velo, borders, tmpl, n_obs, tracks, track_len, ticks, ego_out,
                     iters_out, status_out);
+}
+
+int cilqr_b200_stage_times(cilqr_handle_t* h, double* ms_out, int32_t* launches_out) {
+    if (!h || !ms_out) return fail(CILQR_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 6; ++i) {
+        ms_out[i] = base(h)->stage_ms[i];
+        if (launches_out) launches_out[i] = base(h)->stage_launches[i];
+    }
+    return 0;
 }
 
 int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out) {
