@@ -157,7 +157,7 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *      keep the first that passes; 0 evaluates one alpha per round.
  *  CILQR_OPT_RUN_AHEAD (default 3): device rounds the host may queue beyond the last one
  *      whose active count it has seen.
- *  CILQR_OPT_PREFETCH_BELOW (default 32768): batches up to this size run the backward pass
+ *  CILQR_OPT_PREFETCH_BELOW (default 12288, the measured crossover): batches up to this size run the backward pass
  *      with next-step operands prefetched into registers (latency-bound regime); larger
  *      batches use the leaner streaming variant (bandwidth-bound regime).
  *  CILQR_OPT_BENCH_PREFETCH (default 0): which of the two cilqr_b200_bench_backward times.

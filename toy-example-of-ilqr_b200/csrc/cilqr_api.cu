@@ -48,7 +48,7 @@ struct Base {
     bool any_alm = false;
     int max_rounds = 0;
     int run_ahead = 3;
-    int prefetch_below = 32768;  // batches up to this size use the operand-prefetching Riccati kernel
+    int prefetch_below = 12288;  // batches up to this size use the latency-regime kernel variants (measured crossover ~12k)
     int bench_prefetch = 0;
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
