@@ -1,7 +1,7 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import cilqr_b200 as cb
-for B in (2048, 8192, 16384, 32768, 65536):
+for B in (8192, 12288, 16384, 24576, 32768):
     pb = cb.synthetic_batch("C1", B, N=50)
     with cb.BatchSolver(pb.templates, B, 50, pb.max_obs, "f64") as s:
         s.upload(pb)

@@ -93,6 +93,23 @@ def test_batch_fp64(cfg):
     assert cnt2["rounds"] >= cnt["rounds"] and cnt2["total_trials"] <= cnt["total_trials"]
 
 
+@pytest.mark.parametrize("cfg,dtype", [("C1", "f64"), ("C3", "f64"), ("C2", "f32")])
+def test_kernel_variants_return_the_same_bits(cfg, dtype):
+    """The regime switch (latency / throughput kernel variants) and the rollout+match pipeline (off, 16- and
+    8-lane scan windows) are execution strategies: every combination must return identical bits."""
+    pb = cb.synthetic_batch(cfg, 333, N=50)
+    outs = []
+    with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, dtype) as s:
+        for threshold, pipe in ((1 << 30, 0), (1 << 30, 16), (1 << 30, 8), (1 << 30, 1), (0, 1)):
+            s.set_option(s.OPT_PREFETCH_BELOW, threshold)
+            s.set_option(s.OPT_PIPELINE, pipe)
+            outs.append(s.solve(pb))
+    assert int(outs[0].iters.sum()) > pb.B
+    for o in outs[1:]:
+        for f in ("u", "x", "J", "K", "d", "iters", "status", "exit_reason", "step_cost"):
+            assert np.array_equal(getattr(outs[0], f), getattr(o, f), equal_nan=True), f
+
+
 def test_fp32_first_iteration_vs_fp32_oracle():
     """fp32 amplifies the same sensitivity ~1e9 x more (SURVEY hard part 3), so the fp32 solve is held
     to the fp32 oracle in lockstep over the first iter_step only, where decisions still agree."""

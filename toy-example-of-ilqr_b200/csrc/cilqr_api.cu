@@ -48,8 +48,9 @@ struct Base {
     bool any_alm = false;
     int max_rounds = 0;
     int run_ahead = 3;
-    int prefetch_below = 12288;  // batches up to this size use the latency-regime kernel variants (measured crossover ~12k)
+    int prefetch_below = 16384;  // batches up to this size use the latency-regime kernel variants (measured crossover ~16-18k)
     int bench_prefetch = 0;
+    int pipeline = 1;  // latency regime: rollout and waypoint match as one two-stage kernel
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
@@ -516,12 +517,14 @@ inline void mark_stage(Base* h, int id) {
 }
 
 template <typename T>
-void launch_cost(Impl<T>* h, int B, int trial) {
+void launch_cost(Impl<T>* h, int B, int trial, bool matched = false) {
     const int cap = trial ? h->D.Vs : B;
     if (trial) mark_stage(h, 3);
     // waypoint scan window: 16 lanes per trajectory while the batch is latency-bound (one probe
     // usually covers a step's advance), 8 lanes in the throughput regime
-    if (B <= h->prefetch_below) {
+    if (matched) {
+        // k_rollout_match already wrote the matches of the trial pool
+    } else if (B <= h->prefetch_below) {
         LAUNCH(h, (k_ref_match<T, 16>), gs1(cap * 16), 128, h->D, B, trial);
     } else {
         LAUNCH(h, (k_ref_match<T, 8>), gs1(cap * 8), 128, h->D, B, trial);
@@ -574,12 +577,22 @@ int do_solve_resident(Impl<T>* h, int B) {
             LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 1);
         }
         mark_stage(h, 2);
-        if (B <= h->prefetch_below) {
+        const bool piped = B <= h->prefetch_below && h->pipeline && N + 1 <= kPipeMaxSteps;
+        if (piped) {
+            const int blocks = std::max(1, std::min((trial_cap + kPipeTrials - 1) / kPipeTrials, kGridCap));
+            // 16 scan lanes per trial when the whole trial pool fits one wave at two blocks per SM
+            const bool narrow = h->pipeline == 8 || (h->pipeline == 1 && trial_cap > 2 * 148 * kPipeTrials);
+            if (narrow) {
+                LAUNCH(h, (k_rollout_match<T, 8>), dim3(blocks), pipe_threads(8), h->D, B);
+            } else {
+                LAUNCH(h, (k_rollout_match<T, 16>), dim3(blocks), pipe_threads(16), h->D, B);
+            }
+        } else if (B <= h->prefetch_below) {
             LAUNCH(h, k_forward2<T>, gs1(2 * trial_cap), 128, h->D, B);  // two lanes per trial slot
         } else {
             LAUNCH(h, k_forward<T>, gs1(trial_cap), 128, h->D, B, 1);
         }
-        launch_cost(h, B, 1);
+        launch_cost(h, B, 1, piped);
         mark_stage(h, 5);
         LAUNCH(h, k_decide<T>, gs1(B), 128, h->D, B);
         mark_stage(h, -1);
@@ -1021,6 +1034,9 @@ int do_set_option(Impl<T>* h, int option, int value) {
         case CILQR_OPT_PROFILE_STAGES:
             h->profile = value ? 1 : 0;
             h->prof_stage.clear();
+            return 0;
+        case CILQR_OPT_PIPELINE:
+            h->pipeline = value;
             return 0;
         case CILQR_OPT_BENCH_PREFETCH:
             h->bench_prefetch = value ? 1 : 0;

@@ -294,76 +294,83 @@ __device__ __forceinline__ void ctrl_constraints(const DevParams<T>& P, T acc, T
 // ---------------------------------------------------------------------------
 // kMinBlocks: 8 CTAs/SM (64 registers, small spills) in the throughput regime, where the kernel is
 // fp64-latency bound and more resident warps pay (+11 % whole-solve at B = 262 144); 7 otherwise.
+// cost of step k of trajectory v of a view (instance b), with waypoint match ri
+template <typename T>
+__device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int b, int v, int k, int ri) {
+    const int N = D.N;
+    const size_t Bs = D.Bs;
+    const DevParams<T>& P = D.P[D.tmpl[b]];
+    T x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = V.X[at(V.stride, k, c, 4, v)];
+    const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
+    const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
+    T cost = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        T e = x[c] - ref[c];
+        cost += e * P.Q[c] * e;
+    }
+    if (k < N) {
+        T a = V.U[at(V.stride, k, 0, 2, v)], s = V.U[at(V.stride, k, 1, 2, v)];
+        T ce = a * P.R[0] * a;
+        ce += s * P.R[1] * s;
+        cost += ce;
+    }
+    if (k >= 1) {
+        T a = V.U[at(V.stride, k - 1, 0, 2, v)], s = V.U[at(V.stride, k - 1, 1, 2, v)];
+        T c[8];
+        ctrl_constraints(P, a, s, c);
+        c[4] = x[2] - P.velo_max;
+        c[5] = P.velo_min - x[2];
+        T d_sign, hyp;
+        T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
+        c[6] = cur_d - (D.borders[b] - P.width / 2);
+        c[7] = (D.borders[Bs + b] + P.width / 2) - cur_d;
+        T Jk = 0;
+        const bool alm = P.solve_type == 1;
+        const T rho = alm ? D.rho[b] : T(0);
+        const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+        if (!alm) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) Jk += exp_barrier(c[m], P.st_q1, P.st_q2);
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) Jk += alm_item(c[m], rho, mu[size_t(m) * Bs]);
+        }
+        const int no = D.n_obs[b];
+        if (no > 0) {
+            EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
+            for (int j = 0; j < no; ++j) {
+                // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
+                // evaluated once per upload (k_obs_sincos), not once per cost evaluation
+                const T* ob = D.obs + (size_t(j) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
+                const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
+                T cf = ellipse_margin<T, false>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
+                T cr = ellipse_margin<T, false>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
+                if (!alm) {
+                    Jk += exp_barrier(cf, P.obs_q1, P.obs_q2);
+                    Jk += exp_barrier(cr, P.obs_q1, P.obs_q2);
+                } else {
+                    Jk += alm_item(cf, rho, mu[size_t(8 + 2 * j) * Bs]);
+                    Jk += alm_item(cr, rho, mu[size_t(9 + 2 * j) * Bs]);
+                }
+            }
+        }
+        cost += Jk;
+    }
+    return cost;
+}
+
 template <typename T, int kMinBlocks>
 __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int trial) {
     const View<T> V = view_of(D, trial);
     const int count = view_count(D, trial, B);
     const int N = D.N;
-    const size_t Bs = D.Bs;
     const int k = blockIdx.y;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += gridDim.x * blockDim.x) {
         const int b = V.inst ? V.inst[v] : v;
-        const DevParams<T>& P = D.P[D.tmpl[b]];
-        const int ri = V.ridx[size_t(k) * V.stride + v];
-        T x[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) x[c] = V.X[at(V.stride, k, c, 4, v)];
-        const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
-        const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
-        T cost = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            T e = x[c] - ref[c];
-            cost += e * P.Q[c] * e;
-        }
-        if (k < N) {
-            T a = V.U[at(V.stride, k, 0, 2, v)], s = V.U[at(V.stride, k, 1, 2, v)];
-            T ce = a * P.R[0] * a;
-            ce += s * P.R[1] * s;
-            cost += ce;
-        }
-        if (k >= 1) {
-            T a = V.U[at(V.stride, k - 1, 0, 2, v)], s = V.U[at(V.stride, k - 1, 1, 2, v)];
-            T c[8];
-            ctrl_constraints(P, a, s, c);
-            c[4] = x[2] - P.velo_max;
-            c[5] = P.velo_min - x[2];
-            T d_sign, hyp;
-            T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
-            c[6] = cur_d - (D.borders[b] - P.width / 2);
-            c[7] = (D.borders[Bs + b] + P.width / 2) - cur_d;
-            T Jk = 0;
-            const bool alm = P.solve_type == 1;
-            const T rho = alm ? D.rho[b] : T(0);
-            const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
-            if (!alm) {
-#pragma unroll
-                for (int m = 0; m < 8; ++m) Jk += exp_barrier(c[m], P.st_q1, P.st_q2);
-            } else {
-#pragma unroll
-                for (int m = 0; m < 8; ++m) Jk += alm_item(c[m], rho, mu[size_t(m) * Bs]);
-            }
-            const int no = D.n_obs[b];
-            if (no > 0) {
-                EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
-                for (int j = 0; j < no; ++j) {
-                    // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
-                    // evaluated once per upload (k_obs_sincos), not once per cost evaluation
-                    const T* ob = D.obs + (size_t(j) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
-                    const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
-                    T cf = ellipse_margin<T, false>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
-                    T cr = ellipse_margin<T, false>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, nullptr, nullptr);
-                    if (!alm) {
-                        Jk += exp_barrier(cf, P.obs_q1, P.obs_q2);
-                        Jk += exp_barrier(cr, P.obs_q1, P.obs_q2);
-                    } else {
-                        Jk += alm_item(cf, rho, mu[size_t(8 + 2 * j) * Bs]);
-                        Jk += alm_item(cr, rho, mu[size_t(9 + 2 * j) * Bs]);
-                    }
-                }
-            }
-            cost += Jk;
-        }
+        const T cost = step_cost_of(D, V, b, v, k, V.ridx[size_t(k) * V.stride + v]);
         V.sc[size_t(k) * V.stride + v] = cost;
         if (trial) {
             // the thread that stores the last step cost of a trial sums them in step order (fixed
@@ -1033,6 +1040,172 @@ __global__ void __launch_bounds__(128) k_forward2(Dev<T> D, int B) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) cK[c] = nxK[c];
         }
+    }
+}
+
+// K6 + K1 as a two-stage pipeline inside one block (latency-bound batches).  The waypoint match of
+// step k needs only the position x'_k, so it can trail the rollout instead of following it as a
+// second kernel:
+//   warp 0          rolls 16 trials out, two lanes each as in k_forward2 (lane r of a pair also owns
+//                   control row r: its feedback row, u and d), writes every new position into a
+//                   shared-memory ring covering the whole horizon and publishes its progress
+//                   (fence, then a counter);
+//   G/2 scan warps  match positions as they appear (G lanes per trial, k_ref_match<T,G>'s scan),
+//                   each at its own pace.
+// A round then pays about max(rollout, scan) instead of their sum.  Needs N + 1 <= kPipeMaxSteps
+// (the host falls back to the two kernels otherwise).  A third stage for the step costs was measured
+// and dropped: one cost item is ~3-6 us of serial fp64 work, so hiding it takes >= 8 lanes per trial
+// at the rollout's register count, which no longer fits a benchmark round into one wave
+// (profiles/r01_pipeline_findings.txt).
+constexpr int kPipeTrials = 16;
+constexpr int kPipeMaxSteps = 128;
+constexpr unsigned kPipeBackoffNs = 100;  // waiting scan warps stay off the issue ports
+__host__ __device__ constexpr int pipe_threads(int G) { return 32 + kPipeTrials * G; }
+
+// G = scan lanes per trial: 16 (two blocks per SM) when the whole trial pool fits one wave that way,
+// 8 (four blocks per SM, a slower but still hidden scan) beyond that.
+template <typename T, int G>
+__global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_match(Dev<T> D, int B) {
+    __shared__ T pos[kPipeMaxSteps][kPipeTrials][2];
+    __shared__ int ready;  // positions of steps 0..ready are in the ring
+    const int N = D.N;
+    const size_t Bs = D.Bs, Vs = D.Vs;
+    const int count = view_count(D, 1, B);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool roller = warp == 0;
+    // rollout lanes: slot = lane / 2, role = lane & 1; scan lanes: slot = (32 / G) (warp - 1) + lane / G
+    const int role = lane & 1;
+    const int sub = lane % G;
+    const int grp_shift = lane - sub;
+    const unsigned grp_mask = ((1u << G) - 1u) << grp_shift;
+    const int slot = roller ? (lane >> 1) : ((warp - 1) * (32 / G) + lane / G);
+    for (int base = blockIdx.x * kPipeTrials; base < count; base += gridDim.x * kPipeTrials) {
+        const int v = base + slot;
+        const bool live = v < count;
+        const int vv = live ? v : count - 1;
+        const int b = D.t_inst[vv];
+        const DevParams<T>* Pp = D.P + D.tmpl[b];
+        if (threadIdx.x == 0) ready = -1;
+        __syncthreads();
+        if (roller) {
+            const T p_dt = Pp->dt, p_wb = Pp->wheelbase;
+            const int p_ref = Pp->ref_point;
+            const T alpha = T(1) / T(1 << D.t_aidx[vv]);
+            // lane `role` of a pair owns control row `role`: its feedback row, u and d
+            T xn[4], cx[4], cK[4], cu, cd;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                cx[c] = D.X[at(Bs, 0, c, 4, b)];
+                xn[c] = cx[c];
+            }
+            if (role == 0) {
+                pos[0][slot][0] = xn[0];
+                pos[0][slot][1] = xn[1];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                *(volatile int*)&ready = 0;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (live && role == 0) D.Xt[at(Vs, 0, c, 4, v)] = xn[c];
+            cu = D.U[at(Bs, 0, role, 2, b)];
+            cd = D.dg[at(Bs, 0, role, 2, b)];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cK[c] = D.Kg[at(Bs, 0, role * 4 + c, 8, b)];
+            for (int i = 0; i < N; ++i) {
+                T nxx[4], nxK[4], nxu, nxd;
+                const int ip = i + 1 < N ? i + 1 : i;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) nxx[c] = ld_early(D.X + at(Bs, ip, c, 4, b));
+                nxu = ld_early(D.U + at(Bs, ip, role, 2, b));
+                nxd = ld_early(D.dg + at(Bs, ip, role, 2, b));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) nxK[c] = ld_early(D.Kg + at(Bs, ip, role * 4 + c, 8, b));
+                T fb = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) fb += cK[c] * (xn[c] - cx[c]);
+                const T mine = (cu + fb) + alpha * cd;  // u'[role]
+                const T other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                const T acc = role ? other : mine, steer = role ? mine : other;
+                T s_head, c_head, turn;
+                if (p_ref == 0) {
+                    T sn, cs;
+                    m_sincos(role ? mine : xn[3], &sn, &cs);
+                    const T os = __shfl_xor_sync(0xffffffffu, sn, 1), oc = __shfl_xor_sync(0xffffffffu, cs, 1);
+                    s_head = role ? os : sn;
+                    c_head = role ? oc : cs;
+                    turn = (role ? sn : os) / (role ? cs : oc);
+                } else {
+                    const T beta = m_atan(tan_sc(steer) / 2);
+                    T sn, cs;
+                    m_sincos(role ? beta : beta + xn[3], &sn, &cs);
+                    const T os = __shfl_xor_sync(0xffffffffu, sn, 1), oc = __shfl_xor_sync(0xffffffffu, cs, 1);
+                    s_head = role ? os : sn;
+                    c_head = role ? oc : cs;
+                    turn = role ? sn : os;
+                }
+                T nx[4];
+                step_from_trig(xn, acc, p_dt, p_wb, p_ref, s_head, c_head, turn, nx);
+                // hand the position over first, then this step's global stores (the fence waits
+                // only for stores issued before it)
+                if (role == 0) {
+                    pos[i + 1][slot][0] = nx[0];
+                    pos[i + 1][slot][1] = nx[1];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    *(volatile int*)&ready = i + 1;
+                }
+                if (live) D.Ut[at(Vs, i, role, 2, v)] = mine;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    xn[c] = nx[c];
+                    if (live && role == 0) D.Xt[at(Vs, i + 1, c, 4, v)] = nx[c];
+                    cx[c] = nxx[c];
+                }
+                cu = nxu;
+                cd = nxd;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cK[c] = nxK[c];
+            }
+        } else {
+            const int M = Pp->wp_len;
+            const T* wx = D.wx + Pp->wp_off;
+            const T* wy = D.wy + Pp->wp_off;
+            int start = 0;
+            for (int k = 0; k <= N; ++k) {
+                while (*(volatile int*)&ready < k) __nanosleep(kPipeBackoffNs);
+                __threadfence_block();
+                const T px = pos[k][slot][0], py = pos[k][slot][1];
+                int found = -1;
+                bool done = !live;
+                while (!__all_sync(0xffffffffu, done)) {
+                    int j = start + sub;
+                    int jc = j < M ? j : M - 1;
+                    const T ex = px - __ldg(wx + jc), ey = py - __ldg(wy + jc);
+                    T dj = ex * ex + ey * ey;
+                    T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
+                    bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
+                    unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
+                    if (!done) {
+                        if (m) {
+                            found = start + (__ffs(m) - 1 - grp_shift);
+                            done = true;
+                        } else {
+                            start += G - 1;
+                        }
+                    }
+                }
+                if (live) {
+                    if (sub == 0) D.ridx_t[size_t(k) * Vs + v] = found;
+                    start = found;
+                }
+            }
+        }
+        __syncthreads();  // the ring is reused by the next group of trials
     }
 }
 
