@@ -50,6 +50,7 @@ struct Base {
     int run_ahead = 3;
     int prefetch_below = 16384;  // batches up to this size use the latency-regime kernel variants (measured crossover ~16-18k)
     int bench_prefetch = 0;
+    unsigned scan_epoch = 0;  // tags the look-back words of one verdict launch (never 0, 30 bits)
     int pipeline = 1;  // latency regime: rollout and waypoint match as one two-stage kernel
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
@@ -57,7 +58,7 @@ struct Base {
     std::vector<int> prof_stage;  // stage id that starts at event i (-1 = end marker)
     double stage_ms[6] = {0, 0, 0, 0, 0, 0};
     int stage_launches[6] = {0, 0, 0, 0, 0, 0};
-    volatile int* h_ctl = nullptr;  // mapped pinned: [0] rounds completed, [1] instances active after it
+    volatile int* h_ctl = nullptr;  // mapped pinned, read as one 64-bit word: rounds completed << 32 | instances active after it
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     double* stage = nullptr;  // device staging in host layout
     size_t stage_bytes = 0;
@@ -247,8 +248,8 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         int r;
         {
             int* hc = nullptr;
-            CK(cudaHostAlloc(&hc, 2 * sizeof(int), cudaHostAllocMapped));
-            hc[0] = hc[1] = 0;
+            CK(cudaHostAlloc(&hc, 4 * sizeof(int), cudaHostAllocMapped));
+            hc[0] = hc[1] = hc[2] = hc[3] = 0;
             h->h_ctl = hc;
             int* dc = nullptr;
             CK(cudaHostGetDevicePointer(&dc, hc, 0));
@@ -282,6 +283,8 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.t_count, Bs))) return r;
         if ((r = dalloc(h, &D.commit_src, Bs))) return r;
         if ((r = dalloc(h, &D.wide, Bs))) return r;
+        if ((r = dalloc(h, &D.act, 2 * Bs))) return r;
+        if ((r = dalloc(h, &D.scan_state, Bs / 128 + 1))) return r;
         if ((r = dalloc(h, &D.rec, size_t(N + 1) * kRecFields * Bs))) return r;
         if ((r = dalloc(h, &D.Kg, size_t(N) * 8 * Bs))) return r;
         if ((r = dalloc(h, &D.dg, size_t(N) * 2 * Bs))) return r;
@@ -337,6 +340,8 @@ inline dim3 grid2(int B, int rows) { return dim3((B + 127) / 128, rows); }
 // grid-stride launches: enough CTAs for `count` items, capped at a multiple of the 148 SMs
 inline dim3 gs1(int count) { return dim3(std::max(1, std::min((count + 127) / 128, kGridCap))); }
 inline dim3 gs2(int count, int rows) { return dim3(std::max(1, std::min((count + 127) / 128, kGridCap)), rows); }
+// step-parallel stages (k_cost, k_derivs): x = step, y = blocks of trajectories
+inline dim3 gk(int count, int rows) { return dim3(rows, std::max(1, std::min((count + 127) / 128, kGridCap))); }
 
 template <typename... KArgs, typename... Args>
 inline void launch_kernel(Base* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args&&... args) {
@@ -516,24 +521,25 @@ inline void mark_stage(Base* h, int id) {
     h->prof_stage.push_back(id);
 }
 
+// `count`: an upper bound of the trajectories the launch has to cover (all B instances, or the slots of
+// the trial pool that can be in use this round); `lat`: latency-regime kernel variants.
 template <typename T>
-void launch_cost(Impl<T>* h, int B, int trial, bool matched = false) {
-    const int cap = trial ? h->D.Vs : B;
+void launch_cost(Impl<T>* h, int B, int trial, int count, bool lat, bool matched = false) {
     if (trial) mark_stage(h, 3);
     // waypoint scan window: 16 lanes per trajectory while the batch is latency-bound (one probe
     // usually covers a step's advance), 8 lanes in the throughput regime
     if (matched) {
         // k_rollout_match already wrote the matches of the trial pool
-    } else if (B <= h->prefetch_below) {
-        LAUNCH(h, (k_ref_match<T, 16>), gs1(cap * 16), 128, h->D, B, trial);
+    } else if (lat) {
+        LAUNCH(h, (k_ref_match<T, 16>), gs1(count * 16), 128, h->D, B, trial);
     } else {
-        LAUNCH(h, (k_ref_match<T, 8>), gs1(cap * 8), 128, h->D, B, trial);
+        LAUNCH(h, (k_ref_match<T, 8>), gs1(count * 8), 128, h->D, B, trial);
     }
     if (trial) mark_stage(h, 4);
-    if (B <= h->prefetch_below) {
-        LAUNCH(h, (k_cost<T, 7>), gs2(cap, h->N + 1), 128, h->D, B, trial);
+    if (lat) {
+        LAUNCH(h, (k_cost<T, 7>), gk(count, h->N + 1), 128, h->D, B, trial);
     } else {
-        LAUNCH(h, (k_cost<T, 8>), gs2(cap, h->N + 1), 128, h->D, B, trial);
+        LAUNCH(h, (k_cost<T, 8>), gk(count, h->N + 1), 128, h->D, B, trial);
     }
 }
 
@@ -544,61 +550,75 @@ int do_solve_resident(Impl<T>* h, int B) {
     const int N = h->N;
     h->launches = 0;
     CK(cudaStreamSynchronize(h->stream));
-    h->h_ctl[0] = 0;
-    h->h_ctl[1] = B;
+    // progress words written by the verdict kernel: [0] rounds completed << 32 | instances running,
+    // [1] rounds completed << 32 | entries on the next round's work list
+    volatile unsigned long long* progress = reinterpret_cast<volatile unsigned long long*>(h->h_ctl);
+    progress[0] = static_cast<unsigned long long>(unsigned(B));
+    progress[1] = static_cast<unsigned long long>(unsigned(B));
     CK(cudaMemsetAsync(h->D.ctl, 0, CTL_WORDS * sizeof(int), h->stream));
     LAUNCH(h, k_init<T>, gs1(B), 128, h->D, B, -1, 1);
-    launch_cost(h, B, 0);
+    launch_cost(h, B, 0, B, B <= h->prefetch_below);
     LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 0);
     // One round = one line-search step for every running instance.  The verdict kernel publishes
-    // (rounds completed, instances still running) into mapped host memory; the host keeps at most
-    // run_ahead rounds queued beyond the last count it has seen and stops at zero.
+    // (rounds completed, instances still running, length of the next work list) into mapped host
+    // memory; the host keeps at most run_ahead rounds queued beyond the last count it has seen and
+    // stops at zero.  Work lists only ever shrink, so the last length the host has seen bounds every
+    // later round: it sizes the grids (no tail of empty CTAs once most instances are done) and picks
+    // the kernel variants (all variants of a stage return the same bits, so a big batch switches to
+    // the latency-regime kernels for its stragglers).
     int launched = 0;
-    const int trial_cap = h->D.Vs;
     while (launched < h->max_rounds) {
-        int done = h->h_ctl[0];
-        if (done > 0 && h->h_ctl[1] == 0) break;
+        const unsigned long long w = progress[0];
+        const int done = int(w >> 32);
+        if (done > 0 && unsigned(w) == 0u) break;
         if (launched - done > h->run_ahead) continue;  // spin on the mapped words
+        const int n_bound = std::max(1, std::min(B, int(unsigned(progress[1]))));
+        const int trial_bound = int(std::min<long long>(h->D.Vs, (long long)n_bound * kNumAlphas));
+        const bool lat = n_bound <= h->prefetch_below;
+        const int par = launched & 1;  // which of the two work lists this round reads
         mark_stage(h, 0);
-        if (B <= h->prefetch_below) {
-            LAUNCH(h, (k_derivs<T, -1>), gs2(B, 2 * (N + 1)), 128, h->D, B, 1);
+        if (lat) {
+            LAUNCH(h, (k_derivs<T, -1>), gk(n_bound, 2 * (N + 1)), 128, h->D, B, 1, par);
         } else {
-            LAUNCH(h, (k_derivs<T, 0>), gs2(B, N + 1), 128, h->D, B, 1);
-            LAUNCH(h, (k_derivs<T, 1>), gs2(B, N + 1), 128, h->D, B, 1);
+            LAUNCH(h, (k_derivs<T, 0>), gk(n_bound, N + 1), 128, h->D, B, 1, par);
+            LAUNCH(h, (k_derivs<T, 1>), gk(n_bound, N + 1), 128, h->D, B, 1, par);
         }
         if (h->any_alm) {
-            LAUNCH(h, (k_cost<T, 7>), gs2(B, N + 1), 128, h->D, B, 0);
+            LAUNCH(h, (k_cost<T, 7>), gk(B, N + 1), 128, h->D, B, 0);
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
         mark_stage(h, 1);
-        if (B <= h->prefetch_below) {
-            LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 1);
+        if (lat) {
+            // a short work list is spread over one warp per scheduler (see k_backward)
+            LAUNCH(h, (k_backward<T, true>), gs1(std::max(n_bound, 148 * 128)), 128, h->D, B, 1, par);
         } else {
-            LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 1);
+            LAUNCH(h, (k_backward<T, false>), gs1(n_bound), 128, h->D, B, 1, par);
         }
         mark_stage(h, 2);
-        const bool piped = B <= h->prefetch_below && h->pipeline && N + 1 <= kPipeMaxSteps;
+        const bool piped = lat && h->pipeline && N + 1 <= kPipeMaxSteps;
         if (piped) {
-            const int blocks = std::max(1, std::min((trial_cap + kPipeTrials - 1) / kPipeTrials, kGridCap));
+            const int blocks = std::max(1, std::min((trial_bound + kPipeTrials - 1) / kPipeTrials, kGridCap));
             // 16 scan lanes per trial when the whole trial pool fits one wave at two blocks per SM
-            const bool narrow = h->pipeline == 8 || (h->pipeline == 1 && trial_cap > 2 * 148 * kPipeTrials);
+            const bool narrow = h->pipeline == 8 || (h->pipeline == 1 && trial_bound > 2 * 148 * kPipeTrials);
             if (narrow) {
                 LAUNCH(h, (k_rollout_match<T, 8>), dim3(blocks), pipe_threads(8), h->D, B);
             } else {
                 LAUNCH(h, (k_rollout_match<T, 16>), dim3(blocks), pipe_threads(16), h->D, B);
             }
-        } else if (B <= h->prefetch_below) {
-            LAUNCH(h, k_forward2<T>, gs1(2 * trial_cap), 128, h->D, B);  // two lanes per trial slot
+        } else if (lat) {
+            LAUNCH(h, k_forward2<T>, gs1(2 * trial_bound), 128, h->D, B);  // two lanes per trial slot
         } else {
-            LAUNCH(h, k_forward<T>, gs1(trial_cap), 128, h->D, B, 1);
+            LAUNCH(h, k_forward<T>, gs1(trial_bound), 128, h->D, B, 1);
         }
-        launch_cost(h, B, 1, piped);
+        launch_cost(h, B, 1, trial_bound, lat, piped);
         mark_stage(h, 5);
-        LAUNCH(h, k_decide<T>, gs1(B), 128, h->D, B);
+        h->scan_epoch = (h->scan_epoch % 0x3fffffffu) + 1u;
+        LAUNCH(h, k_decide<T>, gs1(n_bound), 128, h->D, B, par, h->scan_epoch);
         mark_stage(h, -1);
         ++launched;
     }
-    LAUNCH(h, (k_derivs<T, -1>), gs2(B, 2 * (N + 1)), 128, h->D, B, 1);  // commit a step accepted in the last round
+    // commit a step accepted in the last round
+    LAUNCH(h, (k_derivs<T, -1>), gk(B, 2 * (N + 1)), 128, h->D, B, 1, launched & 1);
     LAUNCH(h, k_store_last_u<T>, gs2(B, N), 128, h->D, B);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -733,7 +753,7 @@ int stage_cost(Impl<T>* h, int B, const double* u, const double* x, const double
     if ((rc = upload_problem_data(h, B, ref_velo, borders, tmpl, n_obs, obs, obs_len))) return rc;
     if ((rc = load_traj(h, B, u, x))) return rc;
     if ((rc = load_alm(h, B, alm_mu, alm_rho))) return rc;
-    launch_cost(h, B, 0);
+    launch_cost(h, B, 0, B, B <= h->prefetch_below);
     LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 0);
     if ((rc = unpack_to_host(h, h->D.J_cur, J_out, B, 1))) return rc;
     if ((rc = unpack_to_host(h, h->D.sc, step_cost_out, B, h->N + 1))) return rc;
@@ -755,7 +775,7 @@ int stage_derivs(Impl<T>* h, int B, const double* u, const double* x, const doub
     if ((rc = load_alm(h, B, alm_mu, alm_rho))) return rc;
     constexpr int G = 8;
     LAUNCH(h, k_ref_match<T, G>, gs1(B * G), 128, h->D, B, 0);
-    LAUNCH(h, (k_derivs<T, -1>), gs2(B, 2 * (N + 1)), 128, h->D, B, 0);
+    LAUNCH(h, (k_derivs<T, -1>), gk(B, 2 * (N + 1)), 128, h->D, B, 0, 0);
     // dense conversion on device into a temporary allocation (test path; not part of create-time budget)
     size_t n_lx = size_t(B) * (N + 1) * 4, n_lu = size_t(B) * N * 2, n_lxx = size_t(B) * (N + 1) * 16,
            n_luu = size_t(B) * N * 4, n_A = size_t(B) * N * 16, n_B = size_t(B) * N * 8;
@@ -818,7 +838,7 @@ int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const 
         cudaFree(tmp);
         return rc;
     }
-    LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0);
+    LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
     e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(CILQR_ERR_CUDA, "stage_backward: %s", cudaGetErrorString(e));
@@ -866,9 +886,9 @@ int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float
         }
         CK(cudaEventRecord(h->t0, h->stream));
         if (h->bench_prefetch) {
-            LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0);
+            LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0, 0);
         } else {
-            LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0);
+            LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
         }
         CK(cudaEventRecord(h->t1, h->stream));
         CK(cudaEventSynchronize(h->t1));

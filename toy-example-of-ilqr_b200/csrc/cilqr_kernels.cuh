@@ -43,7 +43,12 @@ enum Phase : int { PH_BACKWARD = 0, PH_SEARCH = 1, PH_DONE = 2 };
 enum Status : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BWD_FAIL = 2, ST_FWD_FAIL = 3, ST_SMALL_STEP = 4 };
 enum ExitReason : int { EX_MAX_ITER = 0, EX_CONVERGED = 1, EX_MAX_LAMB = 2 };
 // device-side loop control words
-enum Ctl : int { CTL_NV = 0, CTL_ACTIVE = 1, CTL_TICKET = 2, CTL_ROUND = 3, CTL_TRIALS = 4, CTL_WORDS = 8 };
+enum Ctl : int {
+    CTL_NV = 0, CTL_ACTIVE = 1, CTL_TICKET = 2, CTL_ROUND = 3, CTL_TRIALS = 4,
+    CTL_NACT = 5,   // [2] entries in the two work lists (round parity)
+    CTL_CHUNK = 7,  // next chunk of the work list to hand out in the verdict kernel
+    CTL_WORDS = 16
+};
 
 // Everything a kernel needs, passed by value.
 template <typename T>
@@ -100,6 +105,12 @@ struct Dev {
     int* exit_reason;
     int* rec_valid;
     int* wide;
+    // work lists, [2][Bs]: the instances round r has to touch are act[(r & 1) * Bs + 0 .. ctl[CTL_NACT + (r & 1)]),
+    // in increasing instance order (so a warp's accesses stay as coalesced as the survivors allow);
+    // the verdict kernel of round r filters its list into the one of round r + 1 (stable, single
+    // pass: per-chunk counts chained through scan_state with decoupled look-back)
+    int* act;
+    unsigned long long* scan_state;  // [Bs / 128 + 1]  epoch << 34 | flag << 32 | count
     T* last_u;   // [N][2][Bs]
     int* first;  // [Bs]
     // augmented-Lagrangian state (allocated only when a template asks for it)
@@ -108,7 +119,7 @@ struct Dev {
     T* rho;      // [Bs]
     // loop control
     int* ctl;             // [CTL_WORDS]
-    volatile int* h_ctl;  // mapped pinned host words: [0] rounds completed, [1] active after that round
+    volatile int* h_ctl;  // mapped pinned host memory, two 64-bit words: rounds completed << 32 | {instances running, next list length}
     // optional per-iteration trace, [trace_cap][Bs]
     int* tr_status;
     int* tr_alpha;
@@ -204,6 +215,12 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
             D.t_count[b] = 0;
             D.dV[b] = 0;
             D.dV[Bs + b] = 0;
+            // round 0 works on every instance
+            D.act[b] = b;
+            if (b == 0) {
+                D.ctl[CTL_NACT + 0] = B;
+                D.ctl[CTL_NACT + 1] = 0;
+            }
         }
     }
 }
@@ -367,8 +384,10 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int t
     const View<T> V = view_of(D, trial);
     const int count = view_count(D, trial, B);
     const int N = D.N;
-    const int k = blockIdx.y;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += gridDim.x * blockDim.x) {
+    // grid: x = step, y = blocks of trajectories (so the blocks that have work are dispatched first
+    // when only the head of the trial pool is in use)
+    const int k = blockIdx.x;
+    for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < count; v += gridDim.y * blockDim.x) {
         const int b = V.inst ? V.inst[v] : v;
         const T cost = step_cost_of(D, V, b, v, k, V.ridx[size_t(k) * V.stride + v]);
         V.sc[size_t(k) * V.stride + v] = cost;
@@ -430,16 +449,21 @@ __device__ __forceinline__ void constraint_weights(bool alm, T c, T q1, T q2, T 
 //     cache rule for rejected steps (cpp:469-474).
 // ---------------------------------------------------------------------------
 template <typename T, int kPart>
-__global__ void __launch_bounds__(128, kPart < 0 ? 4 : 8) k_derivs(Dev<T> D, int B, int masked) {
+__global__ void __launch_bounds__(128, kPart < 0 ? 4 : 8) k_derivs(Dev<T> D, int B, int masked, int par) {
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
     // two independent halves per (instance, step): part 0 = state terms (l_x, l_xx), part 1 = control
     // terms and model Jacobians (l_u, l_uu, A, B).  kPart < 0: one launch, the half taken from
     // blockIdx.y (latency-bound batches: one launch less per round).  kPart = 0 / 1: one launch per
     // half, so that each half gets its own register budget and occupancy (throughput regime).
-    const int k = kPart < 0 ? int(blockIdx.y >> 1) : int(blockIdx.y);
-    const int part = kPart < 0 ? int(blockIdx.y & 1) : kPart;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    // grid: x = step (and half), y = blocks of work-list entries
+    const int k = kPart < 0 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int part = kPart < 0 ? int(blockIdx.x & 1) : kPart;
+    // solver: only the instances on this round's work list (running, or with a step to commit)
+    const int* list = masked ? D.act + size_t(par) * Bs : nullptr;
+    const int n = masked ? D.ctl[CTL_NACT + par] : B;
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n; idx += gridDim.y * blockDim.x) {
+        const int b = list ? list[idx] : idx;
         T x[4], ua = 0, us = 0;
         int ri = 0;
         const int src = masked ? D.commit_src[b] : -1;
@@ -805,12 +829,24 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
 //     for this round (warp-aggregated, one atomic per warp).
 // ---------------------------------------------------------------------------
 template <typename T, bool kPrefetch>
-__global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver) {
+__global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver, int par) {
     const int lane = threadIdx.x & 31;
     const int n_threads = gridDim.x * blockDim.x;
-    const int rounds = (B + n_threads - 1) / n_threads;
-    for (int it = 0, b = blockIdx.x * blockDim.x + threadIdx.x; it < rounds; ++it, b += n_threads) {
-        const bool in = b < B;
+    // solver: only the instances on this round's work list
+    const int* list = solver ? D.act + size_t(par) * D.Bs : nullptr;
+    const int n = solver ? D.ctl[CTL_NACT + par] : B;
+    // a short list is spread over all warps of the grid (lpw consecutive entries per warp) instead of
+    // filling a few warps: the chain latency is the same and the scattered loads of a sparse list
+    // do not queue up in a handful of SMs
+    const int n_warps = n_threads >> 5;
+    int lpw = (n + n_warps - 1) / n_warps;
+    lpw = lpw < 1 ? 1 : (lpw > 32 ? 32 : lpw);
+    const int per_pass = n_warps * lpw;
+    const int rounds = (n + per_pass - 1) / per_pass;
+    const int first_idx = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lpw + lane;
+    for (int it = 0, idx = first_idx; it < rounds; ++it, idx += per_pass) {
+        const bool in = lane < lpw && idx < n;
+        const int b = in ? (list ? list[idx] : idx) : 0;
         int want = 0, a0 = 0;
         if (in) {
             if (!solver) {
@@ -1212,16 +1248,39 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
 // ---------------------------------------------------------------------------
 // K7  the line-search verdict of iter_step (cpp:356-380) over the slots each
 //     searching instance evaluated this round, in alpha order, then solve()'s
-//     bookkeeping.  The last block to finish publishes the number of instances
-//     still running to the host and re-arms the round counters.
+//     bookkeeping.  The same pass filters the round's work list into the next
+//     round's (instances still running, plus finished ones whose last accepted
+//     step the derivative stage has yet to commit), keeping instance order: a
+//     block handles chunks of 128 list entries, scans its survivors, and chains
+//     its count to the preceding chunks' through scan_state (decoupled
+//     look-back; chunks are handed out by ticket, so a chunk only ever waits on
+//     chunks whose blocks are already running).  The last block to finish
+//     publishes progress to the host and re-arms the round counters.
 // ---------------------------------------------------------------------------
+constexpr unsigned long long kScanAgg = 1ull << 32, kScanIncl = 2ull << 32;
+__device__ __forceinline__ unsigned long long scan_word(unsigned epoch, unsigned long long flag, int value) {
+    return (static_cast<unsigned long long>(epoch) << 34) | flag | unsigned(value);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B) {
+__global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsigned epoch) {
     const size_t Bs = D.Bs, Vs = D.Vs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_chunk, s_excl, s_wsum[4], s_active, s_trials;
+    const int* list = D.act + size_t(par) * Bs;
+    int* next_list = D.act + size_t(par ^ 1) * Bs;
+    volatile unsigned long long* state = D.scan_state;
+    const int n = D.ctl[CTL_NACT + par];
+    const int n_chunks = (n + int(blockDim.x) - 1) / int(blockDim.x);
     int my_active = 0, my_trials = 0;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-        int ph = D.phase[b];
-        const int cnt = D.t_count[b];
+    if (threadIdx.x == 0) s_chunk = atomicAdd(&D.ctl[CTL_CHUNK], 1);
+    __syncthreads();
+    for (int chunk = s_chunk; chunk < n_chunks; chunk += gridDim.x) {
+        const int idx = chunk * int(blockDim.x) + int(threadIdx.x);
+        const bool in = idx < n;
+        const int b = in ? list[idx] : 0;
+        int ph = in ? D.phase[b] : PH_DONE;
+        const int cnt = in ? D.t_count[b] : 0;
         if (ph == PH_SEARCH && cnt > 0) {
             const DevParams<T>& P = D.P[D.tmpl[b]];
             const int v0 = D.t_first[b];
@@ -1275,9 +1334,47 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B) {
             ph = D.phase[b];
         }
         my_active += ph != PH_DONE;
+        // survivors of this chunk, in list order
+        const bool keep = in && (ph != PH_DONE || D.commit_src[b] >= 0);
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wsum[warp] = __popc(km);
+        __syncthreads();
+        int rank = __popc(km & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) rank += s_wsum[w];
+        if (warp == 0) {
+            const int total = s_wsum[0] + s_wsum[1] + s_wsum[2] + s_wsum[3];
+            int excl = 0;
+            if (chunk > 0) {
+                if (lane == 0) state[chunk] = scan_word(epoch, kScanAgg, total);
+                // look back over the preceding chunks, 32 at a time, nearest first
+                for (int look = chunk - 1;; look -= 32) {
+                    const int j = look - lane;
+                    unsigned long long v = scan_word(epoch, kScanIncl, 0);  // in front of chunk 0
+                    if (j >= 0) {
+                        do {
+                            v = state[j];
+                        } while (unsigned(v >> 34) != epoch);
+                    }
+                    const unsigned incl = __ballot_sync(0xffffffffu, (v & kScanIncl) != 0);
+                    const int upto = incl ? __ffs(incl) - 1 : 31;  // nearest chunk holding an inclusive prefix
+                    int val = lane <= upto ? int(unsigned(v)) : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                    excl += val;
+                    if (incl) break;
+                }
+            }
+            if (lane == 0) {
+                state[chunk] = scan_word(epoch, kScanIncl, excl + total);
+                s_excl = excl;
+                if (chunk == n_chunks - 1) D.ctl[CTL_NACT + (par ^ 1)] = excl + total;
+            }
+        }
+        __syncthreads();
+        if (keep) next_list[s_excl + rank] = b;
+        __syncthreads();  // s_wsum / s_excl are reused by the next chunk
     }
     // block-level count, then one atomic per block
-    __shared__ int s_active, s_trials;
     if (threadIdx.x == 0) s_active = s_trials = 0;
     __syncthreads();
 #pragma unroll
@@ -1285,28 +1382,34 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B) {
         my_active += __shfl_down_sync(0xffffffffu, my_active, o);
         my_trials += __shfl_down_sync(0xffffffffu, my_trials, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         atomicAdd(&s_active, my_active);
         atomicAdd(&s_trials, my_trials);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        atomicAdd(&D.ctl[CTL_ACTIVE], s_active);
-        atomicAdd(&D.ctl[CTL_TRIALS], s_trials);
+        if (s_active) atomicAdd(&D.ctl[CTL_ACTIVE], s_active);
+        if (s_trials) atomicAdd(&D.ctl[CTL_TRIALS], s_trials);
         __threadfence();
         int ticket = atomicAdd(&D.ctl[CTL_TICKET], 1);
         if (ticket == int(gridDim.x) - 1) {
             __threadfence();
-            int active = atomicAdd(&D.ctl[CTL_ACTIVE], 0);
-            int round = D.ctl[CTL_ROUND] + 1;
+            const int active = atomicAdd(&D.ctl[CTL_ACTIVE], 0);
+            const int n_next = atomicAdd(&D.ctl[CTL_NACT + (par ^ 1)], 0);
+            const int round = D.ctl[CTL_ROUND] + 1;
             D.ctl[CTL_ROUND] = round;
             D.ctl[CTL_ACTIVE] = 0;
             D.ctl[CTL_NV] = 0;
             D.ctl[CTL_TICKET] = 0;
-            D.h_ctl[1] = active;
-            __threadfence_system();
-            D.h_ctl[0] = round;
-            __threadfence_system();
+            D.ctl[CTL_CHUNK] = 0;
+            D.ctl[CTL_NACT + par] = 0;  // consumed; the verdict kernel of the next round refills it
+            // two independent 64-bit words (rounds completed << 32 | instances still running, and
+            // rounds completed << 32 | length of the next work list): the host reads each with one
+            // load and either may be stale (both counts only ever shrink), so no system-scope fence
+            // has to order them
+            volatile unsigned long long* hw = reinterpret_cast<volatile unsigned long long*>(D.h_ctl);
+            hw[1] = (static_cast<unsigned long long>(unsigned(round)) << 32) | unsigned(n_next);
+            hw[0] = (static_cast<unsigned long long>(unsigned(round)) << 32) | unsigned(active);
         }
     }
 }
