@@ -160,19 +160,24 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *  CILQR_OPT_PREFETCH_BELOW (default 16384, the measured crossover): batches up to this size run the backward pass
  *      with next-step operands prefetched into registers (latency-bound regime); larger
  *      batches use the leaner streaming variant (bandwidth-bound regime).
- *  CILQR_OPT_BENCH_PREFETCH (default 0): which of the two cilqr_b200_bench_backward times.
+ *  CILQR_OPT_BENCH_PREFETCH (default 0): which backward kernel cilqr_b200_bench_backward times and
+ *      cilqr_b200_stage_backward runs: 0 streaming, 1 register prefetch, 2 staged (below).
  *  CILQR_OPT_PROFILE_STAGES (default 0): record a CUDA event in front of every stage launch of the
  *      following solves (adds a few microseconds per round; not for timed runs).
  *  CILQR_OPT_PIPELINE (default 1): latency-bound batches run forward_pass and the waypoint match
  *      of the new trajectory as one two-stage kernel (the match trails the rollout through a
- *      shared-memory ring); 0 runs them as two kernels; 8 / 16 force the scan window. */
+ *      shared-memory ring); 0 runs them as two kernels; 8 / 16 force the scan window.
+ *  CILQR_OPT_STAGED_BACKWARD (default 1): latency-bound batches run the backward pass with one warp
+ *      per tile of 32 instances, each step's record brought into a shared-memory ring by bulk
+ *      asynchronous copies (cp.async.bulk + mbarrier) three steps ahead of the recursion. */
 typedef enum cilqr_option_t {
     CILQR_OPT_WIDE_SEARCH = 0,
     CILQR_OPT_RUN_AHEAD = 1,
     CILQR_OPT_PREFETCH_BELOW = 2,
     CILQR_OPT_BENCH_PREFETCH = 3,
     CILQR_OPT_PROFILE_STAGES = 4,
-    CILQR_OPT_PIPELINE = 5
+    CILQR_OPT_PIPELINE = 5,
+    CILQR_OPT_STAGED_BACKWARD = 6
 } cilqr_option_t;
 int cilqr_b200_set_option(cilqr_handle_t* h, int option, int value);
 

@@ -7,18 +7,27 @@ import numpy as np
 import cilqr_b200 as cb
 import cilqr_b200.binding as bd
 
-cfgs = [a.split(":") for a in sys.argv[1:]] or [["C1", "4096", "f64"]]
+# --sets "6=1;6=0": option sets (id=value,...) to run the main library with, one line each
+sets = [""]
+args = sys.argv[1:]
+if "--sets" in args:
+    i = args.index("--sets")
+    sets = args[i + 1].split(";")
+    del args[i:i + 2]
+cfgs = [a.split(":") for a in args] or [["C1", "4096", "f64"]]
 main_lib = bd.LIB_PATH
-libs = sorted(glob.glob(os.path.join(os.path.dirname(main_lib), "libvariant_*.so"))) + [main_lib]
+libs = [(l, "") for l in sorted(glob.glob(os.path.join(os.path.dirname(main_lib), "libvariant_*.so")))] + [(main_lib, o) for o in sets]
 for cfg, B, dt in cfgs:
     B = int(B)
     N = 100 if cfg == "C2" else 50
     pb = cb.synthetic_batch(cfg, B, N=N)
     first = None
-    for lib in libs:
+    for lib, opts in libs:
         bd._lib = None
         bd.LIB_PATH = lib
         with cb.BatchSolver(pb.templates, B, N, pb.max_obs, dt) as s:
+            for kv in filter(None, opts.split(",")):
+                s.set_option(int(kv.split("=")[0]), int(kv.split("=")[1]))
             s.upload(pb)
             ts = []
             for _ in range(5):
@@ -33,6 +42,6 @@ for cfg, B, dt in cfgs:
             first = out
         same = all(np.array_equal(np.asarray(getattr(first, f)), np.asarray(getattr(out, f)), equal_nan=True)
                    for f in ("u", "x", "iters", "status"))
-        print("%-26s %s B=%d N=%d %s: solve %.2f ms (median %.2f) %.2f M iter/s rounds %d  us/launch: %s  same_bits=%s"
-              % (os.path.basename(lib), cfg, B, N, dt, min(ts) * 1e3, np.median(ts) * 1e3,
+        print("%-20s %-8s %s B=%d N=%d %s: solve %.2f ms (median %.2f) %.2f M iter/s rounds %d  us/launch: %s  same_bits=%s"
+              % (os.path.basename(lib), opts, cfg, B, N, dt, min(ts) * 1e3, np.median(ts) * 1e3,
                  out.iters.sum() / min(ts) / 1e6, c["rounds"], per, same), flush=True)

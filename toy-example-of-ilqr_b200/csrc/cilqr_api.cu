@@ -52,6 +52,7 @@ struct Base {
     int bench_prefetch = 0;
     unsigned scan_epoch = 0;  // tags the look-back words of one verdict launch (never 0, 30 bits)
     int pipeline = 1;  // latency regime: rollout and waypoint match as one two-stage kernel
+    int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
@@ -340,6 +341,8 @@ inline dim3 grid2(int B, int rows) { return dim3((B + 127) / 128, rows); }
 // grid-stride launches: enough CTAs for `count` items, capped at a multiple of the 148 SMs
 inline dim3 gs1(int count) { return dim3(std::max(1, std::min((count + 127) / 128, kGridCap))); }
 inline dim3 gs2(int count, int rows) { return dim3(std::max(1, std::min((count + 127) / 128, kGridCap)), rows); }
+// k_backward_staged: one warp per tile of 32 instances, at most 16 warps per SM
+inline dim3 staged_grid(int B) { return dim3(std::max(1, std::min((B + 31) / 32, 148 * 16))); }
 // step-parallel stages (k_cost, k_derivs): x = step, y = blocks of trajectories
 inline dim3 gk(int count, int rows) { return dim3(rows, std::max(1, std::min((count + 127) / 128, kGridCap))); }
 
@@ -349,6 +352,17 @@ inline void launch_kernel(Base* h, void (*kernel)(KArgs...), dim3 grid, dim3 blo
     h->launches++;
 }
 #define LAUNCH(h, kernel, grid, block, ...) launch_kernel(h, kernel, grid, block, __VA_ARGS__)
+// cost / derivative kernels: the ALM paths are compiled in only when a template asks for them
+#define LAUNCH_COST(h, minb, grid, ...)                                     \
+    do {                                                                    \
+        if ((h)->any_alm) LAUNCH(h, (k_cost<T, minb, true>), grid, 128, __VA_ARGS__);  \
+        else LAUNCH(h, (k_cost<T, minb, false>), grid, 128, __VA_ARGS__);   \
+    } while (0)
+#define LAUNCH_DERIVS(h, part, grid, ...)                                   \
+    do {                                                                    \
+        if ((h)->any_alm) LAUNCH(h, (k_derivs<T, part, true>), grid, 128, __VA_ARGS__);  \
+        else LAUNCH(h, (k_derivs<T, part, false>), grid, 128, __VA_ARGS__); \
+    } while (0)
 
 // host layout (double [B][E_src rows]) -> device SoA, chunked through the staging buffer.
 // rows_src/rows_dst/inner: when the source has more rows per block than the destination keeps
@@ -537,9 +551,9 @@ void launch_cost(Impl<T>* h, int B, int trial, int count, bool lat, bool matched
     }
     if (trial) mark_stage(h, 4);
     if (lat) {
-        LAUNCH(h, (k_cost<T, 7>), gk(count, h->N + 1), 128, h->D, B, trial);
+        LAUNCH_COST(h, 7, gk(count, h->N + 1), h->D, B, trial);
     } else {
-        LAUNCH(h, (k_cost<T, 8>), gk(count, h->N + 1), 128, h->D, B, trial);
+        LAUNCH_COST(h, 8, gk(count, h->N + 1), h->D, B, trial);
     }
 }
 
@@ -578,17 +592,20 @@ int do_solve_resident(Impl<T>* h, int B) {
         const int par = launched & 1;  // which of the two work lists this round reads
         mark_stage(h, 0);
         if (lat) {
-            LAUNCH(h, (k_derivs<T, -1>), gk(n_bound, 2 * (N + 1)), 128, h->D, B, 1, par);
+            LAUNCH_DERIVS(h, -1, gk(n_bound, 2 * (N + 1)), h->D, B, 1, par);
         } else {
-            LAUNCH(h, (k_derivs<T, 0>), gk(n_bound, N + 1), 128, h->D, B, 1, par);
-            LAUNCH(h, (k_derivs<T, 1>), gk(n_bound, N + 1), 128, h->D, B, 1, par);
+            LAUNCH_DERIVS(h, 0, gk(n_bound, N + 1), h->D, B, 1, par);
+            LAUNCH_DERIVS(h, 1, gk(n_bound, N + 1), h->D, B, 1, par);
         }
         if (h->any_alm) {
-            LAUNCH(h, (k_cost<T, 7>), gk(B, N + 1), 128, h->D, B, 0);
+            LAUNCH_COST(h, 7, gk(B, N + 1), h->D, B, 0);
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
         mark_stage(h, 1);
-        if (lat) {
+        if (lat && h->staged && B <= h->prefetch_below) {
+            // small batch: one warp per tile of 32 instances, records staged through shared memory
+            LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 1);
+        } else if (lat) {
             // a short work list is spread over one warp per scheduler (see k_backward)
             LAUNCH(h, (k_backward<T, true>), gs1(std::max(n_bound, 148 * 128)), 128, h->D, B, 1, par);
         } else {
@@ -618,7 +635,7 @@ int do_solve_resident(Impl<T>* h, int B) {
         ++launched;
     }
     // commit a step accepted in the last round
-    LAUNCH(h, (k_derivs<T, -1>), gk(B, 2 * (N + 1)), 128, h->D, B, 1, launched & 1);
+    LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 1, launched & 1);
     LAUNCH(h, k_store_last_u<T>, gs2(B, N), 128, h->D, B);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -775,7 +792,7 @@ int stage_derivs(Impl<T>* h, int B, const double* u, const double* x, const doub
     if ((rc = load_alm(h, B, alm_mu, alm_rho))) return rc;
     constexpr int G = 8;
     LAUNCH(h, k_ref_match<T, G>, gs1(B * G), 128, h->D, B, 0);
-    LAUNCH(h, (k_derivs<T, -1>), gk(B, 2 * (N + 1)), 128, h->D, B, 0, 0);
+    LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 0, 0);
     // dense conversion on device into a temporary allocation (test path; not part of create-time budget)
     size_t n_lx = size_t(B) * (N + 1) * 4, n_lu = size_t(B) * N * 2, n_lxx = size_t(B) * (N + 1) * 16,
            n_luu = size_t(B) * N * 4, n_A = size_t(B) * N * 16, n_B = size_t(B) * N * 8;
@@ -838,7 +855,13 @@ int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const 
         cudaFree(tmp);
         return rc;
     }
-    LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
+    if (h->bench_prefetch == 2) {
+        LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
+    } else if (h->bench_prefetch == 1) {
+        LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0, 0);
+    } else {
+        LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
+    }
     e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(CILQR_ERR_CUDA, "stage_backward: %s", cudaGetErrorString(e));
@@ -885,7 +908,9 @@ int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float
             k_flush_l2<<<148 * 8, 256, 0, h->stream>>>(h->flush, h->flush_n);
         }
         CK(cudaEventRecord(h->t0, h->stream));
-        if (h->bench_prefetch) {
+        if (h->bench_prefetch == 2) {
+            LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
+        } else if (h->bench_prefetch) {
             LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0, 0);
         } else {
             LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
@@ -1058,8 +1083,11 @@ int do_set_option(Impl<T>* h, int option, int value) {
         case CILQR_OPT_PIPELINE:
             h->pipeline = value;
             return 0;
+        case CILQR_OPT_STAGED_BACKWARD:
+            h->staged = value ? 1 : 0;
+            return 0;
         case CILQR_OPT_BENCH_PREFETCH:
-            h->bench_prefetch = value ? 1 : 0;
+            h->bench_prefetch = value < 0 ? 0 : (value > 2 ? 2 : value);
             return 0;
         default:
             return fail(CILQR_ERR_INVALID, "unknown option %d", option);
