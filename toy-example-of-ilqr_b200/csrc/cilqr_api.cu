@@ -551,7 +551,7 @@ void launch_cost(Impl<T>* h, int B, int trial, int count, bool lat, bool matched
     }
     if (trial) mark_stage(h, 4);
     if (lat) {
-        LAUNCH_COST(h, 7, gk(count, h->N + 1), h->D, B, trial);
+        LAUNCH_COST(h, 4, gk(count, h->N + 1), h->D, B, trial);
     } else {
         LAUNCH_COST(h, 8, gk(count, h->N + 1), h->D, B, trial);
     }
@@ -598,7 +598,7 @@ int do_solve_resident(Impl<T>* h, int B) {
             LAUNCH_DERIVS(h, 1, gk(n_bound, N + 1), h->D, B, 1, par);
         }
         if (h->any_alm) {
-            LAUNCH_COST(h, 7, gk(B, N + 1), h->D, B, 0);
+            LAUNCH_COST(h, 4, gk(B, N + 1), h->D, B, 0);
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
         mark_stage(h, 1);

@@ -54,6 +54,7 @@ enum Ctl : int {
     CTL_NV = 0, CTL_ACTIVE = 1, CTL_TICKET = 2, CTL_ROUND = 3, CTL_TRIALS = 4,
     CTL_NACT = 5,   // [2] entries in the two work lists (round parity)
     CTL_CHUNK = 7,  // next chunk of the work list to hand out in the verdict kernel
+    CTL_TALLY = 8,  // [2 words, one 64-bit counter] verdict kernel: blocks done << 47 | trials << 23 | running
     CTL_WORDS = 16
 };
 
@@ -324,11 +325,12 @@ __device__ __forceinline__ void ctrl_constraints(const DevParams<T>& P, T acc, T
 //     step k (k >= 1: u_{k-1}, x_k, ref_k, obstacles at tick k).
 // ---------------------------------------------------------------------------
 // kMinBlocks: 8 CTAs/SM (64 registers, small spills) in the throughput regime, where the kernel is
-// fp64-latency bound and more resident warps pay (+11 % whole-solve at B = 262 144); 7 otherwise.
+// fp64-latency bound and more resident warps pay (+11 % whole-solve at B = 262 144); 4 (128 registers, four
+// obstacles in flight per trip) for latency-bound batches, where occupancy is irrelevant.
 // cost of step k of trajectory v of a view (instance b), with waypoint match ri
 // kAlm: the batch may hold augmented-Lagrangian instances; false compiles the ALM paths out, which
 // leaves the barrier terms free of branches (independent exponentials interleave).
-template <typename T, bool kAlm>
+template <typename T, bool kAlm, int kOb>
 __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int b, int v, int k, int ri) {
     const int N = D.N;
     const size_t Bs = D.Bs;
@@ -374,14 +376,13 @@ __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int
         const int no = D.n_obs[b];
         if (no > 0) {
             EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
-            // two obstacles per trip: their four barrier terms are independent, so the exponentials
-            // interleave; the sums keep the reference's order
-            for (int j = 0; j < no; j += 2) {
-                const bool two = j + 1 < no;
-                T item[4];
+            // kOb obstacles per trip: their loads are issued together and their barrier terms are
+            // independent, so the exponentials interleave; the sums keep the reference's order
+            for (int j = 0; j < no; j += kOb) {
+                T item[2 * kOb];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int jj = (q && two) ? j + 1 : j;
+                for (int q = 0; q < kOb; ++q) {
+                    const int jj = j + q < no ? j + q : j;
                     // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
                     // evaluated once per upload (k_obs_sincos), not once per cost evaluation
                     const T* ob = D.obs + (size_t(jj) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
@@ -396,11 +397,12 @@ __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int
                         item[2 * q + 1] = alm_item(cr, rho, mu[size_t(9 + 2 * jj) * Bs]);
                     }
                 }
-                Jk += item[0];
-                Jk += item[1];
-                if (two) {
-                    Jk += item[2];
-                    Jk += item[3];
+#pragma unroll
+                for (int q = 0; q < kOb; ++q) {
+                    if (j + q < no) {
+                        Jk += item[2 * q];
+                        Jk += item[2 * q + 1];
+                    }
                 }
             }
         }
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int t
     const int k = blockIdx.x;
     for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < count; v += gridDim.y * blockDim.x) {
         const int b = V.inst ? V.inst[v] : v;
-        const T cost = step_cost_of<T, kAlm>(D, V, b, v, k, V.ridx[size_t(k) * V.stride + v]);
+        const T cost = step_cost_of<T, kAlm, (kMinBlocks <= 4 ? 4 : 2)>(D, V, b, v, k, V.ridx[size_t(k) * V.stride + v]);
         V.sc[size_t(k) * V.stride + v] = cost;
         if (trial) {
             // the thread that stores the last step cost of a trial sums them in step order (fixed
@@ -1209,7 +1211,7 @@ __global__ void __launch_bounds__(128) k_forward2(Dev<T> D, int B) {
         const int vv = live ? v : count - 1;
         const int b = D.t_inst[vv];
         const DevParams<T>* Pp = D.P + D.tmpl[b];
-        const T p_dt = Pp->dt, p_wb = Pp->wheelbase;
+        const T p_dt = Pp->dt, p_dtw = Pp->dt / Pp->wheelbase;
         const int p_ref = Pp->ref_point;
         const T alpha = T(1) / T(1 << D.t_aidx[vv]);
         T xn[4], cx[4], cu[2], cd[2], cK[8];
@@ -1272,7 +1274,7 @@ __global__ void __launch_bounds__(128) k_forward2(Dev<T> D, int B) {
                 turn = role ? s : os;
             }
             T nx[4];
-            step_from_trig(xn, un[0], p_dt, p_wb, p_ref, s_head, c_head, turn, nx);
+            step_from_trig(xn, un[0], p_dt, p_dtw, p_ref, s_head, c_head, turn, nx);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 xn[c] = nx[c];
@@ -1335,7 +1337,7 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
         if (threadIdx.x == 0) ready = -1;
         __syncthreads();
         if (roller) {
-            const T p_dt = Pp->dt, p_wb = Pp->wheelbase;
+            const T p_dt = Pp->dt, p_dtw = Pp->dt / Pp->wheelbase;
             const int p_ref = Pp->ref_point;
             const T alpha = T(1) / T(1 << D.t_aidx[vv]);
             // lane `role` of a pair owns control row `role`: its feedback row, u and d
@@ -1394,7 +1396,7 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
                     turn = role ? sn : os;
                 }
                 T nx[4];
-                step_from_trig(xn, acc, p_dt, p_wb, p_ref, s_head, c_head, turn, nx);
+                step_from_trig(xn, acc, p_dt, p_dtw, p_ref, s_head, c_head, turn, nx);
                 // hand the position over first, then this step's global stores (the fence waits
                 // only for stores issued before it)
                 if (role == 0) {
@@ -1484,7 +1486,10 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
     const int n = D.ctl[CTL_NACT + par];
     const int n_chunks = (n + int(blockDim.x) - 1) / int(blockDim.x);
     int my_active = 0, my_trials = 0;
-    if (threadIdx.x == 0) s_chunk = atomicAdd(&D.ctl[CTL_CHUNK], 1);
+    // chunks by ticket only when the grid may exceed what is resident at once (a chunk must never wait
+    // on one whose block has not started); small grids save the atomic's round trip
+    const bool by_ticket = gridDim.x > 2 * 148;
+    if (threadIdx.x == 0) s_chunk = by_ticket ? atomicAdd(&D.ctl[CTL_CHUNK], 1) : int(blockIdx.x);
     __syncthreads();
     for (int chunk = s_chunk; chunk < n_chunks; chunk += gridDim.x) {
         const int idx = chunk * int(blockDim.x) + int(threadIdx.x);
@@ -1500,15 +1505,18 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
             const T dV0 = D.dV[b], dV1 = D.dV[Bs + b];
             bool ended = false;
             my_trials += cnt;
-            // all trial costs first (independent loads), then the verdicts in alpha order
-            T Jt[kNumAlphas];
+            // trial costs four at a time (independent loads), then their verdicts in alpha order; the
+            // usual case is a single trial
+            for (int i0 = 0; i0 < cnt && !ended; i0 += 4) {
+            T Jt[4];
 #pragma unroll
-            for (int i = 0; i < kNumAlphas; ++i) Jt[i] = i < cnt ? D.J_t[v0 + i] : T(0);
+            for (int q = 0; q < 4; ++q) Jt[q] = i0 + q < cnt ? D.J_t[v0 + i0 + q] : T(0);
 #pragma unroll
-            for (int i = 0; i < kNumAlphas; ++i) {
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q;
                 if (i >= cnt || ended) break;
                 const int v = v0 + i, a = a0 + i;
-                const T new_J = Jt[i];
+                const T new_J = Jt[q];
                 const T alpha = T(1) / T(1 << a);
                 const T actual = J_cur - new_J;
                 if (a == 0 && m_fabs(actual) < P.conv_thr) {
@@ -1526,6 +1534,7 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
                         ended = true;
                     }
                 }
+            }
             }
             if (!ended) {
                 if (a0 + cnt >= kNumAlphas) {
@@ -1599,19 +1608,22 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_active) atomicAdd(&D.ctl[CTL_ACTIVE], s_active);
-        if (s_trials) atomicAdd(&D.ctl[CTL_TRIALS], s_trials);
+        // one atomic per block: running instances (23 bits), trials (24 bits) and finished blocks in
+        // one 64-bit counter; the block that completes the count has the round's totals in hand
+        unsigned long long* tally = reinterpret_cast<unsigned long long*>(&D.ctl[CTL_TALLY]);
+        const unsigned long long mine = (1ull << 47) | (static_cast<unsigned long long>(unsigned(s_trials)) << 23) | unsigned(s_active);
         __threadfence();
-        int ticket = atomicAdd(&D.ctl[CTL_TICKET], 1);
-        if (ticket == int(gridDim.x) - 1) {
+        const unsigned long long sum = atomicAdd(tally, mine) + mine;
+        if (int(sum >> 47) == int(gridDim.x)) {
             __threadfence();
-            const int active = atomicAdd(&D.ctl[CTL_ACTIVE], 0);
-            const int n_next = atomicAdd(&D.ctl[CTL_NACT + (par ^ 1)], 0);
+            const int active = int(sum & 0x7fffffu);
+            const int trials = int((sum >> 23) & 0xffffffu);
+            const int n_next = *reinterpret_cast<volatile int*>(&D.ctl[CTL_NACT + (par ^ 1)]);
             const int round = D.ctl[CTL_ROUND] + 1;
             D.ctl[CTL_ROUND] = round;
-            D.ctl[CTL_ACTIVE] = 0;
+            D.ctl[CTL_TRIALS] += trials;
+            *tally = 0ull;
             D.ctl[CTL_NV] = 0;
-            D.ctl[CTL_TICKET] = 0;
             D.ctl[CTL_CHUNK] = 0;
             D.ctl[CTL_NACT + par] = 0;  // consumed; the verdict kernel of the next round refills it
             // two independent 64-bit words (rounds completed << 32 | instances still running, and

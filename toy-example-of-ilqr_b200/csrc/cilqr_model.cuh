@@ -115,12 +115,15 @@ __device__ __forceinline__ T tan_sc(T v) {
     return s / c;
 }
 template <typename T>
-__device__ __forceinline__ void step_from_trig(const T x[4], T acc, T dt, T wheelbase, int ref_point, T s_head,
+__device__ __forceinline__ void step_from_trig(const T x[4], T acc, T dt, T dt_over_wb, int ref_point, T s_head,
                                                T c_head, T turn, T out[4]) {
+    // dt_over_wb = dt / wheelbase, formed once per trajectory: the reference's (v tan(steer) dt) / L
+    // becomes (v tan(steer)) (dt / L) — one rounding apart, and no division left on the yaw recurrence,
+    // which is the critical path of every rollout (yaw -> feedback -> steer -> tan -> yaw)
     out[0] = x[0] + x[2] * c_head * dt;
     out[1] = x[1] + x[2] * s_head * dt;
     out[2] = x[2] + acc * dt;
-    out[3] = ref_point == 0 ? x[3] + x[2] * turn * dt / wheelbase : x[3] + 2 * x[2] * turn * dt / wheelbase;
+    out[3] = ref_point == 0 ? x[3] + x[2] * turn * dt_over_wb : x[3] + 2 * x[2] * turn * dt_over_wb;
 }
 template <typename T>
 __device__ __forceinline__ void propagate(const T x[4], T acc, T steer, T dt, T wheelbase,
@@ -135,7 +138,7 @@ __device__ __forceinline__ void propagate(const T x[4], T acc, T steer, T dt, T 
         T cb;
         m_sincos(beta, &turn, &cb);
     }
-    step_from_trig(x, acc, dt, wheelbase, ref_point, s, c, turn, out);
+    step_from_trig(x, acc, dt, dt / wheelbase, ref_point, s, c, turn, out);
 }
 
 // src/utils.cpp:285-342 — the non-trivial entries of A = df/dx (identity plus
