@@ -95,14 +95,19 @@ def test_batch_fp64(cfg):
 
 @pytest.mark.parametrize("cfg,dtype", [("C1", "f64"), ("C3", "f64"), ("C2", "f32")])
 def test_kernel_variants_return_the_same_bits(cfg, dtype):
-    """The regime switch (latency / throughput kernel variants) and the rollout+match pipeline (off, 16- and
-    8-lane scan windows) are execution strategies: every combination must return identical bits."""
+    """The regime switch (latency / throughput kernel variants, per handle and per round), the rollout+match
+    pipeline (off, 16- and 8-lane scan windows) and the staged backward pass are execution strategies:
+    every combination must return identical bits."""
     pb = cb.synthetic_batch(cfg, 333, N=50)
     outs = []
     with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, dtype) as s:
-        for threshold, pipe in ((1 << 30, 0), (1 << 30, 16), (1 << 30, 8), (1 << 30, 1), (0, 1)):
+        for threshold, pipe, staged in ((1 << 30, 0, 1), (1 << 30, 16, 1), (1 << 30, 8, 0), (1 << 30, 1, 0),
+                                        (1 << 30, 1, 1), (0, 1, 1), (100, 1, 1)):
+            # threshold 100: the solve starts on the throughput kernels and moves to the latency ones
+            # (work-list variants) once fewer than 100 instances are still running
             s.set_option(s.OPT_PREFETCH_BELOW, threshold)
             s.set_option(s.OPT_PIPELINE, pipe)
+            s.set_option(s.OPT_STAGED_BACKWARD, staged)
             outs.append(s.solve(pb))
     assert int(outs[0].iters.sum()) > pb.B
     for o in outs[1:]:
@@ -210,3 +215,26 @@ def test_no_obstacles_and_errors():
         with pytest.raises(cb.CilqrError) as e:
             s.solve(short)
         assert e.value.code == -2  # RoutingLine index out of range
+
+
+def test_large_batch_work_lists():
+    """B = 40960: the verdict kernel hands its chunks out by ticket and looks back over more than one
+    window of 32 chunks, the work lists shrink from the whole batch to a handful of instances, and the
+    solve crosses from the throughput to the latency kernels on the way.  Held to: a slice solved on
+    its own (small batch, latency kernels from the start) returns the same bits, and the oracle agrees
+    on that slice as it does for small batches."""
+    pb = cb.synthetic_batch("C1", 40960, N=50)
+    with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, "f64") as s:
+        a = s.solve(pb, want_gains=False)
+        b = s.solve(pb, want_gains=False)
+        c = s.counters()
+        sub = s.solve(pb.slice(20000, 20256), want_gains=False)
+    assert sum(c["exits"].values()) == pb.B
+    for f in ("u", "x", "J", "iters", "status", "exit_reason"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+        assert np.array_equal(getattr(a, f)[20000:20256], getattr(sub, f)), f
+    ref = op.solve_batch(pb.slice(20000, 20256), "f64")
+    same = sub.iters == ref.iters
+    assert same.mean() >= 0.9
+    assert np.median(np.abs(sub.x - ref.x).max(axis=(1, 2))) < 1e-9
+

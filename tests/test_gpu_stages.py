@@ -124,3 +124,27 @@ def test_backward_pass(dtype):
         assert relerr(d2[b], ed) < max(tol, 1e-6) and relerr(K2[b], eK) < max(tol, 1e-6)
     if dtype == "f64":
         assert n_tight >= B // 4
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_backward_variants_same_bits(dtype):
+    """The three backward kernels (streaming, register prefetch, staged through shared memory by bulk
+    async copies) run the same arithmetic: identical bits on the stage operator, including a planted
+    non-PD step (zeroed rows, dV up to the failing step)."""
+    pb = cb.synthetic_batch("C3", 200, N=50)  # 200: partial last tile of 32
+    u, x = perturbed_trajectories(pb, seed=3)
+    B, N = pb.B, pb.N
+    with _solver(pb, dtype) as s:
+        dv = s.stage_derivs(pb, u, x)
+        luu = dv["luu"].copy()
+        luu[::7, N // 3] = -1e6 * np.eye(2)
+        lamb = np.where(np.arange(B) % 2 == 0, 0.0, 0.5)
+        outs = []
+        for variant in (0, 1, 2):
+            s.set_option(s.OPT_BENCH_PREFETCH, variant)
+            outs.append(s.stage_backward(dv["lx"], dv["lu"], dv["lxx"], luu, dv["A"], dv["B"], lamb))
+    assert (outs[0][3] == 2).sum() >= B // 7
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b, equal_nan=True)
+

@@ -860,7 +860,7 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
             for (int c = 0; c < kRecFields; ++c) nxt[c] = ld_early(p + c * kRecFS);
         } else {
 #pragma unroll
-            for (int c = 0; c < kRecFields; ++c) r[c] = rec[(c) * kRecFS];
+            for (int c = 0; c < kRecFields; ++c) r[c] = rec[c * kRecFS];
         }
         T K[8], d0, d1;
         if (!riccati_step(r, lamb, Vx, V, dV0, dV1, K, d0, d1)) {
@@ -952,7 +952,8 @@ __global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver, i
     // do not queue up in a handful of SMs
     const int n_warps = n_threads >> 5;
     int lpw = (n + n_warps - 1) / n_warps;
-    lpw = lpw < 1 ? 1 : (lpw > 32 ? 32 : lpw);
+    lpw = (lpw < 1 ? 1 : (lpw > 32 ? 32 : lpw));
+    if (n > 16384) lpw = 32;  // bandwidth-bound: full warps, whole rows
     const int per_pass = n_warps * lpw;
     const int rounds = (n + per_pass - 1) / per_pass;
     const int first_idx = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lpw + lane;
