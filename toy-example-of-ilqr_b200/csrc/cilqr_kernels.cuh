@@ -715,6 +715,13 @@ __device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T
     }
 }
 
+template <typename T>
+__device__ __forceinline__ constexpr T kEps();
+template <>
+__device__ __forceinline__ constexpr double kEps<double>() { return 2.220446049250313e-16; }
+template <>
+__device__ __forceinline__ constexpr float kEps<float>() { return 1.1920929e-07f; }
+
 // One step of the recursion: consumes the 28-scalar record r of step i and the value function (Vx, V) of
 // step i+1, produces the gains K (2x4), d (2), and overwrites (Vx, V) with step i's.  Returns false —
 // leaving Vx, V, dV untouched — when Q_uu + lambda*I fails the LLT test.  Shared by every variant of
@@ -776,10 +783,23 @@ __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T&
     const T Quu01 = r[kRecLuu + 1] + (G00 * b01 + G01 * b11 + G03 * b31);
     const T Quu10 = r[kRecLuu + 1] + G12 * b20;
     const T Quu11 = (r[kRecLuu + 2] + (G10 * b01 + G11 * b11 + G13 * b31)) + lamb;
-    // LLT positive-definiteness test, as a predicate: the sqrt/divide chain then overlaps the
-    // 1/det chain below instead of serialising in front of it; nothing is stored when it fails
-    const T l10 = Quu10 / m_sqrt(Quu00);
-    const bool not_pd = (Quu00 <= T(0)) || (Quu11 - l10 * l10 <= T(0));
+    // LLT positive-definiteness test (Eigen::LLT, lower, unblocked: fail iff a00 <= 0 or
+    // a11 - (a10 / sqrt(a00))^2 <= 0; NaN passes), as a predicate: nothing is stored when it fails.
+    // The sqrt / divide sequence is ~40 instructions on a serial chain that is bound by its
+    // instruction stream, and the test passes by a wide margin on almost every step, so a
+    // sufficient condition is tried first: in floating point (a10 / sqrt(a00))^2 is
+    // a10^2 / a00 within 5 roundings, so a00 > 0 and a00 a11 - a10^2 > 64 eps a10^2 guarantees that
+    // the exact sequence passes too.  Anything else (near-singular, non-positive, NaN, inf) takes the
+    // exact sequence, so the verdict is always the reference's.
+    bool not_pd = false;
+    {
+        const T a10sq = Quu10 * Quu10;
+        const bool surely_pd = Quu00 > T(0) && (Quu00 * Quu11 - a10sq) > T(64) * kEps<T>() * a10sq;
+        if (!surely_pd) {
+            const T l10 = Quu10 / m_sqrt(Quu00);
+            not_pd = (Quu00 <= T(0)) || (Quu11 - l10 * l10 <= T(0));
+        }
+    }
     const T invdet = T(1) / (Quu00 * Quu11 - Quu10 * Quu01);
     const T i00 = Quu11 * invdet, i01 = -Quu01 * invdet, i10 = -Quu10 * invdet, i11 = Quu00 * invdet;
     d0 = (-i00) * Qu0 + (-i01) * Qu1;
