@@ -1234,6 +1234,7 @@ __global__ void __launch_bounds__(128) k_forward2(Dev<T> D, int B) {
         const DevParams<T>* Pp = D.P + D.tmpl[b];
         const T p_dt = Pp->dt, p_dtw = Pp->dt / Pp->wheelbase;
         const int p_ref = Pp->ref_point;
+        const bool mixed = __any_sync(0xffffffffu, p_ref != 0);
         const T alpha = T(1) / T(1 << D.t_aidx[vv]);
         T xn[4], cx[4], cu[2], cd[2], cK[8];
 #pragma unroll
@@ -1276,23 +1277,13 @@ __global__ void __launch_bounds__(128) k_forward2(Dev<T> D, int B) {
                 D.Ut[at(Vs, i, 0, 2, v)] = un[0];
                 D.Ut[at(Vs, i, 1, 2, v)] = un[1];
             }
-            // the two sin/cos pairs of the step, one per lane, then swapped
+            // the two sin/cos pairs of the step (yaw on lane 0, steering angle on lane 1), then swapped
             T s_head, c_head, turn;
-            if (p_ref == 0) {
+            {
                 T s, c;
                 m_sincos(role ? un[1] : xn[3], &s, &c);
                 const T os = __shfl_xor_sync(0xffffffffu, s, 1), oc = __shfl_xor_sync(0xffffffffu, c, 1);
-                s_head = role ? os : s;
-                c_head = role ? oc : c;
-                turn = (role ? s : os) / (role ? c : oc);
-            } else {
-                const T beta = m_atan(tan_sc(un[1]) / 2);
-                T s, c;
-                m_sincos(role ? beta : beta + xn[3], &s, &c);
-                const T os = __shfl_xor_sync(0xffffffffu, s, 1), oc = __shfl_xor_sync(0xffffffffu, c, 1);
-                s_head = role ? os : s;
-                c_head = role ? oc : c;
-                turn = role ? s : os;
+                step_trig(p_ref, mixed, role ? os : s, role ? oc : c, role ? s : os, role ? c : oc, &s_head, &c_head, &turn);
             }
             T nx[4];
             step_from_trig(xn, un[0], p_dt, p_dtw, p_ref, s_head, c_head, turn, nx);
@@ -1360,6 +1351,7 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
         if (roller) {
             const T p_dt = Pp->dt, p_dtw = Pp->dt / Pp->wheelbase;
             const int p_ref = Pp->ref_point;
+            const bool mixed = __any_sync(0xffffffffu, p_ref != 0);
             const T alpha = T(1) / T(1 << D.t_aidx[vv]);
             // lane `role` of a pair owns control row `role`: its feedback row, u and d
             T xn[4], cx[4], cK[4], cu, cd;
@@ -1398,23 +1390,14 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
                 for (int c = 0; c < 4; ++c) fb += cK[c] * (xn[c] - cx[c]);
                 const T mine = (cu + fb) + alpha * cd;  // u'[role]
                 const T other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                const T acc = role ? other : mine, steer = role ? mine : other;
+                const T acc = role ? other : mine;
                 T s_head, c_head, turn;
-                if (p_ref == 0) {
+                {
                     T sn, cs;
                     m_sincos(role ? mine : xn[3], &sn, &cs);
                     const T os = __shfl_xor_sync(0xffffffffu, sn, 1), oc = __shfl_xor_sync(0xffffffffu, cs, 1);
-                    s_head = role ? os : sn;
-                    c_head = role ? oc : cs;
-                    turn = (role ? sn : os) / (role ? cs : oc);
-                } else {
-                    const T beta = m_atan(tan_sc(steer) / 2);
-                    T sn, cs;
-                    m_sincos(role ? beta : beta + xn[3], &sn, &cs);
-                    const T os = __shfl_xor_sync(0xffffffffu, sn, 1), oc = __shfl_xor_sync(0xffffffffu, cs, 1);
-                    s_head = role ? os : sn;
-                    c_head = role ? oc : cs;
-                    turn = role ? sn : os;
+                    step_trig(p_ref, mixed, role ? os : sn, role ? oc : cs, role ? sn : os, role ? cs : oc, &s_head,
+                              &c_head, &turn);
                 }
                 T nx[4];
                 step_from_trig(xn, acc, p_dt, p_dtw, p_ref, s_head, c_head, turn, nx);

@@ -102,18 +102,39 @@ struct DevParams {
 
 // src/utils.cpp:262-283 — one Euler step of the rear-axle (ref_point 0) or centre-of-gravity (1)
 // bicycle model; all right-hand sides use the old state.  The step is split into its
-// transcendental part and its algebra so that the rollout kernels can evaluate the two independent
-// sin/cos pairs of a step on two lanes at once and still produce the bits of the one-lane version:
-//   rear:    heading = sincos(yaw),        turn = tan(steer)
-//   gravity: heading = sincos(beta + yaw), turn = sin(beta),  beta = atan(tan(steer) / 2)
-// tan(v) is taken as sin(v)/cos(v) from one sincos (<= 2 ulp, the accuracy class of CUDA's tan()),
-// which keeps every lane on the same instruction stream.
+// transcendental part and its algebra so that the rollout kernels can evaluate the two sin/cos
+// pairs of a step — of the yaw and of the steering angle — on two lanes at once, and so that BOTH
+// vehicle models run the same instruction stream (a batch may mix them lane by lane; as two
+// branches the warp would execute both chains one after the other on every step):
+//   rear:    heading = (sin, cos)(yaw),        turn = tan(steer) = sin(steer) / cos(steer)
+//   gravity: heading = (sin, cos)(beta + yaw), turn = sin(beta),  beta = atan(tan(steer) / 2)
+// with beta's sine and cosine taken straight from tan(beta) = tan(steer) / 2 (beta lies in
+// (-pi/2, pi/2), so cos(beta) = 1 / sqrt(1 + tan^2(beta)) > 0) and the heading by the angle-addition
+// formulas — no atan and no third sin/cos on the recurrence.  Each of these is within 2-3 ulp of the
+// reference's operation sequence (absolute error <= 4e-16 on the heading), the accuracy class of
+// CUDA's own tan() / atan().
+// `mixed`: warp-uniform, some lane of the warp runs the gravity model (a pure rear-axle warp skips
+// the beta algebra altogether).
 template <typename T>
-__device__ __forceinline__ T tan_sc(T v) {
-    T s, c;
-    m_sincos(v, &s, &c);
-    return s / c;
+__device__ __forceinline__ void step_trig(int ref_point, bool mixed, T s_yaw, T c_yaw, T s_st, T c_st, T* s_head,
+                                          T* c_head, T* turn) {
+    const T td = s_st / c_st;
+    *s_head = s_yaw;
+    *c_head = c_yaw;
+    *turn = td;
+    if (mixed) {
+        const T tb = T(0.5) * td;
+        const T cb = T(1) / m_sqrt(T(1) + tb * tb);
+        const T sb = tb * cb;
+        if (ref_point != 0) {
+            *s_head = sb * c_yaw + cb * s_yaw;
+            *c_head = cb * c_yaw - sb * s_yaw;
+            *turn = sb;
+        }
+    }
 }
+// warp vote over the lanes that are currently active
+__device__ __forceinline__ bool any_gravity_lane(int ref_point) { return __any_sync(__activemask(), ref_point != 0); }
 template <typename T>
 __device__ __forceinline__ void step_from_trig(const T x[4], T acc, T dt, T dt_over_wb, int ref_point, T s_head,
                                                T c_head, T turn, T out[4]) {
@@ -128,16 +149,10 @@ __device__ __forceinline__ void step_from_trig(const T x[4], T acc, T dt, T dt_o
 template <typename T>
 __device__ __forceinline__ void propagate(const T x[4], T acc, T steer, T dt, T wheelbase,
                                           int ref_point, T out[4]) {
-    T s, c, turn;
-    if (ref_point == 0) {
-        m_sincos(x[3], &s, &c);
-        turn = tan_sc(steer);
-    } else {
-        const T beta = m_atan(tan_sc(steer) / 2);
-        m_sincos(beta + x[3], &s, &c);
-        T cb;
-        m_sincos(beta, &turn, &cb);
-    }
+    T sy, cy, ss, cs, s, c, turn;
+    m_sincos(x[3], &sy, &cy);
+    m_sincos(steer, &ss, &cs);
+    step_trig(ref_point, any_gravity_lane(ref_point), sy, cy, ss, cs, &s, &c, &turn);
     step_from_trig(x, acc, dt, dt / wheelbase, ref_point, s, c, turn, out);
 }
 
