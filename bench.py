@@ -38,10 +38,11 @@ METRIC = "ilqr_iterations_per_sec"
 UNIT = "iterations/s"
 WORKLOAD = "C1: batch=4096 randomized scenario_two_straight instances per GPU, N=50, nx=4, nu=2"
 ROOFLINE_BATCH = 262144
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_backward<double,false> at B=262144, N=50,
-# from the committed `ncu --set full` capture (profiles/r01_ncu_full_summary.txt): 2.9675 GB read +
-# 1.0303 GB written = 0.994 x the algorithmic 4.0223 GB.  Only valid for that dtype / batch.
-ROOFLINE_TRAFFIC_BYTES = {"f64": 2.967507e9 + 1.030318e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_backward<double,true> (the variant the
+# solver uses at this batch) at B=262144, N=50, from the committed `ncu --set full` capture
+# (profiles/r01b_ncu_full_summary.txt): 2.9676 GB read + 1.0291 GB written = 0.994 x the algorithmic
+# 4.0223 GB.  Only valid for that dtype / batch.
+ROOFLINE_TRAFFIC_BYTES = {"f64": 2.967610e9 + 1.029079e9}
 
 
 def measured_peak():
@@ -336,7 +337,7 @@ def main():
         ms, nbytes = rs.bench_backward(Br, 0.0, 20, True)
         rs.close()
         achieved = nbytes / (float(np.mean(ms)) * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_backward (backward_pass Riccati recursion, cpp:383-440)",
+        roofline = {"bound": "hbm", "kernel": "k_backward<T, prefetch> (backward_pass Riccati recursion, cpp:383-440)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ROOFLINE_TRAFFIC_BYTES.get(args.dtype), "peak_source": peak_src,
                     "bytes_per_launch": nbytes, "ms_per_launch": float(np.mean(ms)),

@@ -160,8 +160,9 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *  CILQR_OPT_PREFETCH_BELOW (default 16384, the measured crossover): batches up to this size run the backward pass
  *      with next-step operands prefetched into registers (latency-bound regime); larger
  *      batches use the leaner streaming variant (bandwidth-bound regime).
- *  CILQR_OPT_BENCH_PREFETCH (default 0): which backward kernel cilqr_b200_bench_backward times and
- *      cilqr_b200_stage_backward runs: 0 streaming, 1 register prefetch, 2 staged (below).
+ *  CILQR_OPT_BENCH_PREFETCH (default -1): which backward kernel cilqr_b200_bench_backward times and
+ *      cilqr_b200_stage_backward runs: -1 the one the solver uses at that batch, 0 streaming,
+ *      1 register prefetch, 2 staged (below).
  *  CILQR_OPT_PROFILE_STAGES (default 0): record a CUDA event in front of every stage launch of the
  *      following solves (adds a few microseconds per round; not for timed runs).
  *  CILQR_OPT_PIPELINE (default 1): latency-bound batches run forward_pass and the waypoint match

@@ -49,7 +49,7 @@ struct Base {
     int max_rounds = 0;
     int run_ahead = 3;
     int prefetch_below = 16384;  // batches up to this size use the latency-regime kernel variants (measured crossover ~16-18k)
-    int bench_prefetch = 0;
+    int bench_prefetch = -1;  // stage operator / roofline leg: -1 = the variant the solver uses at that batch
     unsigned scan_epoch = 0;  // tags the look-back words of one verdict launch (never 0, 30 bits)
     int pipeline = 1;  // latency regime: rollout and waypoint match as one two-stage kernel
     int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
@@ -341,6 +341,19 @@ inline dim3 grid2(int B, int rows) { return dim3((B + 127) / 128, rows); }
 // grid-stride launches: enough CTAs for `count` items, capped at a multiple of the 148 SMs
 inline dim3 gs1(int count) { return dim3(std::max(1, std::min((count + 127) / 128, kGridCap))); }
 inline dim3 gs2(int count, int rows) { return dim3(std::max(1, std::min((count + 127) / 128, kGridCap)), rows); }
+// Which feed of the backward recursion a launch over n trajectories uses (all return the same bits):
+//   2  staged through shared memory by bulk async copies — small batches (whole-batch tiles)
+//   1  next step's record prefetched into registers — latency-bound lists, and bandwidth-bound launches
+//      large enough to fill the GPU at 3 CTAs / SM (fp64 measured on the tiled layout: 6815 against
+//      6390 GB/s at 262144, 5349 against 5976 at 65536; fp32: ahead at every size, 5466 against 4233
+//      at 65536, 6365 against 6112 at 262144)
+//   0  plain streaming — fp64 in between
+template <typename T>
+int backward_variant(const Base* h, int n, int B, bool lat) {
+    if (lat) return (h->staged && B <= h->prefetch_below) ? 2 : 1;
+    if (sizeof(T) == 4) return 1;
+    return n >= 196608 ? 1 : 0;
+}
 // k_backward_staged: one warp per tile of 32 instances, at most 16 warps per SM
 inline dim3 staged_grid(int B) { return dim3(std::max(1, std::min((B + 31) / 32, 148 * 16))); }
 // step-parallel stages (k_cost, k_derivs): x = step, y = blocks of trajectories
@@ -602,14 +615,15 @@ int do_solve_resident(Impl<T>* h, int B) {
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
         mark_stage(h, 1);
-        if (lat && h->staged && B <= h->prefetch_below) {
-            // small batch: one warp per tile of 32 instances, records staged through shared memory
-            LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 1);
-        } else if (lat) {
-            // a short work list is spread over one warp per scheduler (see k_backward)
-            LAUNCH(h, (k_backward<T, true>), gs1(std::max(n_bound, 148 * 128)), 128, h->D, B, 1, par);
-        } else {
-            LAUNCH(h, (k_backward<T, false>), gs1(n_bound), 128, h->D, B, 1, par);
+        switch (backward_variant<T>(h, n_bound, B, lat)) {
+            case 2:  // small batch: one warp per tile of 32 instances, records staged through shared memory
+                LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 1);
+                break;
+            case 1:  // a short work list is spread over one warp per scheduler (see k_backward)
+                LAUNCH(h, (k_backward<T, true>), gs1(lat ? std::max(n_bound, 148 * 128) : n_bound), 128, h->D, B, 1, par);
+                break;
+            default:
+                LAUNCH(h, (k_backward<T, false>), gs1(n_bound), 128, h->D, B, 1, par);
         }
         mark_stage(h, 2);
         const bool piped = lat && h->pipeline && N + 1 <= kPipeMaxSteps;
@@ -855,12 +869,15 @@ int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const 
         cudaFree(tmp);
         return rc;
     }
-    if (h->bench_prefetch == 2) {
-        LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
-    } else if (h->bench_prefetch == 1) {
-        LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0, 0);
-    } else {
-        LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
+    {
+        const int variant = h->bench_prefetch >= 0 ? h->bench_prefetch : backward_variant<T>(h, B, B, B <= h->prefetch_below);
+        if (variant == 2) {
+            LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
+        } else if (variant == 1) {
+            LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0, 0);
+        } else {
+            LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
+        }
     }
     e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
@@ -908,9 +925,10 @@ int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float
             k_flush_l2<<<148 * 8, 256, 0, h->stream>>>(h->flush, h->flush_n);
         }
         CK(cudaEventRecord(h->t0, h->stream));
-        if (h->bench_prefetch == 2) {
+        const int variant = h->bench_prefetch >= 0 ? h->bench_prefetch : backward_variant<T>(h, B, B, B <= h->prefetch_below);
+        if (variant == 2) {
             LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
-        } else if (h->bench_prefetch) {
+        } else if (variant == 1) {
             LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0, 0);
         } else {
             LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
@@ -1087,7 +1105,7 @@ int do_set_option(Impl<T>* h, int option, int value) {
             h->staged = value ? 1 : 0;
             return 0;
         case CILQR_OPT_BENCH_PREFETCH:
-            h->bench_prefetch = value < 0 ? 0 : (value > 2 ? 2 : value);
+            h->bench_prefetch = value < 0 ? -1 : (value > 2 ? 2 : value);
             return 0;
         default:
             return fail(CILQR_ERR_INVALID, "unknown option %d", option);
