@@ -170,7 +170,11 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *      shared-memory ring); 0 runs them as two kernels; 8 / 16 force the scan window.
  *  CILQR_OPT_STAGED_BACKWARD (default 1): latency-bound batches run the backward pass with one warp
  *      per tile of 32 instances, each step's record brought into a shared-memory ring by bulk
- *      asynchronous copies (cp.async.bulk + mbarrier) three steps ahead of the recursion. */
+ *      asynchronous copies (cp.async.bulk + mbarrier) three steps ahead of the recursion.
+ *  CILQR_OPT_REPACK (default 1): once the instances still running are an eighth of the slots in use
+ *      (batches above CILQR_OPT_PREFETCH_BELOW), they are moved into a dense prefix of the device
+ *      arrays and the solve carries on as a batch of that size; every instance is moved back into
+ *      its own slot before the solve returns. */
 typedef enum cilqr_option_t {
     CILQR_OPT_WIDE_SEARCH = 0,
     CILQR_OPT_RUN_AHEAD = 1,
@@ -178,7 +182,8 @@ typedef enum cilqr_option_t {
     CILQR_OPT_BENCH_PREFETCH = 3,
     CILQR_OPT_PROFILE_STAGES = 4,
     CILQR_OPT_PIPELINE = 5,
-    CILQR_OPT_STAGED_BACKWARD = 6
+    CILQR_OPT_STAGED_BACKWARD = 6,
+    CILQR_OPT_REPACK = 7
 } cilqr_option_t;
 int cilqr_b200_set_option(cilqr_handle_t* h, int option, int value);
 

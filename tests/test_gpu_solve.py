@@ -219,22 +219,47 @@ def test_no_obstacles_and_errors():
 
 def test_large_batch_work_lists():
     """B = 40960: the verdict kernel hands its chunks out by ticket and looks back over more than one
-    window of 32 chunks, the work lists shrink from the whole batch to a handful of instances, and the
-    solve crosses from the throughput to the latency kernels on the way.  Held to: a slice solved on
-    its own (small batch, latency kernels from the start) returns the same bits, and the oracle agrees
-    on that slice as it does for small batches."""
+    window of 32 chunks, the work lists shrink from the whole batch to a handful of instances, the
+    survivors are repacked into a dense prefix (and moved back at the end), and the solve crosses from
+    the throughput to the latency kernels on the way.  Held to: the same bits with and without the
+    repack, a slice solved on its own (small batch, latency kernels from the start) returns the same
+    bits, and the oracle agrees on that slice as it does for small batches."""
     pb = cb.synthetic_batch("C1", 40960, N=50)
     with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, "f64") as s:
-        a = s.solve(pb, want_gains=False)
-        b = s.solve(pb, want_gains=False)
+        a = s.solve(pb)
+        b = s.solve(pb)
         c = s.counters()
-        sub = s.solve(pb.slice(20000, 20256), want_gains=False)
+        sub = s.solve(pb.slice(20000, 20256))
+        s.set_option(s.OPT_REPACK, 0)  # without moving the survivors into a dense prefix
+        plain = s.solve(pb)
     assert sum(c["exits"].values()) == pb.B
-    for f in ("u", "x", "J", "iters", "status", "exit_reason"):
+    for f in ("u", "x", "J", "K", "d", "iters", "status", "exit_reason", "step_cost"):
         assert np.array_equal(getattr(a, f), getattr(b, f)), f
+        assert np.array_equal(getattr(a, f), getattr(plain, f)), f
         assert np.array_equal(getattr(a, f)[20000:20256], getattr(sub, f)), f
     ref = op.solve_batch(pb.slice(20000, 20256), "f64")
     same = sub.iters == ref.iters
     assert same.mean() >= 0.9
     assert np.median(np.abs(sub.x - ref.x).max(axis=(1, 2))) < 1e-9
+
+
+def test_repack_two_levels_and_warm_state():
+    """B = 163840: two repacks (to <= 20480, then <= 2560 slots).  Same bits as the plain solve, and the
+    per-instance state that outlives a solve (warm-start controls) ends up in its own slot again: a
+    second, warm-started solve agrees too."""
+    pb = cb.synthetic_batch("C1", 163840, N=50)
+    for td in pb.templates:
+        td.params = dict(td.params, use_last_solution=1)
+    outs = {}
+    with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, "f64") as s:
+        for repack in (1, 0):
+            s.set_option(s.OPT_REPACK, repack)
+            s.reset()
+            first = s.solve(pb, want_gains=False)
+            second = s.solve(pb, want_gains=False)  # warm start from the first solve's controls
+            outs[repack] = (first, second)
+    for f in ("u", "x", "J", "iters", "status", "exit_reason"):
+        assert np.array_equal(getattr(outs[1][0], f), getattr(outs[0][0], f)), f
+        assert np.array_equal(getattr(outs[1][1], f), getattr(outs[0][1], f)), f
+    assert outs[1][1].iters.sum() < outs[1][0].iters.sum()  # the warm start really was used
 

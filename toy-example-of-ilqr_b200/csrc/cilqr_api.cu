@@ -53,6 +53,7 @@ struct Base {
     unsigned scan_epoch = 0;  // tags the look-back words of one verdict launch (never 0, 30 bits)
     int pipeline = 1;  // latency regime: rollout and waypoint match as one two-stage kernel
     int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
+    int repack = 1;    // large batches: survivors moved into a dense prefix once they are an eighth of the slots in use
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
@@ -286,6 +287,8 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.wide, Bs))) return r;
         if ((r = dalloc(h, &D.act, 2 * Bs))) return r;
         if ((r = dalloc(h, &D.scan_state, Bs / 128 + 1))) return r;
+        if ((r = dalloc(h, &D.swap_src, size_t(kRepackLevels) * (Bs / 8 + 1)))) return r;
+        if ((r = dalloc(h, &D.swap_dst, size_t(kRepackLevels) * (Bs / 8 + 1)))) return r;
         if ((r = dalloc(h, &D.rec, size_t(N + 1) * kRecFields * Bs))) return r;
         if ((r = dalloc(h, &D.Kg, size_t(N) * 8 * Bs))) return r;
         if ((r = dalloc(h, &D.dg, size_t(N) * 2 * Bs))) return r;
@@ -570,10 +573,74 @@ void launch_cost(Impl<T>* h, int B, int trial, int count, bool lat, bool matched
     }
 }
 
+// Exchange the slot pairs of repack `level` in every per-instance array (see k_plan_repack): moves the
+// survivors into the prefix, and — applied a second time — back.  m_bound >= the number of pairs.
 template <typename T>
-int do_solve_resident(Impl<T>* h, int B) {
+void swap_instances(Impl<T>* h, int level, int m_bound) {
+    const Dev<T>& D = h->D;
+    const size_t Bs = D.Bs;
+    const int N = D.N;
+    const int cap = D.Bs / 8 + 1;
+    const int* src = D.swap_src + size_t(level) * cap;
+    const int* dst = D.swap_dst + size_t(level) * cap;
+    const int* m = D.ctl + CTL_NSWAP + level;
+    const int gx = std::max(1, std::min((m_bound + 127) / 128, kGridCap));
+    auto rows_t = [&](T* p, int rows) {
+        if (p) LAUNCH(h, k_swap_rows<T>, dim3(gx, std::min(rows, 1024)), 128, p, Bs, rows, src, dst, m);
+    };
+    auto rows_i = [&](int* p, int rows) {
+        if (p) LAUNCH(h, k_swap_rows<int>, dim3(gx, std::min(rows, 1024)), 128, p, Bs, rows, src, dst, m);
+    };
+    // problem data
+    rows_t(D.ref_velo, 1);
+    rows_t(D.borders, 2);
+    rows_i(D.tmpl, 1);
+    rows_i(D.n_obs, 1);
+    if (D.max_obs > 0) rows_t(D.obs, D.max_obs * D.obs_len * 4);
+    rows_t(D.x0, 4);
+    // trajectory, records, gains
+    rows_t(D.X, (N + 1) * 4);
+    rows_t(D.U, N * 2);
+    rows_i(D.ridx, N + 1);
+    rows_t(D.sc, N + 1);
+    LAUNCH(h, k_swap_records<T>, dim3(gx, std::min((N + 1) * kRecFields, 1024)), 128, D, src, dst, m);
+    rows_t(D.Kg, N * 8);
+    rows_t(D.dg, N * 2);
+    rows_t(D.dV, 2);
+    // solver state
+    rows_t(D.lamb, 1);
+    rows_t(D.J_cur, 1);
+    rows_t(D.J_init, 1);
+    rows_t(D.alpha, 1);
+    rows_i(D.status, 1);
+    rows_i(D.phase, 1);
+    rows_i(D.aidx, 1);
+    rows_i(D.iters, 1);
+    rows_i(D.exit_reason, 1);
+    rows_i(D.rec_valid, 1);
+    rows_i(D.wide, 1);
+    rows_i(D.commit_src, 1);
+    rows_i(D.t_first, 1);
+    rows_i(D.t_count, 1);
+    rows_t(D.last_u, N * 2);
+    rows_i(D.first, 1);
+    if (D.mu) {
+        rows_t(D.mu, N * D.alm_cols);
+        rows_t(D.mu_next, N * D.alm_cols);
+        rows_t(D.rho, 1);
+    }
+    if (D.trace_cap > 0) {
+        rows_i(D.tr_status, D.trace_cap);
+        rows_i(D.tr_alpha, D.trace_cap);
+        rows_t(D.tr_cost, D.trace_cap);
+    }
+}
+
+template <typename T>
+int do_solve_resident(Impl<T>* h, int Bfull) {
     CK(cudaSetDevice(h->device));
-    if (B == 0) return 0;
+    if (Bfull == 0) return 0;
+    int B = Bfull;  // slots in use: shrinks when the survivors are repacked into a prefix
     const int N = h->N;
     h->launches = 0;
     CK(cudaStreamSynchronize(h->stream));
@@ -594,12 +661,21 @@ int do_solve_resident(Impl<T>* h, int B) {
     // the kernel variants (all variants of a stage return the same bits, so a big batch switches to
     // the latency-regime kernels for its stragglers).
     int launched = 0;
+    int level = 0, repack_bound[kRepackLevels];
     while (launched < h->max_rounds) {
         const unsigned long long w = progress[0];
         const int done = int(w >> 32);
         if (done > 0 && unsigned(w) == 0u) break;
         if (launched - done > h->run_ahead) continue;  // spin on the mapped words
         const int n_bound = std::max(1, std::min(B, int(unsigned(progress[1]))));
+        // Repack: the survivors of a large batch have thinned out to an eighth of the slots in use ->
+        // move them into a dense prefix (swap_instances) and carry on as a batch of that size.
+        if (h->repack && level < kRepackLevels && B > h->prefetch_below && size_t(n_bound) * 8 <= size_t(B)) {
+            LAUNCH(h, k_plan_repack<T>, dim3(1), kPlanThreads, h->D, launched & 1, level);
+            swap_instances(h, level, n_bound);
+            repack_bound[level++] = n_bound;
+            B = n_bound;
+        }
         const int trial_bound = int(std::min<long long>(h->D.Vs, (long long)n_bound * kNumAlphas));
         const bool lat = n_bound <= h->prefetch_below;
         const int par = launched & 1;  // which of the two work lists this round reads
@@ -650,6 +726,12 @@ int do_solve_resident(Impl<T>* h, int B) {
     }
     // commit a step accepted in the last round
     LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 1, launched & 1);
+    // every instance back into its own slot
+    while (level > 0) {
+        --level;
+        swap_instances(h, level, repack_bound[level]);
+    }
+    B = Bfull;
     LAUNCH(h, k_store_last_u<T>, gs2(B, N), 128, h->D, B);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -1103,6 +1185,9 @@ int do_set_option(Impl<T>* h, int option, int value) {
             return 0;
         case CILQR_OPT_STAGED_BACKWARD:
             h->staged = value ? 1 : 0;
+            return 0;
+        case CILQR_OPT_REPACK:
+            h->repack = value ? 1 : 0;
             return 0;
         case CILQR_OPT_BENCH_PREFETCH:
             h->bench_prefetch = value < 0 ? -1 : (value > 2 ? 2 : value);

@@ -45,6 +45,7 @@ constexpr int kRecTile = 32;
 constexpr int kRecFS = kRecTile;  // field stride in scalars
 
 constexpr int kNumAlphas = 20;  // alpha = 2^0 .. 2^-19  (cpp:354)
+constexpr int kRepackLevels = 3;
 
 enum Phase : int { PH_BACKWARD = 0, PH_SEARCH = 1, PH_DONE = 2 };
 enum Status : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BWD_FAIL = 2, ST_FWD_FAIL = 3, ST_SMALL_STEP = 4 };
@@ -55,6 +56,7 @@ enum Ctl : int {
     CTL_NACT = 5,   // [2] entries in the two work lists (round parity)
     CTL_CHUNK = 7,  // next chunk of the work list to hand out in the verdict kernel
     CTL_TALLY = 8,  // [2 words, one 64-bit counter] verdict kernel: blocks done << 47 | trials << 23 | running
+    CTL_NSWAP = 10,  // [kRepackLevels] slot pairs exchanged by each repack of the solve
     CTL_WORDS = 16
 };
 
@@ -119,6 +121,9 @@ struct Dev {
     // pass: per-chunk counts chained through scan_state with decoupled look-back)
     int* act;
     unsigned long long* scan_state;  // [Bs / 128 + 1]  epoch << 34 | flag << 32 | count
+    // repack (large batches): slot pairs (src beyond the prefix, dst a hole inside it) of each level
+    int* swap_src;  // [kRepackLevels][Bs / 8 + 1]
+    int* swap_dst;
     T* last_u;   // [N][2][Bs]
     int* first;  // [Bs]
     // augmented-Lagrangian state (allocated only when a template asks for it)
@@ -1790,6 +1795,115 @@ __global__ void k_tile_records(Dev<T> D, int B0, int B) {
     if (b >= B || b < B0) return;
     const int k = row / kRecFields, c = row % kRecFields;
     rec_at(D, k, b)[c * kRecFS] = rec_at(D, k, b % B0)[c * kRecFS];
+}
+
+// ---------------------------------------------------------------------------
+// Repack (bandwidth-bound batches).  Every array is [row][batch]: once most instances have finished,
+// each 8-byte access of a survivor still costs a 32-byte sector (and a scattered 8-byte store a sector
+// read-modify-write), so a round over n scattered survivors costs several times a round over a dense
+// batch of n.  When the work list has shrunk to an eighth of the slots in use, the survivors are
+// moved into the prefix [0, n): the survivors beyond the prefix trade places with the finished
+// instances inside it (disjoint slot pairs, every per-instance array swapped in place), the work list
+// becomes 0 .. n-1, and the solve carries on as a dense batch of n.  The same swaps applied again at
+// the end of the solve put every instance back into its own slot.
+// ---------------------------------------------------------------------------
+constexpr int kPlanThreads = 1024;
+
+// One block: the list of round `par` (sorted, n entries) -> swap pairs of `level`, then list := 0 .. n-1.
+template <typename T>
+__global__ void __launch_bounds__(kPlanThreads) k_plan_repack(Dev<T> D, int par, int level) {
+    __shared__ int s_part[kPlanThreads / 32];
+    __shared__ int s_inside;
+    const size_t Bs = D.Bs;
+    int* list = D.act + size_t(par) * Bs;
+    int* mark = D.act + size_t(par ^ 1) * Bs;  // the other list is free between rounds
+    const int n = D.ctl[CTL_NACT + par];
+    const int cap = D.Bs / 8 + 1;
+    int* src = D.swap_src + size_t(level) * cap;
+    int* dst = D.swap_dst + size_t(level) * cap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int s = tid; s < n; s += kPlanThreads) mark[s] = 0;
+    __syncthreads();
+    int inside = 0;
+    for (int i = tid; i < n; i += kPlanThreads) {
+        const int e = list[i];
+        if (e < n) {
+            mark[e] = 1;
+            ++inside;
+        }
+    }
+    // entries inside the prefix (the list is sorted: they are its head)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) inside += __shfl_xor_sync(0xffffffffu, inside, o);
+    if (lane == 0) s_part[warp] = inside;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < kPlanThreads / 32; ++w) t += s_part[w];
+        s_inside = t;
+    }
+    __syncthreads();
+    const int n_inside = s_inside;
+    // holes of the prefix, in slot order: contiguous chunk per thread, block scan of the chunk counts
+    const int chunk = (n + kPlanThreads - 1) / kPlanThreads;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int holes = 0;
+    for (int s = lo; s < hi; ++s) holes += mark[s] == 0;
+    int incl = holes;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // s_part is reused
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    int j = incl - holes;
+    for (int w = 0; w < warp; ++w) j += s_part[w];
+    for (int s = lo; s < hi; ++s)
+        if (mark[s] == 0) {
+            dst[j] = s;
+            src[j] = list[n_inside + j];  // the j-th survivor beyond the prefix
+            ++j;
+        }
+    __syncthreads();  // every read of the old list is done
+    for (int i = tid; i < n; i += kPlanThreads) list[i] = i;
+    if (tid == 0) D.ctl[CTL_NSWAP + level] = n - n_inside;
+}
+
+// base[row][src[j]] <-> base[row][dst[j]] for every pair j and every row of a [rows][stride] array.
+template <typename E>
+__global__ void __launch_bounds__(128) k_swap_rows(E* base, size_t stride, int rows, const int* __restrict__ src,
+                                                   const int* __restrict__ dst, const int* __restrict__ m_ptr) {
+    const int m = *m_ptr;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const int a = src[j], b = dst[j];
+        for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+            E* p = base + size_t(row) * stride;
+            const E va = p[a], vb = p[b];
+            p[a] = vb;
+            p[b] = va;
+        }
+    }
+}
+
+// the same for the tiled derivative records
+template <typename T>
+__global__ void __launch_bounds__(128) k_swap_records(Dev<T> D, const int* __restrict__ src, const int* __restrict__ dst,
+                                                      const int* __restrict__ m_ptr) {
+    const int m = *m_ptr;
+    const int rows = (D.N + 1) * kRecFields;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const int a = src[j], b = dst[j];
+        for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+            const int k = row / kRecFields, c = row % kRecFields;
+            T* pa = rec_at(D, k, a) + c * kRecFS;
+            T* pb = rec_at(D, k, b) + c * kRecFS;
+            const T va = *pa, vb = *pb;
+            *pa = vb;
+            *pb = va;
+        }
+    }
 }
 
 // Writes a buffer larger than L2 so that the next timed launch starts cold.
