@@ -244,7 +244,8 @@ def test_large_batch_work_lists():
 
 
 def test_repack_two_levels_and_warm_state():
-    """B = 163840: two repacks (to <= 20480, then <= 2560 slots).  Same bits as the plain solve, and the
+    """B = 163840: the survivors are repacked every time they are down to half of the slots in use (four
+    levels down to <= 16384 slots).  Same bits as the plain solve, and the
     per-instance state that outlives a solve (warm-start controls) ends up in its own slot again: a
     second, warm-started solve agrees too."""
     pb = cb.synthetic_batch("C1", 163840, N=50)

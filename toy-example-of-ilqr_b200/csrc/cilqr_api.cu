@@ -287,8 +287,8 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.wide, Bs))) return r;
         if ((r = dalloc(h, &D.act, 2 * Bs))) return r;
         if ((r = dalloc(h, &D.scan_state, Bs / 128 + 1))) return r;
-        if ((r = dalloc(h, &D.swap_src, size_t(kRepackLevels) * (Bs / 8 + 1)))) return r;
-        if ((r = dalloc(h, &D.swap_dst, size_t(kRepackLevels) * (Bs / 8 + 1)))) return r;
+        if ((r = dalloc(h, &D.swap_src, Bs + 8))) return r;
+        if ((r = dalloc(h, &D.swap_dst, Bs + 8))) return r;
         if ((r = dalloc(h, &D.rec, size_t(N + 1) * kRecFields * Bs))) return r;
         if ((r = dalloc(h, &D.Kg, size_t(N) * 8 * Bs))) return r;
         if ((r = dalloc(h, &D.dg, size_t(N) * 2 * Bs))) return r;
@@ -576,13 +576,12 @@ void launch_cost(Impl<T>* h, int B, int trial, int count, bool lat, bool matched
 // Exchange the slot pairs of repack `level` in every per-instance array (see k_plan_repack): moves the
 // survivors into the prefix, and — applied a second time — back.  m_bound >= the number of pairs.
 template <typename T>
-void swap_instances(Impl<T>* h, int level, int m_bound) {
+void swap_instances(Impl<T>* h, int level, int offset, int m_bound) {
     const Dev<T>& D = h->D;
     const size_t Bs = D.Bs;
     const int N = D.N;
-    const int cap = D.Bs / 8 + 1;
-    const int* src = D.swap_src + size_t(level) * cap;
-    const int* dst = D.swap_dst + size_t(level) * cap;
+    const int* src = D.swap_src + offset;
+    const int* dst = D.swap_dst + offset;
     const int* m = D.ctl + CTL_NSWAP + level;
     const int gx = std::max(1, std::min((m_bound + 127) / 128, kGridCap));
     auto rows_t = [&](T* p, int rows) {
@@ -661,19 +660,22 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // the kernel variants (all variants of a stage return the same bits, so a big batch switches to
     // the latency-regime kernels for its stragglers).
     int launched = 0;
-    int level = 0, repack_bound[kRepackLevels];
+    int level = 0, repack_bound[kRepackLevels], repack_off[kRepackLevels + 1] = {0};
     while (launched < h->max_rounds) {
         const unsigned long long w = progress[0];
         const int done = int(w >> 32);
         if (done > 0 && unsigned(w) == 0u) break;
         if (launched - done > h->run_ahead) continue;  // spin on the mapped words
         const int n_bound = std::max(1, std::min(B, int(unsigned(progress[1]))));
-        // Repack: the survivors of a large batch have thinned out to an eighth of the slots in use ->
-        // move them into a dense prefix (swap_instances) and carry on as a batch of that size.
-        if (h->repack && level < kRepackLevels && B > h->prefetch_below && size_t(n_bound) * 8 <= size_t(B)) {
-            LAUNCH(h, k_plan_repack<T>, dim3(1), kPlanThreads, h->D, launched & 1, level);
-            swap_instances(h, level, n_bound);
-            repack_bound[level++] = n_bound;
+        // Repack: the survivors of a large batch have thinned out to half of the slots in use -> move
+        // them into a dense prefix (swap_instances) and carry on as a batch of that size.
+        if (h->repack && level < kRepackLevels && B > h->prefetch_below && size_t(n_bound) * 2 <= size_t(B)) {
+            LAUNCH(h, k_plan_repack<T>, dim3(1), kPlanThreads, h->D, launched & 1, level, h->D.swap_src + repack_off[level],
+                   h->D.swap_dst + repack_off[level]);
+            swap_instances(h, level, repack_off[level], n_bound);
+            repack_bound[level] = n_bound;
+            repack_off[level + 1] = repack_off[level] + n_bound;  // <= B / 2 pairs per level: < Bs in total
+            ++level;
             B = n_bound;
         }
         const int trial_bound = int(std::min<long long>(h->D.Vs, (long long)n_bound * kNumAlphas));
@@ -729,7 +731,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // every instance back into its own slot
     while (level > 0) {
         --level;
-        swap_instances(h, level, repack_bound[level]);
+        swap_instances(h, level, repack_off[level], repack_bound[level]);
     }
     B = Bfull;
     LAUNCH(h, k_store_last_u<T>, gs2(B, N), 128, h->D, B);

@@ -45,7 +45,7 @@ constexpr int kRecTile = 32;
 constexpr int kRecFS = kRecTile;  // field stride in scalars
 
 constexpr int kNumAlphas = 20;  // alpha = 2^0 .. 2^-19  (cpp:354)
-constexpr int kRepackLevels = 3;
+constexpr int kRepackLevels = 8;
 
 enum Phase : int { PH_BACKWARD = 0, PH_SEARCH = 1, PH_DONE = 2 };
 enum Status : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BWD_FAIL = 2, ST_FWD_FAIL = 3, ST_SMALL_STEP = 4 };
@@ -56,8 +56,8 @@ enum Ctl : int {
     CTL_NACT = 5,   // [2] entries in the two work lists (round parity)
     CTL_CHUNK = 7,  // next chunk of the work list to hand out in the verdict kernel
     CTL_TALLY = 8,  // [2 words, one 64-bit counter] verdict kernel: blocks done << 47 | trials << 23 | running
-    CTL_NSWAP = 10,  // [kRepackLevels] slot pairs exchanged by each repack of the solve
-    CTL_WORDS = 16
+    CTL_NSWAP = 16,  // [kRepackLevels] slot pairs exchanged by each repack of the solve
+    CTL_WORDS = 32
 };
 
 // Everything a kernel needs, passed by value.
@@ -121,8 +121,9 @@ struct Dev {
     // pass: per-chunk counts chained through scan_state with decoupled look-back)
     int* act;
     unsigned long long* scan_state;  // [Bs / 128 + 1]  epoch << 34 | flag << 32 | count
-    // repack (large batches): slot pairs (src beyond the prefix, dst a hole inside it) of each level
-    int* swap_src;  // [kRepackLevels][Bs / 8 + 1]
+    // repack (large batches): slot pairs (src beyond the prefix, dst a hole inside it), the levels of
+    // one solve stacked one after the other (each level has at most half the pairs of the one before)
+    int* swap_src;  // [Bs + 8]
     int* swap_dst;
     T* last_u;   // [N][2][Bs]
     int* first;  // [Bs]
@@ -1801,8 +1802,9 @@ __global__ void k_tile_records(Dev<T> D, int B0, int B) {
 // Repack (bandwidth-bound batches).  Every array is [row][batch]: once most instances have finished,
 // each 8-byte access of a survivor still costs a 32-byte sector (and a scattered 8-byte store a sector
 // read-modify-write), so a round over n scattered survivors costs several times a round over a dense
-// batch of n.  When the work list has shrunk to an eighth of the slots in use, the survivors are
-// moved into the prefix [0, n): the survivors beyond the prefix trade places with the finished
+// batch of n.  When the work list has shrunk to half of the slots in use (measured: halving beats
+// waiting for a quarter or an eighth, profiles/r01b_findings.txt), the survivors are moved into the
+// prefix [0, n): the survivors beyond the prefix trade places with the finished
 // instances inside it (disjoint slot pairs, every per-instance array swapped in place), the work list
 // becomes 0 .. n-1, and the solve carries on as a dense batch of n.  The same swaps applied again at
 // the end of the solve put every instance back into its own slot.
@@ -1811,16 +1813,13 @@ constexpr int kPlanThreads = 1024;
 
 // One block: the list of round `par` (sorted, n entries) -> swap pairs of `level`, then list := 0 .. n-1.
 template <typename T>
-__global__ void __launch_bounds__(kPlanThreads) k_plan_repack(Dev<T> D, int par, int level) {
+__global__ void __launch_bounds__(kPlanThreads) k_plan_repack(Dev<T> D, int par, int level, int* src, int* dst) {
     __shared__ int s_part[kPlanThreads / 32];
     __shared__ int s_inside;
     const size_t Bs = D.Bs;
     int* list = D.act + size_t(par) * Bs;
     int* mark = D.act + size_t(par ^ 1) * Bs;  // the other list is free between rounds
     const int n = D.ctl[CTL_NACT + par];
-    const int cap = D.Bs / 8 + 1;
-    int* src = D.swap_src + size_t(level) * cap;
-    int* dst = D.swap_dst + size_t(level) * cap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int s = tid; s < n; s += kPlanThreads) mark[s] = 0;
     __syncthreads();
