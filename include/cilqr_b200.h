@@ -171,10 +171,10 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *  CILQR_OPT_STAGED_BACKWARD (default 1): latency-bound batches run the backward pass with one warp
  *      per tile of 32 instances, each step's record brought into a shared-memory ring by bulk
  *      asynchronous copies (cp.async.bulk + mbarrier) three steps ahead of the recursion.
- *  CILQR_OPT_REPACK (default 1): whenever the instances still running are down to half of the slots in use
- *      (batches above CILQR_OPT_PREFETCH_BELOW), they are moved into a dense prefix of the device
- *      arrays and the solve carries on as a batch of that size; every instance is moved back into
- *      its own slot before the solve returns. */
+ *  CILQR_OPT_REPACK (default 1): whenever the instances still running are down to half of the slots in
+ *      use (batches above 4096), they are moved into a dense prefix of the device arrays and the
+ *      solve carries on as a batch of that size; every instance is moved back into its own slot
+ *      before the solve returns.  0 disables; a value > 1 sets the smallest batch still repacked. */
 typedef enum cilqr_option_t {
     CILQR_OPT_WIDE_SEARCH = 0,
     CILQR_OPT_RUN_AHEAD = 1,

@@ -45,7 +45,7 @@ constexpr int kRecTile = 32;
 constexpr int kRecFS = kRecTile;  // field stride in scalars
 
 constexpr int kNumAlphas = 20;  // alpha = 2^0 .. 2^-19  (cpp:354)
-constexpr int kRepackLevels = 8;
+constexpr int kRepackLevels = 10;
 
 enum Phase : int { PH_BACKWARD = 0, PH_SEARCH = 1, PH_DONE = 2 };
 enum Status : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BWD_FAIL = 2, ST_FWD_FAIL = 3, ST_SMALL_STEP = 4 };
