@@ -572,7 +572,8 @@ void launch_cost(Impl<T>* h, int B, int trial, int count, bool lat, bool matched
     if (lat) {
         LAUNCH_COST(h, 4, gk(count, h->N + 1), h->D, B, trial);
     } else {
-        LAUNCH_COST(h, 8, gk(count, h->N + 1), h->D, B, trial);
+        LAUNCH_COST(h, 8, gk(count, h->N + 1), h->D, B, trial ? 2 : 0);
+        if (trial) LAUNCH(h, k_sum_trials<T>, gs1(count), 128, h->D, B);
     }
 }
 

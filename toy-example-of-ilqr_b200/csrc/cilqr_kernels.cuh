@@ -417,6 +417,10 @@ __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int
     return cost;
 }
 
+// trial > 0: the trial pool.  trial == 1 also totals each trial's step costs in this kernel (the thread
+// that stores a trial's last step cost sums them in step order: one launch less per round, for
+// latency-bound batches); trial == 2 leaves the totals to k_sum_trials (bandwidth-bound batches: no
+// fence and no atomic per thread).
 template <typename T, int kMinBlocks, bool kAlm>
 __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int trial) {
     const View<T> V = view_of(D, trial);
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int t
         const int b = V.inst ? V.inst[v] : v;
         const T cost = step_cost_of<T, kAlm, (kMinBlocks <= 4 ? 4 : 2)>(D, V, b, v, k, V.ridx[size_t(k) * V.stride + v]);
         V.sc[size_t(k) * V.stride + v] = cost;
-        if (trial) {
+        if (trial == 1) {
             // the thread that stores the last step cost of a trial sums them in step order (fixed
             // order: the total is deterministic whichever thread ends up doing it)
             __threadfence();
@@ -441,6 +445,18 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int t
                 D.t_done[v] = 0;
             }
         }
+    }
+}
+
+// Total cost of every trial of the pool, step costs summed in step order (same bits as k_cost's own sum).
+template <typename T>
+__global__ void __launch_bounds__(128) k_sum_trials(Dev<T> D, int B) {
+    const int count = view_count(D, 1, B);
+    const size_t Vs = D.Vs;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += gridDim.x * blockDim.x) {
+        T J = 0;
+        for (int k = 0; k <= D.N; ++k) J += D.sc_t[size_t(k) * Vs + v];
+        D.J_t[v] = J;
     }
 }
 
