@@ -264,3 +264,27 @@ def test_repack_two_levels_and_warm_state():
         assert np.array_equal(getattr(outs[1][1], f), getattr(outs[0][1], f)), f
     assert outs[1][1].iters.sum() < outs[1][0].iters.sum()  # the warm start really was used
 
+
+@pytest.mark.parametrize("cfg,alm", [("C3", False), ("C1", True)])
+def test_repack_forced_on_small_batches(cfg, alm):
+    """Repack forced down to 8 slots (OPT_REPACK = 8): 333 instances go through half a dozen levels of
+    swaps, with mixed templates (C3), the decision trace switched on, and the augmented-Lagrangian
+    state (multipliers, rho) in the ALM case.  Same bits, same trace as without."""
+    pb = cb.synthetic_batch(cfg, 333, N=50)
+    if alm:
+        for td in pb.templates:
+            td.params = dict(td.params, solve_type=1, alm_rho_init=20.0, alm_gamma=0.0, max_rho=20.0, max_mu=120.0,
+                             max_iter=30)
+    res = {}
+    with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, "f64") as s:
+        s.enable_trace(32)
+        for repack in (8, 0):
+            s.set_option(s.OPT_REPACK, repack)
+            out = s.solve(pb)
+            res[repack] = (out, s.get_trace(pb.B))
+    for f in ("u", "x", "J", "K", "d", "iters", "status", "exit_reason", "step_cost"):
+        assert np.array_equal(getattr(res[8][0], f), getattr(res[0][0], f), equal_nan=True), f
+    for a, b in zip(res[8][1], res[0][1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert res[8][0].iters.max() > 8 * res[8][0].iters.min() or res[8][0].iters.std() > 0  # instances really finish at different times
+
