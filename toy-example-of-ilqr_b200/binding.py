@@ -161,6 +161,7 @@ class BatchSolver:
     OPT_WIDE_SEARCH, OPT_RUN_AHEAD, OPT_PREFETCH_BELOW, OPT_BENCH_PREFETCH, OPT_PROFILE_STAGES, OPT_PIPELINE = 0, 1, 2, 3, 4, 5
     OPT_STAGED_BACKWARD = 6
     OPT_REPACK = 7
+    OPT_WIDE_STEP = 8
     STAGES = ["derivs", "backward", "forward", "ref_match", "cost", "decide"]
 
     def stage_times(self):

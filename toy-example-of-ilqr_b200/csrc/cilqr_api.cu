@@ -56,6 +56,7 @@ struct Base {
     unsigned scan_epoch = 0;  // tags the look-back words of one verdict launch (never 0, 30 bits)
     int pipeline = 1;  // latency regime: rollout and waypoint match as one two-stage kernel
     int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
+    int wide_step = 1; // bandwidth-bound rounds widen a line search step by step (2, 4, 8, 6 alphas) instead of all at once
     int repack = 1;    // survivors moved into a dense prefix whenever they are down to half of the slots in use
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
@@ -697,6 +698,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
         mark_stage(h, 1);
+        h->D.wide_step = (!lat && h->wide_step) ? 1 : 0;
         switch (backward_variant<T>(h, n_bound, B, lat)) {
             case 2:  // small batch: one warp per tile of 32 instances, records staged through shared memory
                 LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 1);
@@ -1191,6 +1193,9 @@ int do_set_option(Impl<T>* h, int option, int value) {
             return 0;
         case CILQR_OPT_STAGED_BACKWARD:
             h->staged = value ? 1 : 0;
+            return 0;
+        case CILQR_OPT_WIDE_STEP:
+            h->wide_step = value ? 1 : 0;
             return 0;
         case CILQR_OPT_REPACK:
             h->repack = value < 0 ? 0 : value;  // > 1: smallest batch that is still repacked (development)

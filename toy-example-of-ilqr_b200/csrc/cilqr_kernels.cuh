@@ -65,6 +65,8 @@ template <typename T>
 struct Dev {
     int N, Bs, Vs, max_obs, alm_cols;
     int wide_mode;     // 0: one alpha per round; 1: adaptive (all remaining alphas while in a rejection streak)
+    int wide_step;     // 1: in a streak, a round evaluates a0 + 2 more alphas instead of all that remain (2, 4, 8, 6:
+                       // bandwidth-bound rounds, where the 29 % of trials that full widening wastes cost real time)
     int trace_cap;     // iterations recorded per instance (0 = off)
     const DevParams<T>* P;  // [CILQR_B200_MAX_TEMPLATES]
     const T* wx;
@@ -971,7 +973,10 @@ __device__ __forceinline__ void after_backward(const Dev<T>& D, int b, bool ran,
     }
     if (ph == PH_SEARCH) {
         *a0 = D.aidx[b];
-        *want = (D.wide_mode && D.wide[b]) ? kNumAlphas - *a0 : 1;
+        const int rem = kNumAlphas - *a0;
+        int w = 1;
+        if (D.wide_mode && D.wide[b]) w = D.wide_step ? (rem < *a0 + 2 ? rem : *a0 + 2) : rem;
+        *want = w;
     }
 }
 
