@@ -723,9 +723,9 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         } else if (lat) {
             LAUNCH(h, k_forward2<T>, gs1(2 * trial_bound), 128, h->D, B);  // two lanes per trial slot
         } else {
-            LAUNCH(h, k_forward<T>, gs1(trial_bound), 128, h->D, B, 1);
+            LAUNCH(h, (k_forward<T, true>), gs1(trial_bound), 128, h->D, B, 1);  // rollout + waypoint match
         }
-        launch_cost(h, B, 1, trial_bound, lat, piped);
+        launch_cost(h, B, 1, trial_bound, lat, piped || !lat);
         mark_stage(h, 5);
         h->scan_epoch = (h->scan_epoch % 0x3fffffffu) + 1u;
         LAUNCH(h, k_decide<T>, gs1(n_bound), 128, h->D, B, par, h->scan_epoch);
@@ -991,7 +991,7 @@ int stage_forward(Impl<T>* h, int B, const double* u, const double* x, const dou
     if ((rc = pack_to_device(h, d, h->D.dg, B, 1, N * 2, N * 2, 1))) return rc;
     if ((rc = pack_to_device(h, K, h->D.Kg, B, 1, N * 8, N * 8, 1))) return rc;
     if ((rc = pack_to_device(h, alpha, h->D.alpha, B, 1, 1, 1, 1))) return rc;
-    LAUNCH(h, k_forward<T>, gs1(B), 128, h->D, B, 0);
+    LAUNCH(h, (k_forward<T, false>), gs1(B), 128, h->D, B, 0);
     if ((rc = unpack_to_host(h, h->D.Ut, new_u, B, N * 2, size_t(h->D.Vs)))) return rc;
     if ((rc = unpack_to_host(h, h->D.Xt, new_x, B, (N + 1) * 4, size_t(h->D.Vs)))) return rc;
     CK(cudaStreamSynchronize(h->stream));

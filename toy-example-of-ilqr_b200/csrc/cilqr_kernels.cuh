@@ -258,6 +258,27 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
 //     differ only for waypoints equidistant to within an ulp).
 //     G lanes per trajectory evaluate a window of G waypoints per probe.
 // ---------------------------------------------------------------------------
+// squared distance to a waypoint, with the operation order spelled out: every kernel that scans
+// (windowed or one by one) must compare the same bits
+template <typename T>
+__device__ __forceinline__ T wp_dist2(T px, T py, T wx, T wy) {
+    const T ex = px - wx, ey = py - wy;
+    return m_fma(ex, ex, ey * ey);
+}
+// the same scan, one waypoint at a time (inside the throughput-regime rollout, one thread per trial)
+template <typename T>
+__device__ __forceinline__ int match_from(const T* __restrict__ wx, const T* __restrict__ wy, int M, int start, T px, T py) {
+    int j = start;
+    T dj = wp_dist2(px, py, __ldg(wx + j), __ldg(wy + j));
+    while (j + 1 < M) {
+        const T dn = wp_dist2(px, py, __ldg(wx + j + 1), __ldg(wy + j + 1));
+        if (!(dn < dj)) break;
+        ++j;
+        dj = dn;
+    }
+    return j;
+}
+
 template <typename T, int G>
 __global__ void __launch_bounds__(128) k_ref_match(Dev<T> D, int B, int trial) {
     const View<T> V = view_of(D, trial);
@@ -296,8 +317,7 @@ __global__ void __launch_bounds__(128) k_ref_match(Dev<T> D, int B, int trial) {
                 int j = start + sub;
                 int jc = j < M ? j : M - 1;
                 // squared distance: the scan only compares distances, and x -> sqrt(x) is monotone
-                const T ex = px - __ldg(wx + jc), ey = py - __ldg(wy + jc);
-                T dj = ex * ex + ey * ey;
+                T dj = wp_dist2(px, py, __ldg(wx + jc), __ldg(wy + jc));
                 T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
                 bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
                 unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
@@ -1167,7 +1187,9 @@ __global__ void __launch_bounds__(32) k_backward_staged(Dev<T> D, int B, int sol
 //     one thread per trial slot.  In the solver alpha = 2^-aidx of the slot;
 //     the stage operator passes explicit alphas (slot v = instance v).
 // ---------------------------------------------------------------------------
-template <typename T>
+// kMatch: the waypoint match of each new position follows in the same thread (bandwidth-bound rounds:
+// no second pass over the trial pool; the scan of a step is ~9 waypoints at the usual speeds).
+template <typename T, bool kMatch>
 __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
@@ -1180,6 +1202,15 @@ __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
         const T p_dt = Pp->dt, p_wb = Pp->wheelbase;
         const int p_ref = Pp->ref_point;
         const T alpha = solver ? T(1) / T(1 << D.t_aidx[v]) : D.alpha[b];
+        const T* wx = D.wx + Pp->wp_off;
+        const T* wy = D.wy + Pp->wp_off;
+        const int wp_len = Pp->wp_len;
+        int match = 0;
+        if (kMatch) {
+            // x'_0 = x_0: the match of step 0 is the current trajectory's
+            match = D.ridx[b];
+            D.ridx_t[v] = match;
+        }
         T xn[4];
         // operands of step i+1 are fetched while step i computes: the rollout is one serial
         // dependency chain, so load latency must stay off it
@@ -1223,6 +1254,10 @@ __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
             }
             T nx[4];
             propagate(xn, un[0], un[1], p_dt, p_wb, p_ref, nx);
+            if (kMatch) {
+                match = match_from(wx, wy, wp_len, match, nx[0], nx[1]);
+                D.ridx_t[size_t(i + 1) * Vs + v] = match;
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 xn[c] = nx[c];
@@ -1465,8 +1500,7 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
                 while (!__all_sync(0xffffffffu, done)) {
                     int j = start + sub;
                     int jc = j < M ? j : M - 1;
-                    const T ex = px - __ldg(wx + jc), ey = py - __ldg(wy + jc);
-                    T dj = ex * ex + ey * ey;
+                    T dj = wp_dist2(px, py, __ldg(wx + jc), __ldg(wy + jc));
                     T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
                     bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
                     unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;

@@ -60,6 +60,8 @@ __device__ __forceinline__ double m_hypot(double a, double b) { return hypot(a, 
 __device__ __forceinline__ float m_hypot(float a, float b) { return hypotf(a, b); }
 __device__ __forceinline__ double m_sqrt(double v) { return sqrt(v); }
 __device__ __forceinline__ float m_sqrt(float v) { return sqrtf(v); }
+__device__ __forceinline__ double m_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float m_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double m_fabs(double v) { return fabs(v); }
 __device__ __forceinline__ float m_fabs(float v) { return fabsf(v); }
 // Loads that must be ISSUED where they are written: the compiler otherwise sinks a software
