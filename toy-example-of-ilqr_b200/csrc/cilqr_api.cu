@@ -35,6 +35,9 @@ int fail(int code, const char* fmt, ...) {
             return fail(CILQR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+#ifndef CILQR_COST_MINB_T
+#define CILQR_COST_MINB_T 8
+#endif
 constexpr int kGridCap = 148 * 32;  // grid-stride kernels: at most 32 CTAs of 128 threads per SM (queued beyond residency)
 // smallest batch that is still repacked: below it a round is a latency chain whatever the slots'
 // order (measured: 8192 instances 20.7 -> 19.5 ms with repacks down to 4096, 4096 unchanged)
@@ -573,7 +576,7 @@ void launch_cost(Impl<T>* h, int B, int trial, int count, bool lat, bool matched
     if (lat) {
         LAUNCH_COST(h, 4, gk(count, h->N + 1), h->D, B, trial);
     } else {
-        LAUNCH_COST(h, 8, gk(count, h->N + 1), h->D, B, trial ? 2 : 0);
+        LAUNCH_COST(h, CILQR_COST_MINB_T, gk(count, h->N + 1), h->D, B, trial ? 2 : 0);
         if (trial) LAUNCH(h, k_sum_trials<T>, gs1(count), 128, h->D, B);
     }
 }

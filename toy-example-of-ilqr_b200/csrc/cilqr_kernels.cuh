@@ -525,7 +525,13 @@ __device__ __forceinline__ void constraint_weights(bool alm, T c, T q1, T q2, T 
 //     cache rule for rejected steps (cpp:469-474).
 // ---------------------------------------------------------------------------
 template <typename T, int kPart, bool kAlm>
-__global__ void __launch_bounds__(128, kPart < 0 ? 4 : 8) k_derivs(Dev<T> D, int B, int masked, int par) {
+#ifndef CILQR_DERIVS0_MINB
+#define CILQR_DERIVS0_MINB 8
+#endif
+#ifndef CILQR_DERIVS1_MINB
+#define CILQR_DERIVS1_MINB 8
+#endif
+__global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIVS0_MINB : CILQR_DERIVS1_MINB)) k_derivs(Dev<T> D, int B, int masked, int par) {
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
     // two independent halves per (instance, step): part 0 = state terms (l_x, l_xx), part 1 = control
