@@ -2,27 +2,37 @@
 //
 // Memory layout ("step-major SoA"): every per-trajectory array is stored as
 // [step][field][batch] with the batch index innermost and a batch stride that is
-// a multiple of 128.  Consecutive lanes of a warp own consecutive trajectories,
-// so every global access below is a fully coalesced 128-byte (fp32) or 256-byte
-// (fp64) row, whichever stage is running:
+// a multiple of 128 (the derivative records: [step][tile of 32][field][32], see
+// rec_at).  Consecutive lanes of a warp own consecutive trajectories, so every
+// global access below is a fully coalesced 128-byte (fp32) or 256-byte (fp64)
+// row, whichever stage is running:
 //   * step-parallel stages (cost, derivatives): one thread per (trajectory, step);
 //   * serial chains (rollouts, Riccati recursion): one thread per trajectory, the
 //     4x4 / 4x2 / 2x2 blocks held in registers, A and B in their sparse form
-//     (5 + 4 non-trivial entries), V_xx / l_xx symmetric (10 entries);
+//     (5 + 4 non-trivial entries), V_xx / l_xx symmetric (10 entries); small
+//     batches feed the recursion from a shared-memory ring filled by bulk
+//     asynchronous copies (k_backward_staged);
 //   * waypoint matching: G lanes per trajectory scan a G-wide window of the
-//     reference line per probe and pick the first local minimum by ballot.
+//     reference line per probe and pick the first local minimum by ballot
+//     (k_ref_match, k_rollout_match), or the rollout thread scans on one by one
+//     (k_forward in bandwidth-bound rounds).
 // No tensor cores: the largest contraction is 4x4x4.
 //
 // Line search as a trial pool.  The reference tries alpha = 1, 1/2, ... one after
 // the other and keeps the first that passes (cpp:354-372).  Here every searching
 // instance claims `count` consecutive slots of a trial pool per round — one slot
-// normally, all remaining alphas while it is in a streak of rejected steps — the
-// pool is rolled out / matched / costed in bulk, and the verdict kernel walks the
-// instance's slots in alpha order and takes the first that passes: same decision,
-// up to 20x fewer dependent rounds for the stragglers.
+// normally, more while it is in a streak of rejected steps — the pool is rolled
+// out / matched / costed in bulk, and the verdict kernel walks the instance's
+// slots in alpha order and takes the first that passes: same decision, up to
+// 20x fewer dependent rounds for the stragglers.
 //
-// All kernels are grid-stride over device-side counts, so one launch shape serves
-// every round (grids are sized in multiples of the 148 SMs by the host).
+// Work lists and repack.  A round touches only the instances still running (a
+// list kept in instance order by the verdict kernel), and whenever they are down
+// to half of the slots in use they are swapped into a dense prefix of every
+// array (k_plan_repack, k_swap_rows) — and back at the end of the solve.
+//
+// All kernels are grid-stride over device-side counts; the host sizes the grids
+// from the last list length it has seen (an upper bound: lists only shrink).
 #pragma once
 
 #include "cilqr_model.cuh"
