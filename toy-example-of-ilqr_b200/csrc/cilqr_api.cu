@@ -731,7 +731,9 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         launch_cost(h, B, 1, trial_bound, lat, piped || !lat);
         mark_stage(h, 5);
         h->scan_epoch = (h->scan_epoch % 0x3fffffffu) + 1u;
-        LAUNCH(h, k_decide<T>, gs1(n_bound), 128, h->D, B, par, h->scan_epoch);
+        // one CTA per chunk of the work list, never fewer (no striding): a CTA that went on to a second
+        // chunk would wait, in the look-back, on chunks whose CTAs cannot start before it exits
+        LAUNCH(h, k_decide<T>, dim3((n_bound + 127) / 128), 128, h->D, B, par, h->scan_epoch);
         mark_stage(h, -1);
         ++launched;
     }

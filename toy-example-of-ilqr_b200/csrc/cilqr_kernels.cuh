@@ -1549,8 +1549,8 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
 //     step the derivative stage has yet to commit), keeping instance order: a
 //     block handles chunks of 128 list entries, scans its survivors, and chains
 //     its count to the preceding chunks' through scan_state (decoupled
-//     look-back; chunks are handed out by ticket, so a chunk only ever waits on
-//     chunks whose blocks are already running).  The last block to finish
+//     look-back; one chunk per CTA, handed out by ticket, so a chunk only ever
+//     waits on chunks whose CTAs are already running).  The last block to finish
 //     publishes progress to the host and re-arms the round counters.
 // ---------------------------------------------------------------------------
 constexpr unsigned long long kScanAgg = 1ull << 32, kScanIncl = 2ull << 32;
@@ -1574,7 +1574,10 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
     const bool by_ticket = gridDim.x > 2 * 148;
     if (threadIdx.x == 0) s_chunk = by_ticket ? atomicAdd(&D.ctl[CTL_CHUNK], 1) : int(blockIdx.x);
     __syncthreads();
-    for (int chunk = s_chunk; chunk < n_chunks; chunk += gridDim.x) {
+    // One chunk per CTA: the host launches ceil(n_bound / 128) >= n_chunks CTAs.  (A CTA must not take a
+    // second chunk: with more CTAs than fit on the GPU it would wait on chunks whose CTAs can only
+    // start once it has exited.)  Written as a loop so that the tail of the kernel is reached uniformly.
+    for (int chunk = s_chunk; chunk < n_chunks; chunk = n_chunks) {
         const int idx = chunk * int(blockDim.x) + int(threadIdx.x);
         const bool in = idx < n;
         const int b = in ? list[idx] : 0;
