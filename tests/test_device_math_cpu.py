@@ -100,3 +100,28 @@ def test_pd_filter_never_overrules_the_exact_llt_test(dtype):
             sure = (a00 > 0) & (d > margin * a10sq)
             assert not np.any(sure & exact_fails)
             assert sure.mean() > 0.1  # the filter does fire on the well-conditioned part
+
+
+def test_gravity_model_heading_by_angle_addition():
+    """step_trig (csrc/cilqr_model.cuh): for the centre-of-gravity model sin / cos of beta = atan(tan(steer) / 2) are
+    taken from tan(beta) and the heading (beta + yaw) by angle addition, instead of atan + a third sin/cos as the
+    reference does (src/utils.cpp:262-283).  The documented bound: a few 1e-16 absolute on the heading, a few ulp on
+    the turn term."""
+    rng = np.random.default_rng(11)
+    n = 1_000_000
+    steer = rng.uniform(-1.2, 1.2, n)
+    yaw = rng.uniform(-3.2, 3.2, n)
+    # reference sequence
+    beta = np.arctan(np.tan(steer) / 2)
+    ref_s, ref_c, ref_turn = np.sin(beta + yaw), np.cos(beta + yaw), np.sin(beta)
+    # device sequence
+    td = np.sin(steer) / np.cos(steer)
+    tb = 0.5 * td
+    cb = 1.0 / np.sqrt(1.0 + tb * tb)
+    sb = tb * cb
+    s_head = sb * np.cos(yaw) + cb * np.sin(yaw)
+    c_head = cb * np.cos(yaw) - sb * np.sin(yaw)
+    assert np.abs(s_head - ref_s).max() < 6e-16 and np.abs(c_head - ref_c).max() < 6e-16
+    assert np.abs(sb - ref_turn).max() < 4e-16
+    nz = np.abs(ref_turn) > 1e-3
+    assert (np.abs(sb - ref_turn)[nz] / np.abs(ref_turn)[nz]).max() < 8 * np.finfo(float).eps
