@@ -174,10 +174,12 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *  CILQR_OPT_REPACK (default 1): whenever the instances still running are down to half of the slots in
  *      use (batches above 4096), they are moved into a dense prefix of the device arrays and the
  *      solve carries on as a batch of that size; every instance is moved back into its own slot
- *      before the solve returns.  0 disables; a value > 1 sets the smallest batch still repacked. */
- /* CILQR_OPT_WIDE_STEP (default 1): in bandwidth-bound rounds an instance in a streak of rejected steps
+ *      before the solve returns.  0 disables; a value > 1 sets the smallest batch still repacked.
+ *  CILQR_OPT_WIDE_STEP (default 1): in bandwidth-bound rounds an instance in a streak of rejected steps
  *      evaluates 2, 4, 8, 6 more alphas per round instead of all that remain (same decisions, ~18 % fewer
- *      trials; latency-bound rounds keep evaluating all of them at once). */
+ *      trials; latency-bound rounds keep evaluating all of them at once).
+ *  The regime threshold (CILQR_OPT_PREFETCH_BELOW) is applied per round to the number of instances still
+ *      running, so a large batch moves to the latency-regime kernels for its stragglers. */
 typedef enum cilqr_option_t {
     CILQR_OPT_WIDE_SEARCH = 0,
     CILQR_OPT_RUN_AHEAD = 1,
