@@ -27,6 +27,37 @@
 
 namespace cilqr_oracle {
 
+// Transcendentals of the restatement.  Default flavour: glibc's (std::), as the reference calls them; this is
+// the flavour pinned bit-for-bit to the reference sources (oracle/_ref).  -DCILQR_ORACLE_PMATH ("pm" flavour,
+// liboracle_pm.so): the portable implementations the PARITY build of the CUDA library uses too
+// (toy-example-of-ilqr_b200/csrc/cilqr_pmath.h — pure IEEE add/mul/div/sqrt/fma, identical bits under gcc and nvcc),
+// so that the GPU parity build can be compared with this restatement bit for bit.  sq(x) = std::pow(x, 2).
+#ifdef CILQR_ORACLE_PMATH
+}  // namespace cilqr_oracle
+#include "../toy-example-of-ilqr_b200/csrc/cilqr_pmath.h"
+namespace cilqr_oracle {
+namespace om {
+template <typename T> inline T sin(T v) { return cilqr_pm::pm_sin(v); }
+template <typename T> inline T cos(T v) { return cilqr_pm::pm_cos(v); }
+template <typename T> inline T tan(T v) { return cilqr_pm::pm_tan(v); }
+template <typename T> inline T atan(T v) { return cilqr_pm::pm_atan(v); }
+template <typename T> inline T exp(T v) { return cilqr_pm::pm_exp(v); }
+template <typename T> inline T hypot(T a, T b) { return cilqr_pm::pm_hypot(a, b); }
+template <typename T> inline T sq(T v) { return v * v; }
+}  // namespace om
+#else
+namespace om {
+using std::sin;
+using std::cos;
+using std::tan;
+using std::atan;
+using std::exp;
+using std::hypot;
+template <typename T> inline T sq(T v) { return std::pow(v, T(2)); }
+}  // namespace om
+#endif
+
+
 // Plain-data mirror of the scalars the reference constructor reads
 // (src/cilqr_solver.cpp:17-83).  Field order is shared with the ctypes
 // Structure in tests/ (python side: cilqr_params fields).
@@ -90,17 +121,17 @@ struct Problem {
 template <typename T>
 inline void kinematic_propagate(const T x[4], const T u[2], T dt, T wheelbase, int ref_point,
                                 T out[4]) {
-    T beta = std::atan(std::tan(u[1]) / 2);
+    T beta = om::atan(om::tan(u[1]) / 2);
     if (ref_point == 0) {
-        out[0] = x[0] + x[2] * std::cos(x[3]) * dt;
-        out[1] = x[1] + x[2] * std::sin(x[3]) * dt;
+        out[0] = x[0] + x[2] * om::cos(x[3]) * dt;
+        out[1] = x[1] + x[2] * om::sin(x[3]) * dt;
         out[2] = x[2] + u[0] * dt;
-        out[3] = x[3] + x[2] * std::tan(u[1]) * dt / wheelbase;
+        out[3] = x[3] + x[2] * om::tan(u[1]) * dt / wheelbase;
     } else {
-        out[0] = x[0] + x[2] * std::cos(beta + x[3]) * dt;
-        out[1] = x[1] + x[2] * std::sin(beta + x[3]) * dt;
+        out[0] = x[0] + x[2] * om::cos(beta + x[3]) * dt;
+        out[1] = x[1] + x[2] * om::sin(beta + x[3]) * dt;
         out[2] = x[2] + u[0] * dt;
-        out[3] = x[3] + 2 * x[2] * std::sin(beta) * dt / wheelbase;
+        out[3] = x[3] + 2 * x[2] * om::sin(beta) * dt / wheelbase;
     }
 }
 
@@ -114,28 +145,28 @@ inline void model_derivatives(const T x[4], const T u[2], T dt, T wheelbase, int
         for (int c = 0; c < 4; ++c) A[r * 4 + c] = (r == c) ? T(1) : T(0);
     for (int i = 0; i < 8; ++i) B[i] = 0;
     T velo = x[2], yaw = x[3], delta = u[1];
-    T beta = std::atan(std::tan(delta / 2));
-    T tan_d = std::tan(delta);
+    T beta = om::atan(om::tan(delta / 2));
+    T tan_d = om::tan(delta);
     T tan_sq = tan_d * tan_d;
     T beta_over_stl = T(0.5) * (1 + tan_sq) / (1 + T(0.25) * tan_sq);
     if (ref_point == 0) {
-        A[0 * 4 + 2] = std::cos(yaw) * dt;
-        A[0 * 4 + 3] = velo * (-std::sin(yaw)) * dt;
-        A[1 * 4 + 2] = std::sin(yaw) * dt;
-        A[1 * 4 + 3] = velo * std::cos(yaw) * dt;
-        A[3 * 4 + 2] = std::tan(delta) * dt / wheelbase;
+        A[0 * 4 + 2] = om::cos(yaw) * dt;
+        A[0 * 4 + 3] = velo * (-om::sin(yaw)) * dt;
+        A[1 * 4 + 2] = om::sin(yaw) * dt;
+        A[1 * 4 + 3] = velo * om::cos(yaw) * dt;
+        A[3 * 4 + 2] = om::tan(delta) * dt / wheelbase;
         B[2 * 2 + 0] = dt;
-        B[3 * 2 + 1] = (velo * dt / wheelbase) / (std::cos(delta) * std::cos(delta));
+        B[3 * 2 + 1] = (velo * dt / wheelbase) / (om::cos(delta) * om::cos(delta));
     } else {
-        A[0 * 4 + 2] = std::cos(beta + yaw) * dt;
-        A[0 * 4 + 3] = velo * (-std::sin(beta + yaw)) * dt;
-        A[1 * 4 + 2] = std::sin(beta + yaw) * dt;
-        A[1 * 4 + 3] = velo * std::cos(beta + yaw) * dt;
-        A[3 * 4 + 2] = 2 * std::sin(beta) * dt / wheelbase;
-        B[0 * 2 + 1] = velo * (-std::sin(beta + yaw)) * dt * beta_over_stl;
-        B[1 * 2 + 1] = velo * std::cos(beta + yaw) * dt * beta_over_stl;
+        A[0 * 4 + 2] = om::cos(beta + yaw) * dt;
+        A[0 * 4 + 3] = velo * (-om::sin(beta + yaw)) * dt;
+        A[1 * 4 + 2] = om::sin(beta + yaw) * dt;
+        A[1 * 4 + 3] = velo * om::cos(beta + yaw) * dt;
+        A[3 * 4 + 2] = 2 * om::sin(beta) * dt / wheelbase;
+        B[0 * 2 + 1] = velo * (-om::sin(beta + yaw)) * dt * beta_over_stl;
+        B[1 * 2 + 1] = velo * om::cos(beta + yaw) * dt * beta_over_stl;
         B[2 * 2 + 0] = dt;
-        B[3 * 2 + 1] = (2 * velo * dt / wheelbase) * std::cos(beta) * beta_over_stl;
+        B[3 * 2 + 1] = (2 * velo * dt / wheelbase) * om::cos(beta) * beta_over_stl;
     }
 }
 
@@ -143,7 +174,7 @@ inline void model_derivatives(const T x[4], const T u[2], T dt, T wheelbase, int
 template <typename T>
 inline void front_rear_centers(const T x[4], T wheelbase, int ref_point, T front[2], T rear[2]) {
     T yaw = x[3];
-    T wv[2] = {wheelbase * std::cos(yaw), wheelbase * std::sin(yaw)};
+    T wv[2] = {wheelbase * om::cos(yaw), wheelbase * om::sin(yaw)};
     if (ref_point == 0) {
         front[0] = x[0] + wv[0];
         front[1] = x[1] + wv[1];
@@ -171,10 +202,10 @@ template <typename T>
 inline T ellipse_margin(const T pnt[2], const T obs[3], const T ab[2]) {
     T theta = obs[2];
     T dx = pnt[0] - obs[0], dy = pnt[1] - obs[1];
-    T c = std::cos(theta), s = std::sin(theta);
+    T c = om::cos(theta), s = om::sin(theta);
     T xs = c * dx + s * dy;
     T ys = -s * dx + c * dy;
-    return 1 - (std::pow(xs, T(2)) / std::pow(ab[0], T(2)) + std::pow(ys, T(2)) / std::pow(ab[1], T(2)));
+    return 1 - (om::sq(xs) / om::sq(ab[0]) + om::sq(ys) / om::sq(ab[1]));
 }
 
 // src/utils.cpp:409-439 — gradient of the margin w.r.t. the point.
@@ -182,10 +213,10 @@ template <typename T>
 inline void ellipse_margin_grad(const T pnt[2], const T obs[3], const T ab[2], T g[2]) {
     T theta = obs[2];
     T dx = pnt[0] - obs[0], dy = pnt[1] - obs[1];
-    T c = std::cos(theta), s = std::sin(theta);
+    T c = om::cos(theta), s = om::sin(theta);
     T xs = c * dx + s * dy;
     T ys = -s * dx + c * dy;
-    T gs[2] = {-2 * xs / std::pow(ab[0], T(2)), -2 * ys / std::pow(ab[1], T(2))};
+    T gs[2] = {-2 * xs / om::sq(ab[0]), -2 * ys / om::sq(ab[1])};
     // rotation^T * gs, then identity * that (:427-436)
     g[0] = c * gs[0] + (-s) * gs[1];
     g[1] = s * gs[0] + c * gs[1];
@@ -212,11 +243,11 @@ inline void obstacle_constr_grad(const Params& p, const T x[4], const T obs[3], 
     T yaw = x[3];
     T half = T(0.5) * T(p.wheelbase);
     // 4x2 Jacobians (rows = state component, cols = point component)
-    T Jf[4][2] = {{1, 0}, {0, 1}, {0, 0}, {half * (-std::sin(yaw)), half * std::cos(yaw)}};
-    T Jr[4][2] = {{1, 0}, {0, 1}, {0, 0}, {-half * (-std::sin(yaw)), -half * std::cos(yaw)}};
+    T Jf[4][2] = {{1, 0}, {0, 1}, {0, 0}, {half * (-om::sin(yaw)), half * om::cos(yaw)}};
+    T Jr[4][2] = {{1, 0}, {0, 1}, {0, 0}, {-half * (-om::sin(yaw)), -half * om::cos(yaw)}};
     if (p.reference_point == 0) {
-        Jf[3][0] = T(p.wheelbase) * (-std::sin(yaw));
-        Jf[3][1] = T(p.wheelbase) * std::cos(yaw);
+        Jf[3][0] = T(p.wheelbase) * (-om::sin(yaw));
+        Jf[3][1] = T(p.wheelbase) * om::cos(yaw);
         Jr[3][0] = 0;
         Jr[3][1] = 0;
     }
@@ -282,7 +313,7 @@ class Solver {
             int32_t min_idx = -1;
             T min_d = std::numeric_limits<T>::max();
             for (size_t j = start; j < size_t(pb.M); ++j) {
-                T cur = std::hypot(x[i * 4 + 0] - pb.wx[j], x[i * 4 + 1] - pb.wy[j]);
+                T cur = om::hypot(x[i * 4 + 0] - pb.wx[j], x[i * 4 + 1] - pb.wy[j]);
                 if (min_idx < 0 || cur < min_d) {
                     min_idx = int32_t(j);
                     min_d = cur;
@@ -296,9 +327,9 @@ class Solver {
     }
 
     T alm_item(T c, T rho, T mu) const {  // hpp:81-83
-        return rho * std::pow(std::max(c + mu / rho, T(0)), T(2)) / 2;
+        return rho * om::sq(std::max(c + mu / rho, T(0))) / 2;
     }
-    T exp_barrier(T c, T q1, T q2) const { return q1 * std::exp(q2 * c); }  // hpp:80
+    T exp_barrier(T c, T q1, T q2) const { return q1 * om::exp(q2 * c); }  // hpp:80
 
     // The eight box constraints of step k in the reference's order
     // (cpp:222-241 / :507-519): acc up/lo, steer up/lo, velocity up/lo, lateral up/lo.
@@ -310,8 +341,8 @@ class Solver {
         c[3] = -T(p.stl_lim) - uk[1];
         c[4] = xk[2] - T(p.velo_max);
         c[5] = T(p.velo_min) - xk[2];
-        T d_sign = (xk[1] - ref[1]) * std::cos(ref[2]) - (xk[0] - ref[0]) * std::sin(ref[2]);
-        T hyp = std::hypot(xk[0] - ref[0], xk[1] - ref[1]);
+        T d_sign = (xk[1] - ref[1]) * om::cos(ref[2]) - (xk[0] - ref[0]) * om::sin(ref[2]);
+        T hyp = om::hypot(xk[0] - ref[0], xk[1] - ref[1]);
         T cur_d = sign_of(d_sign) * hyp;
         c[6] = cur_d - (pb.border_up - T(p.width) / 2);
         c[7] = (pb.border_lo + T(p.width) / 2) - cur_d;
@@ -398,7 +429,7 @@ class Solver {
     void add_constraint(T c, const T* c_dot, int n, T q1, T q2, T mu, T* grad, T* hess) const {
         if (p.solve_type == 0) {
             T b = exp_barrier(c, q1, q2);
-            T q2sq = std::pow(q2, T(2));
+            T q2sq = om::sq(q2);
             for (int r = 0; r < n; ++r) grad[r] += q2 * b * c_dot[r];
             for (int r = 0; r < n; ++r)
                 for (int cc = 0; cc < n; ++cc) hess[r * n + cc] += q2sq * b * (c_dot[r] * c_dot[cc]);
@@ -439,8 +470,8 @@ class Solver {
             const T cu[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
             T cx[4][4] = {{0, 0, 1, 0}, {0, 0, -1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
             // lateral gradient (:527-533); hypot is re-evaluated per component in the reference
-            cx[2][0] = (xk[0] - ref[0]) / std::hypot(xk[0] - ref[0], xk[1] - ref[1]);
-            cx[2][1] = (xk[1] - ref[1]) / std::hypot(xk[0] - ref[0], xk[1] - ref[1]);
+            cx[2][0] = (xk[0] - ref[0]) / om::hypot(xk[0] - ref[0], xk[1] - ref[1]);
+            cx[2][1] = (xk[1] - ref[1]) / om::hypot(xk[0] - ref[0], xk[1] - ref[1]);
             if (d_sign < 0)
                 for (int r = 0; r < 4; ++r) cx[2][r] = -1 * cx[2][r];
             for (int r = 0; r < 4; ++r) cx[3][r] = -1 * cx[2][r];

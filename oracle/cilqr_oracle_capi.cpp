@@ -54,12 +54,29 @@ struct ProblemStore {
     }
 };
 
+// dtype codes of the C surface: 0 = fp64, 1 = fp32, 2 = x87 long double (64-bit mantissa; the "truth" the
+// parity tests measure fp64 implementations against; glibc flavour only).
+#ifdef CILQR_ORACLE_PMATH
+#define ORACLE_DISPATCH(dtype, FN, ...) ((dtype) == 0 ? FN<double>(__VA_ARGS__) : FN<float>(__VA_ARGS__))
+#else
+#define ORACLE_DISPATCH(dtype, FN, ...) \
+    ((dtype) == 0 ? FN<double>(__VA_ARGS__) : (dtype) == 1 ? FN<float>(__VA_ARGS__) : FN<long double>(__VA_ARGS__))
+#endif
+
 struct AnySolver {
     int dtype;
     int N;
-    Solver<double>* s64 = nullptr;
-    Solver<float>* s32 = nullptr;
+    virtual ~AnySolver() {}
 };
+template <typename T>
+struct TypedSolver : AnySolver {
+    Solver<T> s;
+    TypedSolver(const Params& p, int N_) : s(p, N_) {}
+};
+template <typename T>
+AnySolver* make_solver(const Params* p, int N) {
+    return new TypedSolver<T>(*p, N);
+}
 
 template <typename T>
 int do_total_cost(const Params* p, int N, int M, const double* wx, const double* wy,
@@ -156,159 +173,70 @@ void solve_one(Solver<T>& s, int M, const double* wx, const double* wy, const do
     if (lamb_out) *lamb_out = double(s.final_lamb);
 }
 
-}  // namespace
 
-extern "C" {
-
-int oracle_sizeof_params() { return int(sizeof(Params)); }
-
-int oracle_propagate(const Params* p, int dtype, const double* x, const double* u, double* out) {
-    if (dtype == 0) {
-        kinematic_propagate<double>(x, u, p->dt, p->wheelbase, p->reference_point, out);
-    } else {
-        float xf[4] = {float(x[0]), float(x[1]), float(x[2]), float(x[3])};
-        float uf[2] = {float(u[0]), float(u[1])};
-        float of[4];
-        kinematic_propagate<float>(xf, uf, float(p->dt), float(p->wheelbase), p->reference_point, of);
-        for (int c = 0; c < 4; ++c) out[c] = of[c];
-    }
+template <typename T>
+int do_propagate(const Params* p, const double* x, const double* u, double* out) {
+    T xf[4] = {T(x[0]), T(x[1]), T(x[2]), T(x[3])};
+    T uf[2] = {T(u[0]), T(u[1])};
+    T of[4];
+    kinematic_propagate<T>(xf, uf, T(p->dt), T(p->wheelbase), p->reference_point, of);
+    for (int c = 0; c < 4; ++c) out[c] = double(of[c]);
     return 0;
 }
 
-int oracle_dyn_derivs(const Params* p, int dtype, int N, const double* u, const double* x, double* A,
-                      double* B) {
-    if (dtype == 0) {
-        Solver<double> s(*p, N);
-        std::vector<double> a, b;
-        s.dyn_derivatives(u, x, a, b);
-        cast_out(a, A);
-        cast_out(b, B);
-    } else {
-        Solver<float> s(*p, N);
-        auto uu = cast_in<float>(u, size_t(N) * 2);
-        auto xx = cast_in<float>(x, size_t(N + 1) * 4);
-        std::vector<float> a, b;
-        s.dyn_derivatives(uu.data(), xx.data(), a, b);
-        cast_out(a, A);
-        cast_out(b, B);
-    }
+template <typename T>
+int do_dyn_derivs(const Params* p, int N, const double* u, const double* x, double* A, double* B) {
+    Solver<T> s(*p, N);
+    auto uu = cast_in<T>(u, size_t(N) * 2);
+    auto xx = cast_in<T>(x, size_t(N + 1) * 4);
+    std::vector<T> a, b;
+    s.dyn_derivatives(uu.data(), xx.data(), a, b);
+    cast_out(a, A);
+    cast_out(b, B);
     return 0;
 }
 
-int oracle_ref_match(int dtype, int M, const double* wx, const double* wy, int rows, const double* x,
-                     int32_t* idx_out) {
+template <typename T>
+int do_ref_match(int M, const double* wx, const double* wy, int rows, const double* x, int32_t* idx_out) {
     Params p{};
     std::vector<int> idx;
-    if (dtype == 0) {
-        Solver<double> s(p, rows - 1);
-        Problem<double> pb;
-        pb.wx = wx;
-        pb.wy = wy;
-        pb.M = M;
-        s.ref_match(pb, x, rows, idx);
-    } else {
-        Solver<float> s(p, rows - 1);
-        auto a = cast_in<float>(wx, M), b = cast_in<float>(wy, M);
-        auto xx = cast_in<float>(x, size_t(rows) * 4);
-        Problem<float> pb;
-        pb.wx = a.data();
-        pb.wy = b.data();
-        pb.M = M;
-        s.ref_match(pb, xx.data(), rows, idx);
-    }
+    Solver<T> s(p, rows - 1);
+    auto a = cast_in<T>(wx, M), b = cast_in<T>(wy, M);
+    auto xx = cast_in<T>(x, size_t(rows) * 4);
+    Problem<T> pb;
+    pb.wx = a.data();
+    pb.wy = b.data();
+    pb.M = M;
+    s.ref_match(pb, xx.data(), rows, idx);
     for (int i = 0; i < rows; ++i) idx_out[i] = idx[i];
     return 0;
 }
 
-int oracle_total_cost(const Params* p, int dtype, int N, int M, const double* wx, const double* wy,
-                      const double* wyaw, double ref_velo, int n_obs, int obs_len, const double* obs,
-                      const double* borders, const double* u, const double* x, const double* alm_mu,
-                      double alm_rho, double* J, double* step_cost) {
-    return dtype == 0 ? do_total_cost<double>(p, N, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs,
-                                              borders, u, x, alm_mu, alm_rho, J, step_cost)
-                      : do_total_cost<float>(p, N, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs,
-                                             borders, u, x, alm_mu, alm_rho, J, step_cost);
-}
-
-int oracle_cost_derivs(const Params* p, int dtype, int N, int M, const double* wx, const double* wy,
-                       const double* wyaw, double ref_velo, int n_obs, int obs_len, const double* obs,
-                       const double* borders, const double* u, const double* x, const double* alm_mu,
-                       double alm_rho, double* lx, double* lu, double* lxx, double* luu,
-                       double* alm_mu_next) {
-    return dtype == 0
-               ? do_cost_derivs<double>(p, N, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs, borders,
-                                        u, x, alm_mu, alm_rho, lx, lu, lxx, luu, alm_mu_next)
-               : do_cost_derivs<float>(p, N, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs, borders,
-                                       u, x, alm_mu, alm_rho, lx, lu, lxx, luu, alm_mu_next);
-}
-
-int oracle_riccati(int dtype, int N, const double* lx, const double* lu, const double* lxx,
-                   const double* luu, const double* A, const double* B, double lamb, double* d,
-                   double* K, double* dV, int32_t* status) {
-    return dtype == 0 ? do_riccati<double>(N, lx, lu, lxx, luu, A, B, lamb, d, K, dV, status)
-                      : do_riccati<float>(N, lx, lu, lxx, luu, A, B, lamb, d, K, dV, status);
-}
-
-int oracle_forward(const Params* p, int dtype, int N, const double* u, const double* x,
-                   const double* d, const double* K, double alpha, double* new_u, double* new_x) {
-    if (dtype == 0) {
-        Solver<double> s(*p, N);
-        s.forward_pass(u, x, d, K, alpha, new_u, new_x);
-    } else {
-        Solver<float> s(*p, N);
-        auto a = cast_in<float>(u, size_t(N) * 2), b = cast_in<float>(x, size_t(N + 1) * 4);
-        auto c = cast_in<float>(d, size_t(N) * 2), e = cast_in<float>(K, size_t(N) * 8);
-        std::vector<float> nu(size_t(N) * 2), nx(size_t(N + 1) * 4);
-        s.forward_pass(a.data(), b.data(), c.data(), e.data(), float(alpha), nu.data(), nx.data());
-        cast_out(nu, new_u);
-        cast_out(nx, new_x);
-    }
+template <typename T>
+int do_forward(const Params* p, int N, const double* u, const double* x, const double* d, const double* K,
+               double alpha, double* new_u, double* new_x) {
+    Solver<T> s(*p, N);
+    auto a = cast_in<T>(u, size_t(N) * 2), b = cast_in<T>(x, size_t(N + 1) * 4);
+    auto c = cast_in<T>(d, size_t(N) * 2), e = cast_in<T>(K, size_t(N) * 8);
+    std::vector<T> nu(size_t(N) * 2), nx(size_t(N + 1) * 4);
+    s.forward_pass(a.data(), b.data(), c.data(), e.data(), T(alpha), nu.data(), nx.data());
+    cast_out(nu, new_u);
+    cast_out(nx, new_x);
     return 0;
 }
 
-// Stateful solver (warm start, cached derivatives, ALM multipliers persist
-// between solve() calls exactly as in the reference object).
-void* oracle_solver_create(const Params* p, int dtype, int N) {
-    auto* a = new AnySolver;
-    a->dtype = dtype;
-    a->N = N;
-    if (dtype == 0)
-        a->s64 = new Solver<double>(*p, N);
-    else
-        a->s32 = new Solver<float>(*p, N);
-    return a;
-}
-
-void oracle_solver_destroy(void* h) {
-    auto* a = static_cast<AnySolver*>(h);
-    delete a->s64;
-    delete a->s32;
-    delete a;
-}
-
-// info = {status, iters, exit_reason, n_trace}.  trace (optional) receives up to
-// trace_cap rows of {status, alpha_index, effective, ori_cost, new_cost, lamb_after}.
-int oracle_solver_solve(void* h, int M, const double* wx, const double* wy, const double* wyaw,
-                        double ref_velo, int n_obs, int obs_len, const double* obs,
-                        const double* borders, const double* x0, double* u_out, double* x_out,
-                        double* K_out, double* d_out, double* J_out, double* step_cost_out,
-                        int32_t* info, double* lamb_out, double* trace, int trace_cap) {
-    auto* a = static_cast<AnySolver*>(h);
-    if (obs_len < a->N + 1 && n_obs > 0) return -2;  // RoutingLine::operator[] would throw (utils.cpp:52-58)
-    const std::vector<IterTrace>* tr;
-    if (a->dtype == 0) {
-        solve_one(*a->s64, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs, borders, x0, u_out, x_out,
-                  K_out, d_out, J_out, step_cost_out, info, lamb_out, trace != nullptr);
-        tr = &a->s64->trace;
-    } else {
-        solve_one(*a->s32, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs, borders, x0, u_out, x_out,
-                  K_out, d_out, J_out, step_cost_out, info, lamb_out, trace != nullptr);
-        tr = &a->s32->trace;
-    }
+template <typename T>
+int do_solver_solve(AnySolver* a, int M, const double* wx, const double* wy, const double* wyaw, double ref_velo,
+                    int n_obs, int obs_len, const double* obs, const double* borders, const double* x0,
+                    double* u_out, double* x_out, double* K_out, double* d_out, double* J_out,
+                    double* step_cost_out, int32_t* info, double* lamb_out, double* trace, int trace_cap) {
+    Solver<T>& s = static_cast<TypedSolver<T>*>(a)->s;
+    solve_one(s, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs, borders, x0, u_out, x_out, K_out, d_out, J_out,
+              step_cost_out, info, lamb_out, trace != nullptr);
     if (trace) {
-        int n = std::min<int>(int(tr->size()), trace_cap);
+        int n = std::min<int>(int(s.trace.size()), trace_cap);
         for (int i = 0; i < n; ++i) {
-            const IterTrace& t = (*tr)[i];
+            const IterTrace& t = s.trace[i];
             double* row = trace + size_t(i) * 6;
             row[0] = t.status;
             row[1] = t.alpha_index;
@@ -320,6 +248,90 @@ int oracle_solver_solve(void* h, int M, const double* wx, const double* wy, cons
         if (info) info[3] = n;
     }
     return 0;
+}
+
+template <typename T>
+int do_batch_one(const Params& prm, int N, int M, const double* wx, const double* wy, const double* wyaw,
+                 double ref_velo, int n_obs, int obs_len, const double* ob, const double* borders, const double* x0,
+                 double* uo, double* xo, double* Ko, double* dout, double* J2, int32_t* info, int trace_cap,
+                 std::vector<IterTrace>* tr_out) {
+    Solver<T> s(prm, N);
+    solve_one(s, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, ob, borders, x0, uo, xo, Ko, dout, J2, nullptr, info,
+              nullptr, trace_cap > 0);
+    *tr_out = s.trace;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oracle_sizeof_params() { return int(sizeof(Params)); }
+
+int oracle_propagate(const Params* p, int dtype, const double* x, const double* u, double* out) {
+    return ORACLE_DISPATCH(dtype, do_propagate, p, x, u, out);
+}
+
+int oracle_dyn_derivs(const Params* p, int dtype, int N, const double* u, const double* x, double* A,
+                      double* B) {
+    return ORACLE_DISPATCH(dtype, do_dyn_derivs, p, N, u, x, A, B);
+}
+
+int oracle_ref_match(int dtype, int M, const double* wx, const double* wy, int rows, const double* x,
+                     int32_t* idx_out) {
+    return ORACLE_DISPATCH(dtype, do_ref_match, M, wx, wy, rows, x, idx_out);
+}
+
+int oracle_total_cost(const Params* p, int dtype, int N, int M, const double* wx, const double* wy,
+                      const double* wyaw, double ref_velo, int n_obs, int obs_len, const double* obs,
+                      const double* borders, const double* u, const double* x, const double* alm_mu,
+                      double alm_rho, double* J, double* step_cost) {
+    return ORACLE_DISPATCH(dtype, do_total_cost, p, N, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs, borders, u, x,
+                           alm_mu, alm_rho, J, step_cost);
+}
+
+int oracle_cost_derivs(const Params* p, int dtype, int N, int M, const double* wx, const double* wy,
+                       const double* wyaw, double ref_velo, int n_obs, int obs_len, const double* obs,
+                       const double* borders, const double* u, const double* x, const double* alm_mu,
+                       double alm_rho, double* lx, double* lu, double* lxx, double* luu,
+                       double* alm_mu_next) {
+    return ORACLE_DISPATCH(dtype, do_cost_derivs, p, N, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs, borders, u, x,
+                           alm_mu, alm_rho, lx, lu, lxx, luu, alm_mu_next);
+}
+
+int oracle_riccati(int dtype, int N, const double* lx, const double* lu, const double* lxx,
+                   const double* luu, const double* A, const double* B, double lamb, double* d,
+                   double* K, double* dV, int32_t* status) {
+    return ORACLE_DISPATCH(dtype, do_riccati, N, lx, lu, lxx, luu, A, B, lamb, d, K, dV, status);
+}
+
+int oracle_forward(const Params* p, int dtype, int N, const double* u, const double* x,
+                   const double* d, const double* K, double alpha, double* new_u, double* new_x) {
+    return ORACLE_DISPATCH(dtype, do_forward, p, N, u, x, d, K, alpha, new_u, new_x);
+}
+
+// Stateful solver (warm start, cached derivatives, ALM multipliers persist
+// between solve() calls exactly as in the reference object).
+void* oracle_solver_create(const Params* p, int dtype, int N) {
+    AnySolver* a = ORACLE_DISPATCH(dtype, make_solver, p, N);
+    a->dtype = dtype;
+    a->N = N;
+    return a;
+}
+
+void oracle_solver_destroy(void* h) { delete static_cast<AnySolver*>(h); }
+
+// info = {status, iters, exit_reason, n_trace}.  trace (optional) receives up to
+// trace_cap rows of {status, alpha_index, effective, ori_cost, new_cost, lamb_after}.
+int oracle_solver_solve(void* h, int M, const double* wx, const double* wy, const double* wyaw,
+                        double ref_velo, int n_obs, int obs_len, const double* obs,
+                        const double* borders, const double* x0, double* u_out, double* x_out,
+                        double* K_out, double* d_out, double* J_out, double* step_cost_out,
+                        int32_t* info, double* lamb_out, double* trace, int trace_cap) {
+    auto* a = static_cast<AnySolver*>(h);
+    if (obs_len < a->N + 1 && n_obs > 0) return -2;  // RoutingLine::operator[] would throw (utils.cpp:52-58)
+    return ORACLE_DISPATCH(a->dtype, do_solver_solve, a, M, wx, wy, wyaw, ref_velo, n_obs, obs_len, obs, borders, x0,
+                           u_out, x_out, K_out, d_out, J_out, step_cost_out, info, lamb_out, trace, trace_cap);
 }
 
 // Batch of independent first solves, one fresh solver per instance, instances
@@ -360,19 +372,11 @@ int oracle_solve_batch(int dtype, int N, int n_tmpl, const Params* params, const
             double* xo = x_out ? x_out + size_t(b) * (N + 1) * 4 : nullptr;
             double* Ko = K_out ? K_out + size_t(b) * N * 8 : nullptr;
             double* dout = d_out ? d_out + size_t(b) * N * 2 : nullptr;
-            if (dtype == 0) {
-                Solver<double> s(params[t], N);
-                solve_one(s, M, wx + off, wy + off, wyaw + off, ref_velo[b], n_obs[b], obs_len, ob,
-                          borders + size_t(b) * 2, x0 + size_t(b) * 4, uo, xo, Ko, dout, J2, nullptr,
-                          info, nullptr, trace_cap > 0);
-                copy_trace(s.trace, b);
-            } else {
-                Solver<float> s(params[t], N);
-                solve_one(s, M, wx + off, wy + off, wyaw + off, ref_velo[b], n_obs[b], obs_len, ob,
-                          borders + size_t(b) * 2, x0 + size_t(b) * 4, uo, xo, Ko, dout, J2, nullptr,
-                          info, nullptr, trace_cap > 0);
-                copy_trace(s.trace, b);
-            }
+            std::vector<IterTrace> tr;
+            ORACLE_DISPATCH(dtype, do_batch_one, params[t], N, M, wx + off, wy + off, wyaw + off, ref_velo[b], n_obs[b],
+                            obs_len, ob, borders + size_t(b) * 2, x0 + size_t(b) * 4, uo, xo, Ko, dout, J2, info,
+                            trace_cap, &tr);
+            copy_trace(tr, b);
             if (J_out) {
                 J_out[size_t(b) * 2 + 0] = J2[0];
                 J_out[size_t(b) * 2 + 1] = J2[1];
@@ -388,5 +392,24 @@ int oracle_solve_batch(int dtype, int N, int n_tmpl, const Params* params, const
     for (auto& th : pool) th.join();
     return bad ? -1 : 0;
 }
+
+#ifdef CILQR_ORACLE_PMATH
+// Test hook (tests/test_pmath_cpu.py): the portable transcendentals evaluated over an array.
+// fn: 0 sin, 1 cos, 2 tan, 3 atan, 4 exp, 5 hypot(a, b).
+int oracle_pmath_eval(int fn, int n, const double* a, const double* b, double* out) {
+    for (int i = 0; i < n; ++i) {
+        switch (fn) {
+            case 0: out[i] = cilqr_pm::pm_sin(a[i]); break;
+            case 1: out[i] = cilqr_pm::pm_cos(a[i]); break;
+            case 2: out[i] = cilqr_pm::pm_tan(a[i]); break;
+            case 3: out[i] = cilqr_pm::pm_atan(a[i]); break;
+            case 4: out[i] = cilqr_pm::pm_exp(a[i]); break;
+            case 5: out[i] = cilqr_pm::pm_hypot(a[i], b[i]); break;
+            default: return -1;
+        }
+    }
+    return 0;
+}
+#endif
 
 }  // extern "C"

@@ -12,6 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
+LIB_PM_PATH = os.path.join(_HERE, "liboracle_pm.so")
 
 PARAM_FIELDS = [
     ("dt", "d"),
@@ -38,18 +39,29 @@ class Params(C.Structure):
         return p
 
 
-_lib = None
+_libs = {}
+
+# dtype strings of this module -> (library flavour, dtype code of the C surface)
+#   f64 / f32    the restatement with glibc's transcendentals (pinned to the reference sources, oracle/_ref)
+#   f80          the same in x87 long double (64-bit mantissa): the "truth" fp64 implementations are measured against
+#   f64pm/f32pm  transcendentals from the portable header shared with the CUDA PARITY build (bit-identical on GPU)
+_DT = {"f64": ("glibc", 0), "f32": ("glibc", 1), "f80": ("glibc", 2), "f64pm": ("pm", 0), "f32pm": ("pm", 1)}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            subprocess.run(["make", "-s", "-C", _HERE, "liboracle.so"], check=True)
-        _lib = C.CDLL(LIB_PATH)
-        assert _lib.oracle_sizeof_params() == C.sizeof(Params)
-        _lib.oracle_solver_create.restype = C.c_void_p
-    return _lib
+def lib(dtype="f64"):
+    flavour = _DT[dtype][0]
+    if flavour not in _libs:
+        path = LIB_PATH if flavour == "glibc" else LIB_PM_PATH
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", _HERE, os.path.basename(path)], check=True)
+        l = C.CDLL(path)
+        assert l.oracle_sizeof_params() == C.sizeof(Params)
+        l.oracle_solver_create.restype = C.c_void_p
+        _libs[flavour] = l
+    return _libs[flavour]
+
+
+DT = {k: v[1] for k, v in _DT.items()}
 
 
 def _dp(a):
@@ -64,13 +76,12 @@ def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-DT = {"f64": 0, "f32": 1}
 
 
 def propagate(params, x, u, dtype="f64"):
     p = Params.from_dict(params)
     x, u, out = _f64(x), _f64(u), np.empty(4)
-    lib().oracle_propagate(C.byref(p), DT[dtype], _dp(x), _dp(u), _dp(out))
+    lib(dtype).oracle_propagate(C.byref(p), DT[dtype], _dp(x), _dp(u), _dp(out))
     return out
 
 
@@ -78,14 +89,14 @@ def dyn_derivs(params, N, u, x, dtype="f64"):
     p = Params.from_dict(params)
     u, x = _f64(u), _f64(x)
     A, B = np.empty((N, 4, 4)), np.empty((N, 4, 2))
-    lib().oracle_dyn_derivs(C.byref(p), DT[dtype], N, _dp(u), _dp(x), _dp(A), _dp(B))
+    lib(dtype).oracle_dyn_derivs(C.byref(p), DT[dtype], N, _dp(u), _dp(x), _dp(A), _dp(B))
     return A, B
 
 
 def ref_match(wx, wy, x, dtype="f64"):
     wx, wy, x = _f64(wx), _f64(wy), _f64(x)
     idx = np.empty(x.shape[0], np.int32)
-    lib().oracle_ref_match(DT[dtype], len(wx), _dp(wx), _dp(wy), x.shape[0], _dp(x), _ip(idx))
+    lib(dtype).oracle_ref_match(DT[dtype], len(wx), _dp(wx), _dp(wy), x.shape[0], _dp(x), _ip(idx))
     return idx
 
 
@@ -105,7 +116,7 @@ def total_cost(td, N, ref_velo, n_obs, obs, borders, u, x, dtype="f64", alm_mu=N
     u, x, mu = _f64(u), _f64(x), _f64(alm_mu)
     J = C.c_double()
     sc = np.empty(N + 1)
-    lib().oracle_total_cost(C.byref(p), DT[dtype], N, *args, _dp(u), _dp(x), _dp(mu), C.c_double(alm_rho),
+    lib(dtype).oracle_total_cost(C.byref(p), DT[dtype], N, *args, _dp(u), _dp(x), _dp(mu), C.c_double(alm_rho),
                             C.byref(J), _dp(sc))
     return J.value, sc
 
@@ -116,7 +127,7 @@ def cost_derivs(td, N, ref_velo, n_obs, obs, borders, u, x, dtype="f64", alm_mu=
     u, x, mu = _f64(u), _f64(x), _f64(alm_mu)
     lx, lu, lxx, luu = np.empty((N + 1, 4)), np.empty((N, 2)), np.empty((N + 1, 4, 4)), np.empty((N, 2, 2))
     mun = np.empty((N, 8 + 2 * n_obs)) if alm_mu is not None else None
-    lib().oracle_cost_derivs(C.byref(p), DT[dtype], N, *args, _dp(u), _dp(x), _dp(mu), C.c_double(alm_rho),
+    lib(dtype).oracle_cost_derivs(C.byref(p), DT[dtype], N, *args, _dp(u), _dp(x), _dp(mu), C.c_double(alm_rho),
                              _dp(lx), _dp(lu), _dp(lxx), _dp(luu), _dp(mun))
     return dict(lx=lx, lu=lu, lxx=lxx, luu=luu, mu_next=mun)
 
@@ -125,7 +136,7 @@ def riccati(N, lx, lu, lxx, luu, A, B, lamb, dtype="f64"):
     a = [_f64(v) for v in (lx, lu, lxx, luu, A, B)]
     d, K, dV = np.empty((N, 2)), np.empty((N, 2, 4)), np.empty(2)
     st = C.c_int32()
-    lib().oracle_riccati(DT[dtype], N, *[_dp(v) for v in a], C.c_double(lamb), _dp(d), _dp(K), _dp(dV), C.byref(st))
+    lib(dtype).oracle_riccati(DT[dtype], N, *[_dp(v) for v in a], C.c_double(lamb), _dp(d), _dp(K), _dp(dV), C.byref(st))
     return d, K, dV, st.value
 
 
@@ -133,7 +144,7 @@ def forward(params, N, u, x, d, K, alpha, dtype="f64"):
     p = Params.from_dict(params)
     a = [_f64(v) for v in (u, x, d, K)]
     nu, nx = np.empty((N, 2)), np.empty((N + 1, 4))
-    lib().oracle_forward(C.byref(p), DT[dtype], N, *[_dp(v) for v in a], C.c_double(alpha), _dp(nu), _dp(nx))
+    lib(dtype).oracle_forward(C.byref(p), DT[dtype], N, *[_dp(v) for v in a], C.c_double(alpha), _dp(nu), _dp(nx))
     return nu, nx
 
 
@@ -158,11 +169,12 @@ class Solver:
     def __init__(self, params, N, dtype="f64"):
         self.N = N
         self.p = Params.from_dict(params)
-        self.h = C.c_void_p(lib().oracle_solver_create(C.byref(self.p), DT[dtype], N))
+        self.lib = lib(dtype)
+        self.h = C.c_void_p(self.lib.oracle_solver_create(C.byref(self.p), DT[dtype], N))
 
     def close(self):
         if self.h:
-            lib().oracle_solver_destroy(self.h)
+            self.lib.oracle_solver_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -176,7 +188,7 @@ class Solver:
         J, sc, info = np.empty(2), np.empty(N + 1), np.zeros(4, np.int32)
         lamb = C.c_double()
         tr = np.zeros((trace_cap, 6))
-        rc = lib().oracle_solver_solve(self.h, *args, _dp(x0), _dp(u), _dp(x), _dp(K), _dp(d), _dp(J), _dp(sc),
+        rc = self.lib.oracle_solver_solve(self.h, *args, _dp(x0), _dp(u), _dp(x), _dp(K), _dp(d), _dp(J), _dp(sc),
                                        _ip(info), C.byref(lamb), _dp(tr), trace_cap)
         if rc == -2:
             raise IndexError("Index out of range")
@@ -226,10 +238,21 @@ def solve_batch(pb, dtype="f64", nthreads=None, want_traj=True, trace_cap=0):
     if trace_cap > 0:
         trs, tra = np.zeros((B, trace_cap), np.int32), np.zeros((B, trace_cap), np.int32)
         trc = np.zeros((B, trace_cap))
-    rc = lib().oracle_solve_batch(DT[dtype], N, nt, parr, _ip(off), _dp(wx), _dp(wy), _dp(wyaw), B, _ip(tm),
+    rc = lib(dtype).oracle_solve_batch(DT[dtype], N, nt, parr, _ip(off), _dp(wx), _dp(wy), _dp(wyaw), B, _ip(tm),
                                   _dp(x0), _dp(rv), _dp(bd), _ip(no), int(pb.max_obs), int(pb.obs_len), _dp(ob),
                                   _dp(u), _dp(x), _dp(K), _dp(d), _dp(J), _ip(st), _ip(it), _ip(ex),
                                   int(trace_cap), _ip(trs), _ip(tra), _dp(trc), int(nthreads))
     if rc != 0:
         raise RuntimeError("oracle_solve_batch failed: %d" % rc)
     return BatchResult(u, x, K, d, J, st, it, ex, trs, tra, trc)
+
+
+def pmath_eval(fn, a, b=None):
+    """The portable transcendentals (csrc/cilqr_pmath.h, as compiled into liboracle_pm.so) over an array."""
+    code = {"sin": 0, "cos": 1, "tan": 2, "atan": 3, "exp": 4, "hypot": 5}[fn]
+    a = _f64(a)
+    b = _f64(b) if b is not None else a
+    out = np.empty_like(a)
+    rc = lib("f64pm").oracle_pmath_eval(code, a.size, _dp(a), _dp(b), _dp(out))
+    assert rc == 0
+    return out

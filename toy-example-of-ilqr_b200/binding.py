@@ -61,12 +61,24 @@ class CilqrError(RuntimeError):
         self.code = code
 
 
+LIB_PARITY_PATH = os.path.join(_HERE, "libcilqr_b200_parity.so")
 _lib = None
+_lib_parity = None
 
 
-def load_library():
-    """Loads libcilqr_b200.so; raises (never falls back) when it has not been built."""
-    global _lib
+def load_library(flavour="fast"):
+    """Loads libcilqr_b200.so; raises (never falls back) when it has not been built.
+    flavour "parity": libcilqr_b200_parity.so, the same kernels compiled with -DCILQR_PARITY -fmad=false
+    (reference operation order, portable transcendentals) for bit-for-bit comparisons with the CPU."""
+    global _lib, _lib_parity
+    if flavour == "parity":
+        if _lib_parity is None:
+            if not os.path.exists(LIB_PARITY_PATH):
+                raise ImportError("%s is missing: run `python __graft_entry__.py` first" % LIB_PARITY_PATH)
+            _lib_parity = C.CDLL(LIB_PARITY_PATH)
+            _lib_parity.cilqr_b200_last_error.restype = C.c_char_p
+            _lib_parity.cilqr_b200_version.restype = C.c_char_p
+        return _lib_parity
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ImportError("%s is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first; "
@@ -107,8 +119,8 @@ class SolveResult:
 
 
 class BatchSolver:
-    def __init__(self, templates, max_batch, N, max_obs, dtype="f64", device=0):
-        self.lib = load_library()
+    def __init__(self, templates, max_batch, N, max_obs, dtype="f64", device=0, flavour="fast"):
+        self.lib = load_library(flavour)
         self.N, self.max_batch, self.max_obs = int(N), int(max_batch), int(max_obs)
         self.dtype = {"f64": 0, "f32": 1}[dtype]
         self.h = C.c_void_p()

@@ -120,8 +120,13 @@ DevParams<T> convert_params(const cilqr_params_t& p) {
     T radius = T(0.5) * T(p.width);
     T a = T(0.5) * T(p.length) + T(p.d_safe) * 6 + radius;
     T b = T(0.5) * T(p.width) + T(p.d_safe) + radius;
+#ifdef CILQR_PARITY
+    d.ell_a2 = a * a;  // parity build: the squares themselves, divided by as in the reference (ellipse_margin)
+    d.ell_b2 = b * b;
+#else
     d.ell_a2 = T(1) / (a * a);
     d.ell_b2 = T(1) / (b * b);
+#endif
     d.alm_rho_init = T(p.alm_rho_init);
     d.alm_gamma = T(p.alm_gamma);
     d.max_rho = T(p.max_rho);
@@ -279,11 +284,11 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.X, size_t(N + 1) * 4 * Bs))) return r;
         if ((r = dalloc(h, &D.U, size_t(N) * 2 * Bs))) return r;
         if ((r = dalloc(h, &D.ridx, size_t(N + 1) * Bs))) return r;
-        if ((r = dalloc(h, &D.sc, size_t(N + 1) * Bs))) return r;
+        if ((r = dalloc(h, &D.sc, size_t(N + 1) * kScPlanes * Bs))) return r;
         if ((r = dalloc(h, &D.Xt, size_t(N + 1) * 4 * Vs))) return r;
         if ((r = dalloc(h, &D.Ut, size_t(N) * 2 * Vs))) return r;
         if ((r = dalloc(h, &D.ridx_t, size_t(N + 1) * Vs))) return r;
-        if ((r = dalloc(h, &D.sc_t, size_t(N + 1) * Vs))) return r;
+        if ((r = dalloc(h, &D.sc_t, size_t(N + 1) * kScPlanes * Vs))) return r;
         if ((r = dalloc(h, &D.t_inst, Vs))) return r;
         if ((r = dalloc(h, &D.t_aidx, Vs))) return r;
         if ((r = dalloc(h, &D.t_done, Vs))) return r;
@@ -609,7 +614,7 @@ void swap_instances(Impl<T>* h, int level, int offset, int m_bound) {
     rows_t(D.X, (N + 1) * 4);
     rows_t(D.U, N * 2);
     rows_i(D.ridx, N + 1);
-    rows_t(D.sc, N + 1);
+    rows_t(D.sc, (N + 1) * kScPlanes);
     LAUNCH(h, k_swap_records<T>, dim3(gx, std::min((N + 1) * kRecFields, 1024)), 128, D, src, dst, m);
     rows_t(D.Kg, N * 8);
     rows_t(D.dg, N * 2);
@@ -713,7 +718,9 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
                 LAUNCH(h, (k_backward<T, false>), gs1(n_bound), 128, h->D, B, 1, par);
         }
         mark_stage(h, 2);
-        const bool piped = lat && h->pipeline && N + 1 <= kPipeMaxSteps;
+        // (the parity build keeps to the one-thread rollout: the two-lane kernels split the step's trigonometry
+        // in a way that is a few ulp from the reference's sequence)
+        const bool piped = !kParity && lat && h->pipeline && N + 1 <= kPipeMaxSteps;
         if (piped) {
             const int blocks = std::max(1, std::min((trial_bound + kPipeTrials - 1) / kPipeTrials, kGridCap));
             // 16 scan lanes per trial when the whole trial pool fits one wave at two blocks per SM
@@ -723,12 +730,12 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             } else {
                 LAUNCH(h, (k_rollout_match<T, 16>), dim3(blocks), pipe_threads(16), h->D, B);
             }
-        } else if (lat) {
+        } else if (lat && !kParity) {
             LAUNCH(h, k_forward2<T>, gs1(2 * trial_bound), 128, h->D, B);  // two lanes per trial slot
         } else {
             LAUNCH(h, (k_forward<T, true>), gs1(trial_bound), 128, h->D, B, 1);  // rollout + waypoint match
         }
-        launch_cost(h, B, 1, trial_bound, lat, piped || !lat);
+        launch_cost(h, B, 1, trial_bound, lat, piped || !lat || kParity);
         mark_stage(h, 5);
         h->scan_epoch = (h->scan_epoch % 0x3fffffffu) + 1u;
         // one CTA per chunk of the work list, never fewer (no striding): a CTA that went on to a second
@@ -1266,7 +1273,11 @@ int do_destroy(Impl<T>* h) {
 extern "C" {
 
 const char* cilqr_b200_last_error(void) { return g_err.c_str(); }
-const char* cilqr_b200_version(void) { return "cilqr_b200 0.1 (sm_100a)"; }
+#ifdef CILQR_PARITY
+const char* cilqr_b200_version(void) { return "cilqr_b200 0.2 (sm_100a, parity build: reference operation order, portable transcendentals, no FMA contraction)"; }
+#else
+const char* cilqr_b200_version(void) { return "cilqr_b200 0.2 (sm_100a)"; }
+#endif
 
 int cilqr_b200_create(const cilqr_params_t* params, int device, int max_batch, int N, int max_obs, int dtype,
                       cilqr_handle_t** out) {

@@ -39,6 +39,7 @@
 
 namespace cilqr {
 
+#ifndef CILQR_PARITY
 constexpr int kRecFields = 28;  // compact derivative record per step
 constexpr int kRecLx = 0;       // l_x   [4]
 constexpr int kRecLxx = 4;      // l_xx  sym: 00 01 02 03 11 12 13 22 23 33
@@ -46,6 +47,22 @@ constexpr int kRecLu = 14;      // l_u   [2]
 constexpr int kRecLuu = 16;     // l_uu  sym: 00 01 11
 constexpr int kRecA = 19;       // A     a02 a03 a12 a13 a32
 constexpr int kRecB = 24;       // B     b01 b11 b20 b31
+constexpr int kVN = 10;         // value-function Hessian carried by the recursion: symmetric, upper triangle
+constexpr int kScPlanes = 1;    // per-step cost rows
+#else
+// Parity build: l_xx and V_xx are kept as the full 4x4 the reference carries (its products do not
+// return bitwise-symmetric matrices, and in ALM mode l_xx itself is not bitwise symmetric), and the
+// step costs are kept split into the three sums the reference forms (get_total_cost, cpp:211-213, :286).
+constexpr int kRecFields = 34;
+constexpr int kRecLx = 0;    // l_x   [4]
+constexpr int kRecLxx = 4;   // l_xx  [4][4] row-major
+constexpr int kRecLu = 20;   // l_u   [2]
+constexpr int kRecLuu = 22;  // l_uu  00 01 11 (both off-diagonals are exactly zero in the reference)
+constexpr int kRecA = 25;    // A     a02 a03 a12 a13 a32 (the other entries are exactly 0 / 1)
+constexpr int kRecB = 30;    // B     b01 b11 b20 b31
+constexpr int kVN = 16;
+constexpr int kScPlanes = 4;  // plane 0: step total; 1: state term; 2: control term; 3: constraint terms
+#endif
 
 // The records are stored tiled, [step][tile of 32 instances][field][32]: the 28 fields of an
 // instance's step sit a constant 32 scalars apart (immediate offsets, no per-field address
@@ -190,6 +207,29 @@ __device__ __forceinline__ size_t at(size_t stride, int step, int field, int nfi
     return (size_t(step) * nfields + field) * stride + i;
 }
 
+// Total cost of trajectory i from its per-step costs sc [kScPlanes][N+1][stride].  Default build: the step
+// totals in step order.  Parity build: the reference's three sums (states, controls, constraints: cpp:211-213,
+// :217-286) each in step order, then (states + controls) + constraints.  kCg: read through L2 (the values
+// were just written by other threads of the same kernel).
+template <typename T, bool kCg>
+__device__ __forceinline__ T sum_step_costs(const T* sc, size_t stride, int N, int i) {
+    auto ld = [&](size_t idx) { return kCg ? __ldcg(sc + idx) : sc[idx]; };
+#ifndef CILQR_PARITY
+    T J = 0;
+    for (int k = 0; k <= N; ++k) J += ld(size_t(k) * stride + i);
+    return J;
+#else
+    T part[3];
+    for (int p = 0; p < 3; ++p) {
+        T a = 0;
+        const int k0 = p == 2 ? 1 : 0, k1 = p == 1 ? N - 1 : N;
+        for (int k = k0; k <= k1; ++k) a += ld((size_t(p + 1) * (N + 1) + k) * stride + i);
+        part[p] = a;
+    }
+    return (part[0] + part[1]) + part[2];
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // K0  initial trajectory: get_init_traj (cpp:155-161, :182-197) or the shifted
 //     warm start get_init_traj_increment (cpp:163-180); also resets the
@@ -272,8 +312,12 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
 // (windowed or one by one) must compare the same bits
 template <typename T>
 __device__ __forceinline__ T wp_dist2(T px, T py, T wx, T wy) {
+#ifdef CILQR_PARITY
+    return m_hypot(px - wx, py - wy);  // the reference compares hypot() values (cpp:300-309)
+#else
     const T ex = px - wx, ey = py - wy;
     return m_fma(ex, ex, ey * ey);
+#endif
 }
 // the same scan, one waypoint at a time (inside the throughput-regime rollout, one thread per trial)
 template <typename T>
@@ -369,7 +413,7 @@ __device__ __forceinline__ void ctrl_constraints(const DevParams<T>& P, T acc, T
 // kAlm: the batch may hold augmented-Lagrangian instances; false compiles the ALM paths out, which
 // leaves the barrier terms free of branches (independent exponentials interleave).
 template <typename T, bool kAlm, int kOb>
-__device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int b, int v, int k, int ri) {
+__device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int b, int v, int k, int ri, T* parts = nullptr) {
     const int N = D.N;
     const size_t Bs = D.Bs;
     const DevParams<T>& P = D.P[D.tmpl[b]];
@@ -384,11 +428,13 @@ __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int
         T e = x[c] - ref[c];
         cost += e * P.Q[c] * e;
     }
+    if (parts) parts[0] = cost, parts[1] = 0, parts[2] = 0;
     if (k < N) {
         T a = V.U[at(V.stride, k, 0, 2, v)], s = V.U[at(V.stride, k, 1, 2, v)];
         T ce = a * P.R[0] * a;
         ce += s * P.R[1] * s;
         cost += ce;
+        if (parts) parts[1] = ce;
     }
     if (k >= 1) {
         T a = V.U[at(V.stride, k - 1, 0, 2, v)], s = V.U[at(V.stride, k - 1, 1, 2, v)];
@@ -445,6 +491,7 @@ __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int
             }
         }
         cost += Jk;
+        if (parts) parts[2] = Jk;
     }
     return cost;
 }
@@ -463,7 +510,13 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int t
     const int k = blockIdx.x;
     for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < count; v += gridDim.y * blockDim.x) {
         const int b = V.inst ? V.inst[v] : v;
+#ifdef CILQR_PARITY
+        T parts[3];
+        const T cost = step_cost_of<T, kAlm, (kMinBlocks <= 4 ? 4 : 2)>(D, V, b, v, k, V.ridx[size_t(k) * V.stride + v], parts);
+        for (int p = 0; p < 3; ++p) V.sc[(size_t(p + 1) * (N + 1) + k) * V.stride + v] = parts[p];
+#else
         const T cost = step_cost_of<T, kAlm, (kMinBlocks <= 4 ? 4 : 2)>(D, V, b, v, k, V.ridx[size_t(k) * V.stride + v]);
+#endif
         V.sc[size_t(k) * V.stride + v] = cost;
         if (trial == 1) {
             // the thread that stores the last step cost of a trial sums them in step order (fixed
@@ -471,9 +524,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int t
             __threadfence();
             if (atomicAdd(&D.t_done[v], 1) == N) {
                 __threadfence();
-                T J = 0;
-                for (int kk = 0; kk <= N; ++kk) J += __ldcg(&V.sc[size_t(kk) * V.stride + v]);
-                D.J_t[v] = J;
+                D.J_t[v] = sum_step_costs<T, true>(V.sc, V.stride, N, v);
                 D.t_done[v] = 0;
             }
         }
@@ -486,9 +537,7 @@ __global__ void __launch_bounds__(128) k_sum_trials(Dev<T> D, int B) {
     const int count = view_count(D, 1, B);
     const size_t Vs = D.Vs;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += gridDim.x * blockDim.x) {
-        T J = 0;
-        for (int k = 0; k <= D.N; ++k) J += D.sc_t[size_t(k) * Vs + v];
-        D.J_t[v] = J;
+        D.J_t[v] = sum_step_costs<T, false>(D.sc_t, Vs, D.N, v);
     }
 }
 
@@ -499,8 +548,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) k_sum_cost(Dev<T> D, int B, int mode) {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         if (mode == 1 && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) continue;
-        T J = 0;
-        for (int k = 0; k <= D.N; ++k) J += D.sc[size_t(k) * D.Bs + b];
+        const T J = sum_step_costs<T, false>(D.sc, D.Bs, D.N, b);
         D.J_cur[b] = J;
         if (mode == 0) D.J_init[b] = J;
     }
@@ -522,6 +570,35 @@ __device__ __forceinline__ void constraint_weights(bool alm, T c, T q1, T q2, T 
         *h = w;
     }
 }
+
+#ifdef CILQR_PARITY
+// Parity build: one constraint's contribution formed exactly as the reference forms it — barrier
+// cpp:692-699 (grad += q2 b c_dot, hess += q2^2 b c_dot c_dot^T), ALM cpp:701-713 (b_dot = rho (c + mu/rho) c_dot,
+// hess += b_dot c_dot^T) — over all n entries of c_dot, zeros included.
+template <typename T, int n>
+__device__ __forceinline__ void add_constraint_ref(bool alm, T c, const T* c_dot, T q1, T q2, T rho, T mu, T* grad, T* hess) {
+    if (!alm) {
+        const T b = exp_barrier(c, q1, q2);
+        const T q2sq = q2 * q2;
+#pragma unroll
+        for (int r = 0; r < n; ++r) grad[r] += q2 * b * c_dot[r];
+#pragma unroll
+        for (int r = 0; r < n; ++r)
+#pragma unroll
+            for (int cc = 0; cc < n; ++cc) hess[r * n + cc] += q2sq * b * (c_dot[r] * c_dot[cc]);
+    } else if ((c + mu / rho) > 0) {
+        T bd[n];
+#pragma unroll
+        for (int r = 0; r < n; ++r) bd[r] = rho * (c + mu / rho) * c_dot[r];
+#pragma unroll
+        for (int r = 0; r < n; ++r) grad[r] += bd[r];
+#pragma unroll
+        for (int r = 0; r < n; ++r)
+#pragma unroll
+            for (int cc = 0; cc < n; ++cc) hess[r * n + cc] += bd[r] * c_dot[cc];
+    }
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // K3 + K4  get_total_cost_derivatives_and_Hessians (cpp:463-690) and
@@ -571,7 +648,8 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
                 for (int c = 0; c < 4; ++c) D.X[at(Bs, k, c, 4, b)] = x[c];
                 ri = D.ridx_t[size_t(k) * Vs + src];
                 D.ridx[size_t(k) * Bs + b] = ri;
-                D.sc[size_t(k) * Bs + b] = D.sc_t[size_t(k) * Vs + src];
+                for (int p = 0; p < kScPlanes; ++p)
+                    D.sc[(size_t(p) * (N + 1) + k) * Bs + b] = D.sc_t[(size_t(p) * (N + 1) + k) * Vs + src];
             } else if (k < N) {
                 ua = D.Ut[at(Vs, k, 0, 2, src)];
                 us = D.Ut[at(Vs, k, 1, 2, src)];
@@ -597,7 +675,64 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
         if (part == 0) {
         const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
         const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
-
+#ifdef CILQR_PARITY
+        // the reference's accumulation, literally (cpp:497-689): velocity up / lo, border up / lo into the
+        // row, then per obstacle (front + rear) summed first and added to the row, the prime part last
+        T gx[4] = {0, 0, 0, 0};
+        T Hx[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (k >= 1) {
+            const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+            T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+            T d_sign, hyp;
+            const T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
+            const T cc4[4] = {x[2] - P.velo_max, P.velo_min - x[2], cur_d - (D.borders[b] - P.width / 2),
+                              (D.borders[Bs + b] + P.width / 2) - cur_d};
+            T cx[4][4] = {{0, 0, 1, 0}, {0, 0, -1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+            cx[2][0] = (x[0] - rx) / hyp;
+            cx[2][1] = (x[1] - ry) / hyp;
+            if (d_sign < 0)
+                for (int r = 0; r < 4; ++r) cx[2][r] = -1 * cx[2][r];
+            for (int r = 0; r < 4; ++r) cx[3][r] = -1 * cx[2][r];
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                add_constraint_ref<T, 4>(alm, cc4[m], cx[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4 + m) * Bs] : T(0), gx, Hx);
+            if (alm)
+                for (int m = 0; m < 4; ++m)
+                    mun[size_t(4 + m) * Bs] = std_min(std_max(mu[size_t(4 + m) * Bs] + rho * cc4[m], T(0)), P.max_mu);
+            const int no = D.n_obs[b];
+            if (no > 0) {
+                const EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
+                for (int j = 0; j < no; ++j) {
+                    const T* ob = D.obs + (size_t(j) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
+                    const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
+                    T gfx, gfy, grx, gry;
+                    const T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
+                    const T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
+                    // 4x2 centre Jacobians times the point gradients (utils.cpp:363-385, cpp:728-736)
+                    const T gf[4] = {T(1) * gfx + T(0) * gfy, T(0) * gfx + T(1) * gfy, T(0) * gfx + T(0) * gfy,
+                                     e.jf0 * gfx + e.jf1 * gfy};
+                    const T gr[4] = {T(1) * grx + T(0) * gry, T(0) * grx + T(1) * gry, T(0) * grx + T(0) * gry,
+                                     e.jr0 * grx + e.jr1 * gry};
+                    T g2[4] = {0, 0, 0, 0};
+                    T H2[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    add_constraint_ref<T, 4>(alm, cf, gf, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(8 + 2 * j) * Bs] : T(0), g2, H2);
+                    add_constraint_ref<T, 4>(alm, cr, gr, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(9 + 2 * j) * Bs] : T(0), g2, H2);
+                    for (int r = 0; r < 4; ++r) gx[r] += g2[r];
+                    for (int r = 0; r < 16; ++r) Hx[r] += H2[r];
+                    if (alm) {
+                        mun[size_t(8 + 2 * j) * Bs] = std_min(std_max(mu[size_t(8 + 2 * j) * Bs] + rho * cf, T(0)), P.max_mu);
+                        mun[size_t(9 + 2 * j) * Bs] = std_min(std_max(mu[size_t(9 + 2 * j) * Bs] + rho * cr, T(0)), P.max_mu);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Hx[c * 4 + c] = 2 * P.Q[c] + Hx[c * 4 + c];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) rec[(kRecLxx + c) * kRecFS] = Hx[c];
+#else
         T gx[4] = {0, 0, 0, 0};
         T H[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
         if (k >= 1) {
@@ -707,12 +842,30 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
         H[9] += 2 * P.Q[3];
 #pragma unroll
         for (int c = 0; c < 10; ++c) rec[(kRecLxx + c) * kRecFS] = H[c];
+#endif
         }  // part 0
 
         if (part == 1 && k < N) {
             T c[4];
             ctrl_constraints(P, ua, us, c);
             const T* mu = alm ? D.mu + size_t(k) * D.alm_cols * Bs + b : nullptr;
+#ifdef CILQR_PARITY
+            const T cu[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+            T gu[2] = {0, 0}, Hu[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                add_constraint_ref<T, 2>(alm, c[m], cu[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * Bs] : T(0), gu, Hu);
+            if (alm) {
+                T* mun = D.mu_next + size_t(k) * D.alm_cols * Bs + b;
+                for (int m = 0; m < 4; ++m)
+                    mun[size_t(m) * Bs] = std_min(std_max(mu[size_t(m) * Bs] + rho * c[m], T(0)), P.max_mu);
+            }
+            rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu[0];
+            rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu[1];
+            rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + Hu[0];
+            rec[(kRecLuu + 1) * kRecFS] = Hu[1];
+            rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + Hu[3];
+#else
             T g[4], h[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m)
@@ -732,6 +885,7 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
             rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + hu0;
             rec[(kRecLuu + 1) * kRecFS] = 0;
             rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + hu1;
+#endif
             T ja[5], jb[4];
             model_jacobians(x[2], x[3], us, P.dt, P.wheelbase, P.ref_point, ja, jb);
 #pragma unroll
@@ -788,6 +942,141 @@ __device__ __forceinline__ constexpr float kEps<float>() { return 1.1920929e-07f
 // step i+1, produces the gains K (2x4), d (2), and overwrites (Vx, V) with step i's.  Returns false —
 // leaving Vx, V, dV untouched — when Q_uu + lambda*I fails the LLT test.  Shared by every variant of
 // the backward kernel, so they all return the same bits.
+#ifdef CILQR_PARITY
+// Parity build: the same step as the reference writes it (cpp:398-437) — dense 4x4 / 4x2 products, inner sums
+// over k = 0..3 from zero, (A^T V) A and (B^T V) A / B associated from the left, the full (not symmetrised)
+// V_xx, Eigen::LLT's test sequence, the adjugate inverse, the three-term value update.
+template <typename T>
+__device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T& dV0, T& dV1, T* K, T& d0, T& d1) {
+    T A[16], B[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[i] = (i % 5 == 0) ? T(1) : T(0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) B[i] = 0;
+    A[0 * 4 + 2] = r[kRecA + 0];
+    A[0 * 4 + 3] = r[kRecA + 1];
+    A[1 * 4 + 2] = r[kRecA + 2];
+    A[1 * 4 + 3] = r[kRecA + 3];
+    A[3 * 4 + 2] = r[kRecA + 4];
+    B[0 * 2 + 1] = r[kRecB + 0];
+    B[1 * 2 + 1] = r[kRecB + 1];
+    B[2 * 2 + 0] = r[kRecB + 2];
+    B[3 * 2 + 1] = r[kRecB + 3];
+    const T luu[4] = {r[kRecLuu + 0], r[kRecLuu + 1], r[kRecLuu + 1], r[kRecLuu + 2]};
+    T Qx[4], Qu[2], Qxx[16], Quu[4], Qux[8], AtV[16], BtV[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        T s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s += A[k * 4 + i] * Vx[k];
+        Qx[i] = r[kRecLx + i] + s;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        T s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s += B[k * 2 + i] * Vx[k];
+        Qu[i] = r[kRecLu + i] + s;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            T s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += A[k * 4 + i] * V[k * 4 + c];
+            AtV[i * 4 + c] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            T s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += B[k * 2 + i] * V[k * 4 + c];
+            BtV[i * 4 + c] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            T s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += AtV[i * 4 + k] * A[k * 4 + c];
+            Qxx[i * 4 + c] = r[kRecLxx + i * 4 + c] + s;
+        }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            T s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += BtV[i * 4 + k] * B[k * 2 + c];
+            Quu[i * 2 + c] = (luu[i * 2 + c] + s) + lamb * (i == c ? T(1) : T(0));
+        }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            T s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += BtV[i * 4 + k] * A[k * 4 + c];
+            Qux[i * 4 + c] = T(0) + s;
+        }
+    {
+        const T a00 = Quu[0];
+        if (a00 <= T(0)) return false;
+        const T l00 = m_sqrt(a00);
+        const T l10 = Quu[2] / l00;
+        const T a11 = Quu[3] - l10 * l10;
+        if (a11 <= T(0)) return false;
+    }
+    const T det = Quu[0] * Quu[3] - Quu[2] * Quu[1];
+    const T invdet = T(1) / det;
+    const T inv[4] = {Quu[3] * invdet, -Quu[1] * invdet, -Quu[2] * invdet, Quu[0] * invdet};
+    T d[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = (-inv[i * 2 + 0]) * Qu[0] + (-inv[i * 2 + 1]) * Qu[1];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) K[i * 4 + c] = (-inv[i * 2 + 0]) * Qux[0 * 4 + c] + (-inv[i * 2 + 1]) * Qux[1 * 4 + c];
+    d0 = d[0];
+    d1 = d[1];
+    T KtQuu[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) KtQuu[i * 2 + c] = K[0 * 4 + i] * Quu[0 * 2 + c] + K[1 * 4 + i] * Quu[1 * 2 + c];
+    T nVx[4], nV[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T t1 = KtQuu[i * 2 + 0] * d[0] + KtQuu[i * 2 + 1] * d[1];
+        const T t2 = K[0 * 4 + i] * Qu[0] + K[1 * 4 + i] * Qu[1];
+        const T t3 = Qux[0 * 4 + i] * d[0] + Qux[1 * 4 + i] * d[1];
+        nVx[i] = ((Qx[i] + t1) + t2) + t3;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const T t1 = KtQuu[i * 2 + 0] * K[0 * 4 + c] + KtQuu[i * 2 + 1] * K[1 * 4 + c];
+            const T t2 = K[0 * 4 + i] * Qux[0 * 4 + c] + K[1 * 4 + i] * Qux[1 * 4 + c];
+            const T t3 = Qux[0 * 4 + i] * K[0 * 4 + c] + Qux[1 * 4 + i] * K[1 * 4 + c];
+            nV[i * 4 + c] = ((Qxx[i * 4 + c] + t1) + t2) + t3;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Vx[i] = nVx[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) V[i] = nV[i];
+    const T hd0 = T(0.5) * d[0], hd1 = T(0.5) * d[1];
+    const T r0 = hd0 * Quu[0] + hd1 * Quu[2];
+    const T r1 = hd0 * Quu[1] + hd1 * Quu[3];
+    dV0 += r0 * d[0] + r1 * d[1];
+    dV1 += d[0] * Qu[0] + d[1] * Qu[1];
+    return true;
+}
+#else
 template <typename T>
 __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T& dV0, T& dV1, T* K, T& d0, T& d1) {
     const T a02 = r[kRecA + 0], a03 = r[kRecA + 1], a12 = r[kRecA + 2], a13 = r[kRecA + 3], a32 = r[kRecA + 4];
@@ -905,6 +1194,8 @@ __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T&
     return true;
 }
 
+#endif
+
 // The Riccati recursion of one trajectory.  Streams the 28-scalar record of each
 // step (l_x 4, l_xx 10, l_u 2, l_uu 3, A 5, B 4) and writes K (8) and d (2):
 // (38 N + 18) * sizeof(T) algorithmic bytes per trajectory.  Q_uu + lambda*I is
@@ -916,11 +1207,11 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
     const int N = D.N;
     const size_t Bs = D.Bs;
     const T* rec = rec_at(D, N, b);
-    T Vx[4], V[10];
+    T Vx[4], V[kVN];
 #pragma unroll
     for (int c = 0; c < 4; ++c) Vx[c] = rec[(kRecLx + c) * kRecFS];
 #pragma unroll
-    for (int c = 0; c < 10; ++c) V[c] = rec[(kRecLxx + c) * kRecFS];
+    for (int c = 0; c < kVN; ++c) V[c] = rec[(kRecLxx + c) * kRecFS];
     T dV0 = 0, dV1 = 0;
     bool failed = false;
     int i = N - 1;
@@ -1149,13 +1440,13 @@ __global__ void __launch_bounds__(32) k_backward_staged(Dev<T> D, int B, int sol
             };
             for (int j = 0; j < kStagedStages && j < N; ++j) issue(N - 1 - j);
             const T lamb = run ? D.lamb[b] : T(0);
-            T Vx[4], V[10];
+            T Vx[4], V[kVN];
             {
                 const T* rec = rec_at(D, N, in ? b : 0);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) Vx[c] = rec[(kRecLx + c) * kRecFS];
 #pragma unroll
-                for (int c = 0; c < 10; ++c) V[c] = rec[(kRecLxx + c) * kRecFS];
+                for (int c = 0; c < kVN; ++c) V[c] = rec[(kRecLxx + c) * kRecFS];
             }
             T dV0 = 0, dV1 = 0;
             T* Kp = D.Kg + size_t(N) * 8 * Bs + (in ? b : 0);
@@ -1590,6 +1881,7 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
             const T J_cur = D.J_cur[b];
             const T dV0 = D.dV[b], dV1 = D.dV[Bs + b];
             bool ended = false;
+            T last_J = J_cur;  // cost of the last trial looked at: what iter_step returns when every alpha was rejected (cpp:380)
             my_trials += cnt;
             // trial costs four at a time (independent loads), then their verdicts in alpha order; the
             // usual case is a single trial
@@ -1603,6 +1895,7 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
                 if (i >= cnt || ended) break;
                 const int v = v0 + i, a = a0 + i;
                 const T new_J = Jt[q];
+                last_J = new_J;
                 const T alpha = T(1) / T(1 << a);
                 const T actual = J_cur - new_J;
                 if (a == 0 && m_fabs(actual) < P.conv_thr) {
@@ -1631,7 +1924,7 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
                         D.rec_valid[b] = 0;
                     }
                     D.wide[b] = 1;
-                    end_iteration(D, P, b, ST_FWD_FAIL, -1, J_cur);
+                    end_iteration(D, P, b, ST_FWD_FAIL, -1, last_J);
                 } else {
                     D.aidx[b] = a0 + cnt;
                     D.wide[b] = 1;  // alpha = 1 was rejected: evaluate the remaining alphas together
@@ -1795,9 +2088,13 @@ __global__ void k_records_from_dense(Dev<T> D, int B, const double* lx, const do
     const double* px = lx + (size_t(b) * (N + 1) + k) * 4;
     const double* pxx = lxx + (size_t(b) * (N + 1) + k) * 16;
     for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = T(px[c]);
+#ifdef CILQR_PARITY
+    for (int e = 0; e < 16; ++e) rec[(kRecLxx + e) * kRecFS] = T(pxx[e]);
+#else
     int e = 0;
     for (int r = 0; r < 4; ++r)
         for (int c = r; c < 4; ++c, ++e) rec[(kRecLxx + e) * kRecFS] = T(pxx[r * 4 + c]);
+#endif
     if (k < N) {
         const double* pu = lu + (size_t(b) * N + k) * 2;
         const double* puu = luu + (size_t(b) * N + k) * 4;
@@ -1832,6 +2129,9 @@ __global__ void k_records_to_dense(Dev<T> D, int B, double* lx, double* lu, doub
     double* px = lx + (size_t(b) * (N + 1) + k) * 4;
     double* pxx = lxx + (size_t(b) * (N + 1) + k) * 16;
     for (int c = 0; c < 4; ++c) px[c] = double(rec[(kRecLx + c) * kRecFS]);
+#ifdef CILQR_PARITY
+    for (int e = 0; e < 16; ++e) pxx[e] = double(rec[(kRecLxx + e) * kRecFS]);
+#else
     int e = 0;
     for (int r = 0; r < 4; ++r)
         for (int c = r; c < 4; ++c, ++e) {
@@ -1839,6 +2139,7 @@ __global__ void k_records_to_dense(Dev<T> D, int B, double* lx, double* lu, doub
             pxx[r * 4 + c] = v;
             pxx[c * 4 + r] = v;
         }
+#endif
     if (k < N) {
         double* pu = lu + (size_t(b) * N + k) * 2;
         double* puu = luu + (size_t(b) * N + k) * 4;

@@ -7,10 +7,37 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef CILQR_PARITY
+#include "cilqr_pmath.h"
+#endif
 
 namespace cilqr {
 
+// ---- build flavours -----------------------------------------------------------
+// default        the fast build: CUDA libdevice transcendentals, FMA contraction, the algebraic shortcuts
+//                listed in DESIGN.md section 3 (each a few ulp from the reference's operation sequence).
+// CILQR_PARITY   libcilqr_b200_parity.so (also needs nvcc -fmad=false): every stage evaluates the reference's
+//                own operation sequence (the order the tests' CPU restatement is written in, which is
+//                bit-identical to the reference sources) with the portable transcendentals of
+//                cilqr_pmath.h, so that a whole free-running solve can be compared with the CPU bit for
+//                bit.  Same kernels, same work lists / trial pool / verdict logic; only the arithmetic
+//                inside the device functions differs.  Not a performance build.
+#ifdef CILQR_PARITY
+constexpr bool kParity = true;
+#else
+constexpr bool kParity = false;
+#endif
+
 // ---- scalar math, overloaded on the compute type --------------------------
+#ifdef CILQR_PARITY
+template <typename T> __device__ __forceinline__ T m_sin(T v) { return cilqr_pm::pm_sin(v); }
+template <typename T> __device__ __forceinline__ T m_cos(T v) { return cilqr_pm::pm_cos(v); }
+template <typename T> __device__ __forceinline__ void m_sincos(T v, T* s, T* c) { *s = cilqr_pm::pm_sin(v); *c = cilqr_pm::pm_cos(v); }
+template <typename T> __device__ __forceinline__ T m_tan(T v) { return cilqr_pm::pm_tan(v); }
+template <typename T> __device__ __forceinline__ T m_atan(T v) { return cilqr_pm::pm_atan(v); }
+template <typename T> __device__ __forceinline__ T m_exp(T v) { return cilqr_pm::pm_exp(v); }
+template <typename T> __device__ __forceinline__ T m_hypot(T a, T b) { return cilqr_pm::pm_hypot(a, b); }
+#else
 __device__ __forceinline__ double m_sin(double v) { return sin(v); }
 __device__ __forceinline__ float m_sin(float v) { return sinf(v); }
 __device__ __forceinline__ double m_cos(double v) { return cos(v); }
@@ -58,6 +85,7 @@ __device__ __forceinline__ double m_exp(double x) {
 __device__ __forceinline__ float m_exp(float v) { return expf(v); }
 __device__ __forceinline__ double m_hypot(double a, double b) { return hypot(a, b); }
 __device__ __forceinline__ float m_hypot(float a, float b) { return hypotf(a, b); }
+#endif
 __device__ __forceinline__ double m_sqrt(double v) { return sqrt(v); }
 __device__ __forceinline__ float m_sqrt(float v) { return sqrtf(v); }
 __device__ __forceinline__ double m_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
@@ -151,11 +179,27 @@ __device__ __forceinline__ void step_from_trig(const T x[4], T acc, T dt, T dt_o
 template <typename T>
 __device__ __forceinline__ void propagate(const T x[4], T acc, T steer, T dt, T wheelbase,
                                           int ref_point, T out[4]) {
+#ifdef CILQR_PARITY
+    // the reference's own sequence (src/utils.cpp:262-283)
+    const T beta = m_atan(m_tan(steer) / 2);
+    if (ref_point == 0) {
+        out[0] = x[0] + x[2] * m_cos(x[3]) * dt;
+        out[1] = x[1] + x[2] * m_sin(x[3]) * dt;
+        out[2] = x[2] + acc * dt;
+        out[3] = x[3] + x[2] * m_tan(steer) * dt / wheelbase;
+    } else {
+        out[0] = x[0] + x[2] * m_cos(beta + x[3]) * dt;
+        out[1] = x[1] + x[2] * m_sin(beta + x[3]) * dt;
+        out[2] = x[2] + acc * dt;
+        out[3] = x[3] + 2 * x[2] * m_sin(beta) * dt / wheelbase;
+    }
+#else
     T sy, cy, ss, cs, s, c, turn;
     m_sincos(x[3], &sy, &cy);
     m_sincos(steer, &ss, &cs);
     step_trig(ref_point, any_gravity_lane(ref_point), sy, cy, ss, cs, &s, &c, &turn);
     step_from_trig(x, acc, dt, dt / wheelbase, ref_point, s, c, turn, out);
+#endif
 }
 
 // src/utils.cpp:285-342 — the non-trivial entries of A = df/dx (identity plus
@@ -244,12 +288,22 @@ __device__ __forceinline__ T ellipse_margin(T px, T py, T ox, T oy, T so, T co, 
     T dx = px - ox, dy = py - oy;
     T xs = co * dx + so * dy;
     T ys = -so * dx + co * dy;
+#ifdef CILQR_PARITY
+    // parity build: inv_a2 / inv_b2 hold a^2 and b^2 themselves and the reference's divisions are kept
+    T margin = 1 - ((xs * xs) / inv_a2 + (ys * ys) / inv_b2);
+    if (kGrad) {
+        T g0 = -2 * xs / inv_a2, g1 = -2 * ys / inv_b2;
+        *gx = co * g0 + (-so) * g1;
+        *gy = so * g0 + co * g1;
+    }
+#else
     T margin = 1 - ((xs * xs) * inv_a2 + (ys * ys) * inv_b2);
     if (kGrad) {
         T g0 = -2 * xs * inv_a2, g1 = -2 * ys * inv_b2;
         *gx = co * g0 + (-so) * g1;
         *gy = so * g0 + co * g1;
     }
+#endif
     return margin;
 }
 
