@@ -84,7 +84,7 @@ const char* cilqr_b200_version(void);
 
 /* Replaces the constructor (cpp:17-83).  Allocates every device buffer for
  * max_batch problems of horizon N with up to max_obs obstacles each; nothing
- * is allocated by later calls.  `params` becomes template 0. */
+ * is allocated by later calls.  `params` becomes template 0.  max_batch <= 8388480 per handle. */
 int cilqr_b200_create(const cilqr_params_t* params, int device, int max_batch, int N, int max_obs,
                       int dtype, cilqr_handle_t** out);
 int cilqr_b200_destroy(cilqr_handle_t* h);
@@ -126,11 +126,13 @@ int cilqr_b200_download(cilqr_handle_t* h, int B, double* u_out, double* x_out, 
                         int32_t* exit_out);
 
 /* The step after the path: the receding-horizon loop of src/motion_planning.cpp:180-197
- * for B independent scenarios, entirely on the device.  Per tick t = 0 .. ticks-1:
- *     (u, x) = solve(ego_state, ref line, ref_velo, get_sub_routing_lines(tracks, t), borders);
+ * for B independent scenarios, entirely on the device.  Per tick i = 0 .. ticks-1, with t = 0, dt, 2 dt, ...
+ * accumulated in floating point and index = size_t(t / delta_t) exactly as the reference computes it
+ * (motion_planning.cpp:180-181; for delta_t = 0.1 the sequence is 0,1,2,3,4,5,5,6,...):
+ *     (u, x) = solve(ego_state, ref line, ref_velo, get_sub_routing_lines(tracks, index), borders);
  *     ego_state = x.row(1);
  * with the warm start of lqr/use_last_solution carried between ticks.  tracks [B][max_obs][track_len][3]
- * are the full obstacle tracks (tick t reads samples t .. t+N; track_len < ticks + N is
+ * are the full obstacle tracks (a tick reads samples index .. index+N; a track too short for the last tick is
  * CILQR_ERR_RANGE, the reference's std::out_of_range).  ego_out [B][ticks+1][4] (ego_out[.][0] = x0),
  * iters_out / status_out [B][ticks] may be NULL.  Track and history buffers are (re)allocated here when a
  * longer simulation than any before is requested. */

@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
 LIB_PM_PATH = os.path.join(_HERE, "liboracle_pm.so")
+LIB_FMA_PATH = os.path.join(_HERE, "liboracle_fma.so")
 
 PARAM_FIELDS = [
     ("dt", "d"),
@@ -45,13 +46,26 @@ _libs = {}
 #   f64 / f32    the restatement with glibc's transcendentals (pinned to the reference sources, oracle/_ref)
 #   f80          the same in x87 long double (64-bit mantissa): the "truth" fp64 implementations are measured against
 #   f64pm/f32pm  transcendentals from the portable header shared with the CUDA PARITY build (bit-identical on GPU)
-_DT = {"f64": ("glibc", 0), "f32": ("glibc", 1), "f80": ("glibc", 2), "f64pm": ("pm", 0), "f32pm": ("pm", 1)}
+#   f64fma/f32fma  the glibc flavour compiled with FMA contraction (another toolchain's rounding pattern)
+_DT = {"f64": ("glibc", 0), "f32": ("glibc", 1), "f80": ("glibc", 2), "f64pm": ("pm", 0), "f32pm": ("pm", 1),
+       "f64fma": ("fma", 0), "f32fma": ("fma", 1)}
+_PATHS = {"glibc": LIB_PATH, "pm": LIB_PM_PATH, "fma": LIB_FMA_PATH}
+
+
+def fma_available():
+    """The fma flavour executes FMA instructions: only on a host CPU that has them."""
+    try:
+        return " fma " in open("/proc/cpuinfo").read()
+    except OSError:
+        return False
 
 
 def lib(dtype="f64"):
     flavour = _DT[dtype][0]
     if flavour not in _libs:
-        path = LIB_PATH if flavour == "glibc" else LIB_PM_PATH
+        path = _PATHS[flavour]
+        if flavour == "fma" and not fma_available():
+            raise RuntimeError("this CPU has no FMA instructions: the fma flavour of the oracle cannot run")
         if not os.path.exists(path):
             subprocess.run(["make", "-s", "-C", _HERE, os.path.basename(path)], check=True)
         l = C.CDLL(path)

@@ -37,9 +37,23 @@ def oracle_stage(pb, b, u, x, dtype="f64"):
     return J, sc, dv, A, Bm, idx
 
 
-def relerr(a, b, floor=1.0):
+def relerr(a, b, floor=1.0, loose_nonfinite=False):
+    """max |a - b| / max(|b|, floor); entries where both sides hold the same inf (an overflowed barrier term) or
+    both NaN count as equal, a non-finite value on one side only as an infinite error.  loose_nonfinite: an entry
+    that overflowed on both sides counts as equal whether it ended up inf or NaN (fp32 with several overflowed
+    terms: inf - inf versus inf + NaN depends on the order the terms meet)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+    if not a.size:
+        return 0.0
+    fin = np.isfinite(a) & np.isfinite(b)
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    if loose_nonfinite:
+        same |= ~np.isfinite(a) & ~np.isfinite(b)
+    if np.any(~fin & ~same):
+        return float("inf")
+    with np.errstate(invalid="ignore"):
+        e = np.where(fin, np.abs(a - b) / np.maximum(np.abs(b), floor), 0.0)
+    return float(np.max(e))
 
 
 def compare_traces(gpu_solver, out, ref, cap):

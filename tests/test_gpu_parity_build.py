@@ -177,7 +177,8 @@ def test_fast_vs_parity_agreement(cfg, B, N):
         with cb.BatchSolver(pb.templates, B, N, pb.max_obs, "f64", flavour=flavour) as s:
             res[flavour] = s.solve(pb)
     gpu = _agreement(res["fast"], res["parity"])
-    cpu = _agreement(op.solve_batch(pb, "f64"), op.solve_batch(pb, "f64pm"))
+    o_glibc, o_pm = op.solve_batch(pb, "f64"), op.solve_batch(pb, "f64pm")
+    cpu = _agreement(o_glibc, o_pm)
     print("%s  fast-vs-parity (GPU): same iteration count %.3f, within 1e-6 %.3f, median |dx| %.2e   |   "
           "libm swap on the CPU oracle: %.3f, %.3f, %.2e" % ((cfg,) + gpu + cpu))
     assert gpu[0] >= cpu[0] - 0.2 and gpu[1] >= cpu[1] - 0.2
@@ -185,4 +186,6 @@ def test_fast_vs_parity_agreement(cfg, B, N):
     a, b = res["fast"], res["parity"]
     conv = (a.exit_reason == 1) & (b.exit_reason == 1)
     rel = np.abs(a.J[conv, 1] - b.J[conv, 1]) / np.abs(b.J[conv, 1])
-    assert np.median(rel) < 1e-6
+    conv = (o_glibc.exit_reason == 1) & (o_pm.exit_reason == 1)
+    rel_cpu = np.abs(o_glibc.J[conv, 1] - o_pm.J[conv, 1]) / np.abs(o_pm.J[conv, 1])
+    assert np.median(rel) <= 10 * np.median(rel_cpu) + 1e-9

@@ -57,20 +57,27 @@ def test_first_iterations_lockstep(cfg, max_iter):
 @pytest.mark.parametrize("name", cb.templates.TEMPLATE_ORDER)
 @pytest.mark.parametrize("N", [30, 50])
 def test_templates_first_solve_fp64(name, N):
+    """The four shipped scenarios (BASELINE config C0 = two_straight at N = 50) on the default build.  The PARITY
+    build reproduces all eight bit for bit and within 1e-6 of the glibc oracle (tests/test_gpu_parity_build.py);
+    the default build is held to 1e-6 wherever it takes the oracle's decisions, and to the same converged cost
+    where a decision within rounding noise went the other way (the nominal two_straight start sits on waypoints
+    to ~1e-14 m, so the direction of its border gradient is rounding noise, SURVEY hard part 1)."""
     scn = cb.get_scenario(name)
     pb = cb.single_problem(scn, N)
     o = op.Solver(scn.params, N)
     r = o.solve(pb.templates[0], pb.ref_velo[0], pb.n_obs[0], pb.obs[0], pb.borders[0], pb.x0[0])
     with cb.BatchSolver(pb.templates, 1, N, pb.max_obs, "f64") as s:
         out = s.solve(pb)
-    # the nominal two_straight start sits on waypoints to ~1e-14 m: its border-gradient direction is
-    # rounding noise (SURVEY hard part 1), so only the decision-stable templates are held to 1e-6
+    assert relerr(out.J[0, 0], r.J[0]) < 1e-12
     if out.iters[0] == r.iters and out.exit_reason[0] == r.exit_reason:
         assert np.abs(out.x[0] - r.x).max() < 1e-6
         assert np.abs(out.u[0] - r.u).max() < 1e-6
         assert relerr(out.J[0], r.J) < 1e-6
     else:
-        assert name == "two_straight" or name == "three_bend", (name, out.iters, r.iters)
+        print("%s N=%d: %d iterations (oracle %d), final cost %.9g (oracle %.9g)" % (name, N, out.iters[0], r.iters, out.J[0, 1], r.J[1]))
+        assert out.exit_reason[0] == r.exit_reason
+        assert abs(out.J[0, 1] - r.J[1]) <= 1e-3 * abs(r.J[1])
+        assert np.abs(out.x[0] - r.x).max() < 0.05
 
 
 @pytest.mark.parametrize("cfg", ["C1", "C3"])

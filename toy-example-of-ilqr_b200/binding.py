@@ -339,10 +339,11 @@ class CILQRSolver:
         self.last = None
 
     def solve(self, x0, ref_waypoints, ref_velo, obs_preds, road_borders):
-        key = (id(ref_waypoints), len(ref_waypoints.x))
-        if key != self._wp_id:
-            self._solver.set_template(0, None, ref_waypoints.x, ref_waypoints.y, ref_waypoints.yaw)
-            self._wp_id = key
+        # the reference reads the line afresh on every solve(): re-upload whenever its content changed
+        line = tuple(np.array(v, dtype=np.float64) for v in (ref_waypoints.x, ref_waypoints.y, ref_waypoints.yaw))
+        if self._wp_id is None or not all(np.array_equal(a, b) for a, b in zip(line, self._wp_id)):
+            self._solver.set_template(0, None, *line)
+            self._wp_id = line
         n = len(obs_preds)
         if n > self._max_obs:
             raise ValueError("more obstacles (%d) than max_obs=%d" % (n, self._max_obs))

@@ -6,6 +6,7 @@
 #include "cilqr_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -427,6 +428,7 @@ int pack_to_device(Impl<T>* h, const double* src, T* dst, int B, int blocks, int
     if (E == 0 || B == 0) return 0;
     size_t per = E * sizeof(double);
     int chunk = int(std::min<size_t>(size_t(B), std::max<size_t>(h->stage_bytes / per, 1)));
+    chunk = std::min(chunk, 65535 * 32);  // gridDim.y of the transpose kernel
     if (per > h->stage_bytes) return fail(CILQR_ERR_INVALID, "one trajectory's array (%zu bytes) exceeds the staging buffer", per);
     for (int b0 = 0; b0 < B; b0 += chunk) {
         int nb = std::min(chunk, B - b0);
@@ -461,6 +463,7 @@ int unpack_to_host(Impl<T>* h, const T* src, double* dst, int B, int E, size_t s
     if (stride == 0) stride = h->Bs;
     size_t per = size_t(E) * sizeof(double);
     int chunk = int(std::min<size_t>(size_t(B), std::max<size_t>(h->stage_bytes / per, 1)));
+    chunk = std::min(chunk, 65535 * 32);  // gridDim.y of the transpose kernel
     for (int b0 = 0; b0 < B; b0 += chunk) {
         int nb = std::min(chunk, B - b0);
         dim3 g((E + 31) / 32, (nb + 31) / 32), blk(32, 8);
@@ -674,11 +677,35 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // the latency-regime kernels for its stragglers).
     int launched = 0;
     int level = 0, repack_bound[kRepackLevels], repack_off[kRepackLevels + 1] = {0};
+    // the spin below must not outlive a device fault or a stalled kernel: every kSpinCheck polls the stream is
+    // queried (a sticky error, or an idle stream whose progress words still say "rounds outstanding", ends the
+    // solve with CILQR_ERR_CUDA), and a round that makes no progress for kStallSeconds is reported as a stall
+    constexpr unsigned kSpinCheck = 1u << 16;
+    constexpr double kStallSeconds = 60.0;
+    unsigned spins = 0;
+    int last_done = -1;
+    auto last_progress = std::chrono::steady_clock::now();
     while (launched < h->max_rounds) {
         const unsigned long long w = progress[0];
         const int done = int(w >> 32);
         if (done > 0 && unsigned(w) == 0u) break;
-        if (launched - done > h->run_ahead) continue;  // spin on the mapped words
+        if (launched - done > h->run_ahead) {  // spin on the mapped words
+            if (done != last_done) {
+                last_done = done;
+                spins = 0;
+                last_progress = std::chrono::steady_clock::now();
+            } else if (++spins % kSpinCheck == 0) {
+                const cudaError_t q = cudaStreamQuery(h->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady)
+                    return fail(CILQR_ERR_CUDA, "solve aborted after %d of %d queued rounds: %s", done, launched, cudaGetErrorString(q));
+                if (q == cudaSuccess && int(progress[0] >> 32) == done)
+                    return fail(CILQR_ERR_CUDA, "solve stalled: the stream is idle but only %d of %d queued rounds reported", done, launched);
+                const double idle = std::chrono::duration<double>(std::chrono::steady_clock::now() - last_progress).count();
+                if (idle > kStallSeconds)
+                    return fail(CILQR_ERR_CUDA, "solve stalled: no round completed for %.0f s (%d of %d queued rounds done)", idle, done, launched);
+            }
+            continue;
+        }
         const int n_bound = std::max(1, std::min(B, int(unsigned(progress[1]))));
         // Repack: the survivors of a large batch have thinned out to half of the slots in use -> move
         // them into a dense prefix (swap_instances) and carry on as a batch of that size.
@@ -774,7 +801,11 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     int ctl[CTL_WORDS];
     CK(cudaMemcpy(ctl, h->D.ctl, sizeof ctl, cudaMemcpyDeviceToHost));
     h->counters.rounds = ctl[CTL_ROUND];
-    h->counters.total_trials = ctl[CTL_TRIALS];
+    {
+        unsigned long long t;
+        memcpy(&t, &ctl[CTL_TRIALS], sizeof t);
+        h->counters.total_trials = int64_t(t);
+    }
     h->counters.launches = h->launches;
     return 0;
 }
@@ -1075,9 +1106,15 @@ int do_simulate(Impl<T>* h, int B, const double* x0, const double* ref_velo, con
     bool any = false;
     if (n_obs)
         for (int b = 0; b < B && !any; ++b) any = n_obs[b] > 0;
-    if (any && track_len < ticks + N)
+    std::vector<int> offs(ticks);
+    {
+        const double dt = h->params[0].dt;
+        double t = 0.;
+        for (int i = 0; i < ticks; ++i, t += dt) offs[i] = int(size_t(t / dt));
+    }
+    if (any && track_len < offs[ticks - 1] + N + 1)
         return fail(CILQR_ERR_RANGE, "obstacle tracks hold %d samples, the last tick needs %d (RoutingLine index out of range)",
-                    track_len, ticks + N);
+                    track_len, offs[ticks - 1] + N + 1);
     int rc;
     if ((rc = check_tmpl_nobs(h, B, tmpl, n_obs, track_len))) return rc;
     // set-up allocations (grow-only): full tracks and the per-tick history
@@ -1105,8 +1142,11 @@ int do_simulate(Impl<T>* h, int B, const double* x0, const double* ref_velo, con
     h->D.obs_len = track_len;
     int64_t total_iters = 0, total_trials = 0;
     int rounds = 0, launches = 0;
+    // the obstacle window of tick i starts at sample size_t(t / delta_t) with t accumulated in floating point,
+    // exactly as the reference's loop does (motion_planning.cpp:180-181: for delta_t = 0.1 the sequence is
+    // 0,1,2,3,4,5,5,6,... — the truncation of 0.6 / 0.1 = 5.999...)
     for (int t = 0; t < ticks; ++t) {
-        h->D.obs_off = t;
+        h->D.obs_off = offs[t];
         if ((rc = do_solve_resident(h, B))) break;
         LAUNCH(h, k_advance<T>, gs1(B), 128, h->D, B, t, h->hist_x, h->hist_iters, h->hist_status);
         total_trials += h->counters.total_trials;
@@ -1286,6 +1326,9 @@ int cilqr_b200_create(const cilqr_params_t* params, int device, int max_batch, i
     int rc = check_params(params);
     if (rc) return rc;
     if (max_batch <= 0) return fail(CILQR_ERR_INVALID, "max_batch must be positive");
+    if (max_batch > kMaxBatch)
+        return fail(CILQR_ERR_INVALID, "max_batch %d exceeds %d (the verdict kernel's per-round tally holds 24-bit counts); "
+                    "shard larger batches over several handles", max_batch, kMaxBatch);
     if (N < 1 || N > 4096) return fail(CILQR_ERR_INVALID, "horizon N must be in [1, 4096]");
     if (max_obs < 0 || max_obs > 64) return fail(CILQR_ERR_INVALID, "max_obs must be in [0, 64]");
     if (dtype != CILQR_F64 && dtype != CILQR_F32) return fail(CILQR_ERR_INVALID, "dtype must be CILQR_F64 or CILQR_F32");

@@ -47,7 +47,7 @@ constexpr int kRecLu = 14;      // l_u   [2]
 constexpr int kRecLuu = 16;     // l_uu  sym: 00 01 11
 constexpr int kRecA = 19;       // A     a02 a03 a12 a13 a32
 constexpr int kRecB = 24;       // B     b01 b11 b20 b31
-constexpr int kVN = 10;         // value-function Hessian carried by the recursion: symmetric, upper triangle
+constexpr int kVN = 16;         // value-function Hessian carried by the recursion: the full 4x4, as in the reference (see riccati_step)
 constexpr int kScPlanes = 1;    // per-step cost rows
 #else
 // Parity build: l_xx and V_xx are kept as the full 4x4 the reference carries (its products do not
@@ -79,13 +79,17 @@ enum Status : int { ST_RUNNING = 0, ST_CONVERGED = 1, ST_BWD_FAIL = 2, ST_FWD_FA
 enum ExitReason : int { EX_MAX_ITER = 0, EX_CONVERGED = 1, EX_MAX_LAMB = 2 };
 // device-side loop control words
 enum Ctl : int {
-    CTL_NV = 0, CTL_ACTIVE = 1, CTL_TICKET = 2, CTL_ROUND = 3, CTL_TRIALS = 4,
+    CTL_NV = 0, CTL_ACTIVE = 1, CTL_TICKET = 2, CTL_ROUND = 3,
     CTL_NACT = 5,   // [2] entries in the two work lists (round parity)
     CTL_CHUNK = 7,  // next chunk of the work list to hand out in the verdict kernel
-    CTL_TALLY = 8,  // [2 words, one 64-bit counter] verdict kernel: blocks done << 47 | trials << 23 | running
+    CTL_TALLY = 8,  // [2 words, one 64-bit counter] verdict kernel: blocks done << 48 | trials << 24 | running
+    CTL_TRIALS = 10,  // [2 words, one 64-bit counter] line-search trials evaluated over the whole solve
     CTL_NSWAP = 16,  // [kRepackLevels] slot pairs exchanged by each repack of the solve
     CTL_WORDS = 32
 };
+// The tally packs the round's running instances and trials into 24 bits each and the finished blocks into 16
+// (one block per 128 work-list entries): cilqr_b200_create refuses batches beyond this.
+constexpr int kMaxBatch = (1 << 23) - 128;
 
 // Everything a kernel needs, passed by value.
 template <typename T>
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
 // (windowed or one by one) must compare the same bits
 template <typename T>
 __device__ __forceinline__ T wp_dist2(T px, T py, T wx, T wy) {
-#ifdef CILQR_PARITY
+#if defined(CILQR_PARITY) || defined(CILQR_EXPERIMENT_HYPOT)
     return m_hypot(px - wx, py - wy);  // the reference compares hypot() values (cpp:300-309)
 #else
     const T ex = px - wx, ey = py - wy;
@@ -740,13 +744,20 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
             T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
             // velocity bounds: c_dot = (0,0,+-1,0)
             T cv[2] = {x[2] - P.velo_max, P.velo_min - x[2]};
+            // zV / zB / zO: what the zero entries of a constraint's c_dot contribute in the reference, which forms
+            // every product (cpp:696-698): 0 for a finite barrier weight, NaN for one that overflowed (0 * inf).
+            // Summed per constraint family and added below to the entries that family does not otherwise touch,
+            // so that an overflowing barrier poisons the same entries as in the reference.
+            T zV = 0, zB = 0, zO = 0;
             T g, h;
             constraint_weights(alm, cv[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4) * Bs] : T(0), &g, &h);
             gx[2] += g;
             H[7] += h;
+            zV += g + h;
             constraint_weights(alm, cv[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(5) * Bs] : T(0), &g, &h);
             gx[2] += -g;
             H[7] += h;
+            zV += g + h;
             // road borders: c_dot = +-(px-rx, py-ry)/hypot, flipped when d_sign < 0 (cpp:527-533)
             T d_sign, hyp;
             T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
@@ -762,12 +773,14 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
             H[0] += h * (n0 * n0);
             H[1] += h * (n0 * n1);
             H[4] += h * (n1 * n1);
+            zB += g + h;
             constraint_weights(alm, cp[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(7) * Bs] : T(0), &g, &h);
             gx[0] += g * (-n0);
             gx[1] += g * (-n1);
             H[0] += h * (n0 * n0);
             H[1] += h * (n0 * n1);
             H[4] += h * (n1 * n1);
+            zB += g + h;
             if (alm) {
                 mun[size_t(4) * Bs] = std_min(std_max(mu[size_t(4) * Bs] + rho * cv[0], T(0)), P.max_mu);
                 mun[size_t(5) * Bs] = std_min(std_max(mu[size_t(5) * Bs] + rho * cv[1], T(0)), P.max_mu);
@@ -809,6 +822,7 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
                         tH[q][3] = hf * (gfy * gfy) + hr * (gry * gry);
                         tH[q][4] = hf * (gfy * f3) + hr * (gry * r3);
                         tH[q][5] = hf * (f3 * f3) + hr * (r3 * r3);
+                        if (q == 0 || two) zO += (gf + hf) + (gr + hr);
                         if (alm && (q == 0 || two)) {
                             mun[size_t(8 + 2 * jj) * Bs] =
                                 std_min(std_max(mu[size_t(8 + 2 * jj) * Bs] + rho * cf, T(0)), P.max_mu);
@@ -832,6 +846,25 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
                     }
                 }
             }
+            // velocity terms have c_dot = (0, 0, +-1, 0), border terms (n0, n1, 0, 0), obstacle terms (gx, gy, 0, g3)
+            zV *= T(0);
+            zB *= T(0);
+            zO *= T(0);
+            gx[0] += zV;
+            gx[1] += zV;
+            gx[2] += zB + zO;
+            gx[3] += zV + zB;
+            const T zVB = zV + zB, zAll = zVB + zO;
+            H[0] += zV;       // 00
+            H[1] += zV;       // 01
+            H[2] += zAll;     // 02
+            H[3] += zVB;      // 03
+            H[4] += zV;       // 11
+            H[5] += zAll;     // 12
+            H[6] += zVB;      // 13
+            H[7] += zB + zO;  // 22
+            H[8] += zAll;     // 23
+            H[9] += zVB;      // 33
         }
         // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
 #pragma unroll
@@ -870,10 +903,13 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
 #pragma unroll
             for (int m = 0; m < 4; ++m)
                 constraint_weights(alm, c[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * Bs] : T(0), &g[m], &h[m]);
-            T gu0 = g[0] + (-g[1]);
-            T gu1 = g[2] + (-g[3]);
-            T hu0 = h[0] + h[1];
-            T hu1 = h[2] + h[3];
+            // (zA / zS: the zero entries of c_dot, as in the state half: an overflowed acceleration barrier
+            // poisons the steering entries and vice versa, both poison the off-diagonal)
+            const T zA = ((g[0] + h[0]) + (g[1] + h[1])) * T(0), zS = ((g[2] + h[2]) + (g[3] + h[3])) * T(0);
+            T gu0 = (g[0] + (-g[1])) + zS;
+            T gu1 = (g[2] + (-g[3])) + zA;
+            T hu0 = (h[0] + h[1]) + zS;
+            T hu1 = (h[2] + h[3]) + zA;
             if (alm) {
                 T* mun = D.mu_next + size_t(k) * D.alm_cols * Bs + b;
 #pragma unroll
@@ -883,7 +919,7 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
             rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu0;
             rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu1;
             rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + hu0;
-            rec[(kRecLuu + 1) * kRecFS] = 0;
+            rec[(kRecLuu + 1) * kRecFS] = zA + zS;
             rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + hu1;
 #endif
             T ja[5], jb[4];
@@ -929,6 +965,25 @@ __device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T
     } else {
         D.phase[b] = PH_BACKWARD;
     }
+}
+
+// V_xx at the horizon = l_xx[N] (cpp:395-396), from the record's l_xx fields (stride kRecFS)
+template <typename T>
+__device__ __forceinline__ void load_terminal_V(const T* rec, T* V) {
+#ifdef CILQR_PARITY
+#pragma unroll
+    for (int c = 0; c < 16; ++c) V[c] = rec[(kRecLxx + c) * kRecFS];
+#else
+    int e = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = r; c < 4; ++c, ++e) {
+            const T v = rec[(kRecLxx + e) * kRecFS];
+            V[r * 4 + c] = v;
+            V[c * 4 + r] = v;
+        }
+#endif
 }
 
 template <typename T>
@@ -1077,34 +1132,40 @@ __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T&
     return true;
 }
 #else
+// The value-function Hessian is carried as the full 4x4 and updated with the reference's three-term form WITHOUT
+// symmetrising it, although in exact arithmetic it is symmetric: the reference's recursion amplifies the
+// antisymmetric part of V_xx (rounding noise to begin with) by roughly rho(A - BK) rho(A + BK) per step, and on long
+// horizons with stiff barrier terms (N >= 100: BASELINE configs C2, C4) that mode grows until Q_uu fails the
+// positive-definiteness test — backward_pass returns BACKWARD_PASS_FAIL and solve() raises lambda (cpp:415-420,
+// :118-120).  A symmetric recursion (10 entries) is cheaper and numerically better behaved, but it sails through
+// where the reference fails (measured: tests/test_gpu_truth_bound.py), i.e. it is a different algorithm on exactly
+// the configs the benchmark names.  Same products as the reference, A and B in their sparse form, sums in the
+// reference's order; FMA contraction is the only liberty taken.
 template <typename T>
 __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T& dV0, T& dV1, T* K, T& d0, T& d1) {
     const T a02 = r[kRecA + 0], a03 = r[kRecA + 1], a12 = r[kRecA + 2], a13 = r[kRecA + 3], a32 = r[kRecA + 4];
     const T b01 = r[kRecB + 0], b11 = r[kRecB + 1], b20 = r[kRecB + 2], b31 = r[kRecB + 3];
-    // symmetric V: 00 01 02 03 11 12 13 22 23 33
-    const T V00 = V[0], V01 = V[1], V02 = V[2], V03 = V[3], V11 = V[4], V12 = V[5], V13 = V[6], V22 = V[7],
-            V23 = V[8], V33 = V[9];
-    // W = V A  (columns 0,1 unchanged)
-    const T W02 = a02 * V00 + a12 * V01 + V02 + a32 * V03;
-    const T W12 = a02 * V01 + a12 * V11 + V12 + a32 * V13;
-    const T W22 = a02 * V02 + a12 * V12 + V22 + a32 * V23;
-    const T W32 = a02 * V03 + a12 * V13 + V23 + a32 * V33;
-    const T W03 = a03 * V00 + a13 * V01 + V03;
-    const T W13 = a03 * V01 + a13 * V11 + V13;
-    const T W23 = a03 * V02 + a13 * V12 + V23;
-    const T W33 = a03 * V03 + a13 * V13 + V33;
-    // Q_xx = l_xx + A^T V A  (symmetric, upper triangle)
-    T Qxx[10];
-    Qxx[0] = r[kRecLxx + 0] + V00;
-    Qxx[1] = r[kRecLxx + 1] + V01;
-    Qxx[2] = r[kRecLxx + 2] + W02;
-    Qxx[3] = r[kRecLxx + 3] + W03;
-    Qxx[4] = r[kRecLxx + 4] + V11;
-    Qxx[5] = r[kRecLxx + 5] + W12;
-    Qxx[6] = r[kRecLxx + 6] + W13;
-    Qxx[7] = r[kRecLxx + 7] + (a02 * W02 + a12 * W12 + W22 + a32 * W32);
-    Qxx[8] = r[kRecLxx + 8] + (a02 * W03 + a12 * W13 + W23 + a32 * W33);
-    Qxx[9] = r[kRecLxx + 9] + (a03 * W03 + a13 * W13 + W33);
+    // P = A^T V: rows 0 and 1 are V's, rows 2 and 3 mix in columns 2 and 3 of A (A = I + {02, 03, 12, 13, 32})
+    T P2[4], P3[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        P2[c] = a02 * V[0 * 4 + c] + a12 * V[1 * 4 + c] + V[2 * 4 + c] + a32 * V[3 * 4 + c];
+        P3[c] = a03 * V[0 * 4 + c] + a13 * V[1 * 4 + c] + V[3 * 4 + c];
+    }
+    // Q_xx = l_xx + P A (l_xx symmetric, upper triangle in the record)
+    T Qxx[16];
+    {
+        const T* P[4] = {V, V + 4, P2, P3};
+        const int sym[16] = {0, 1, 2, 3, 1, 4, 5, 6, 2, 5, 7, 8, 3, 6, 8, 9};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const T* p = P[i];
+            Qxx[i * 4 + 0] = r[kRecLxx + sym[i * 4 + 0]] + p[0];
+            Qxx[i * 4 + 1] = r[kRecLxx + sym[i * 4 + 1]] + p[1];
+            Qxx[i * 4 + 2] = r[kRecLxx + sym[i * 4 + 2]] + (a02 * p[0] + a12 * p[1] + p[2] + a32 * p[3]);
+            Qxx[i * 4 + 3] = r[kRecLxx + sym[i * 4 + 3]] + (a03 * p[0] + a13 * p[1] + p[3]);
+        }
+    }
     // Q_x = l_x + A^T V_x ; Q_u = l_u + B^T V_x
     T Qx[4];
     Qx[0] = r[kRecLx + 0] + Vx[0];
@@ -1113,12 +1174,12 @@ __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T&
     Qx[3] = r[kRecLx + 3] + (a03 * Vx[0] + a13 * Vx[1] + Vx[3]);
     const T Qu0 = r[kRecLu + 0] + b20 * Vx[2];
     const T Qu1 = r[kRecLu + 1] + (b01 * Vx[0] + b11 * Vx[1] + b31 * Vx[3]);
-    // G = B^T V (2x4)
-    const T G00 = b20 * V02, G01 = b20 * V12, G02 = b20 * V22, G03 = b20 * V23;
-    const T G10 = b01 * V00 + b11 * V01 + b31 * V03;
-    const T G11 = b01 * V01 + b11 * V11 + b31 * V13;
-    const T G12 = b01 * V02 + b11 * V12 + b31 * V23;
-    const T G13 = b01 * V03 + b11 * V13 + b31 * V33;
+    // G = B^T V (2x4): row 0 = b20 V[2][.], row 1 = b01 V[0][.] + b11 V[1][.] + b31 V[3][.]
+    const T G00 = b20 * V[8], G01 = b20 * V[9], G02 = b20 * V[10], G03 = b20 * V[11];
+    const T G10 = b01 * V[0] + b11 * V[4] + b31 * V[12];
+    const T G11 = b01 * V[1] + b11 * V[5] + b31 * V[13];
+    const T G12 = b01 * V[2] + b11 * V[6] + b31 * V[14];
+    const T G13 = b01 * V[3] + b11 * V[7] + b31 * V[15];
     // Q_ux = G A (2x4)
     T Qux[8];
     Qux[0] = G00;
@@ -1175,18 +1236,15 @@ __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T&
         T t3 = Qux[c] * d0 + Qux[4 + c] * d1;
         Vx[c] = ((Qx[c] + t1) + t2) + t3;
     }
-    {
-        int e = 0;
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr)
+    for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-            for (int cc = rr; cc < 4; ++cc, ++e) {
-                T t1 = M0[rr] * K[cc] + M1[rr] * K[4 + cc];
-                T t2 = K[rr] * Qux[cc] + K[4 + rr] * Qux[4 + cc];
-                T t3 = Qux[rr] * K[cc] + Qux[4 + rr] * K[4 + cc];
-                V[e] = ((Qxx[e] + t1) + t2) + t3;
-            }
-    }
+        for (int cc = 0; cc < 4; ++cc) {
+            T t1 = M0[rr] * K[cc] + M1[rr] * K[4 + cc];
+            T t2 = K[rr] * Qux[cc] + K[4 + rr] * Qux[4 + cc];
+            T t3 = Qux[rr] * K[cc] + Qux[4 + rr] * K[4 + cc];
+            V[rr * 4 + cc] = ((Qxx[rr * 4 + cc] + t1) + t2) + t3;
+        }
     // expected cost reduction (cpp:435-436)
     const T h0 = T(0.5) * d0, h1 = T(0.5) * d1;
     dV0 += (h0 * Quu00 + h1 * Quu10) * d0 + (h0 * Quu01 + h1 * Quu11) * d1;
@@ -1210,8 +1268,7 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
     T Vx[4], V[kVN];
 #pragma unroll
     for (int c = 0; c < 4; ++c) Vx[c] = rec[(kRecLx + c) * kRecFS];
-#pragma unroll
-    for (int c = 0; c < kVN; ++c) V[c] = rec[(kRecLxx + c) * kRecFS];
+    load_terminal_V(rec, V);
     T dV0 = 0, dV1 = 0;
     bool failed = false;
     int i = N - 1;
@@ -1445,8 +1502,7 @@ __global__ void __launch_bounds__(32) k_backward_staged(Dev<T> D, int B, int sol
                 const T* rec = rec_at(D, N, in ? b : 0);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) Vx[c] = rec[(kRecLx + c) * kRecFS];
-#pragma unroll
-                for (int c = 0; c < kVN; ++c) V[c] = rec[(kRecLxx + c) * kRecFS];
+                load_terminal_V(rec, V);
             }
             T dV0 = 0, dV1 = 0;
             T* Kp = D.Kg + size_t(N) * 8 * Bs + (in ? b : 0);
@@ -1987,20 +2043,20 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        // one atomic per block: running instances (23 bits), trials (24 bits) and finished blocks in
+        // one atomic per block: running instances (24 bits), trials (24 bits) and finished blocks (16 bits) in
         // one 64-bit counter; the block that completes the count has the round's totals in hand
         unsigned long long* tally = reinterpret_cast<unsigned long long*>(&D.ctl[CTL_TALLY]);
-        const unsigned long long mine = (1ull << 47) | (static_cast<unsigned long long>(unsigned(s_trials)) << 23) | unsigned(s_active);
+        const unsigned long long mine = (1ull << 48) | (static_cast<unsigned long long>(unsigned(s_trials)) << 24) | unsigned(s_active);
         __threadfence();
         const unsigned long long sum = atomicAdd(tally, mine) + mine;
-        if (int(sum >> 47) == int(gridDim.x)) {
+        if (int(sum >> 48) == int(gridDim.x)) {
             __threadfence();
-            const int active = int(sum & 0x7fffffu);
-            const int trials = int((sum >> 23) & 0xffffffu);
+            const int active = int(sum & 0xffffffu);
+            const int trials = int((sum >> 24) & 0xffffffu);
             const int n_next = *reinterpret_cast<volatile int*>(&D.ctl[CTL_NACT + (par ^ 1)]);
             const int round = D.ctl[CTL_ROUND] + 1;
             D.ctl[CTL_ROUND] = round;
-            D.ctl[CTL_TRIALS] += trials;
+            *reinterpret_cast<unsigned long long*>(&D.ctl[CTL_TRIALS]) += static_cast<unsigned long long>(trials);
             *tally = 0ull;
             D.ctl[CTL_NV] = 0;
             D.ctl[CTL_CHUNK] = 0;

@@ -22,8 +22,8 @@ namespace cilqr {
 //                cilqr_pmath.h, so that a whole free-running solve can be compared with the CPU bit for
 //                bit.  Same kernels, same work lists / trial pool / verdict logic; only the arithmetic
 //                inside the device functions differs.  Not a performance build.
-#ifdef CILQR_PARITY
-constexpr bool kParity = true;
+#if defined(CILQR_PARITY) || defined(CILQR_EXPERIMENT_DIRECT)
+constexpr bool kParity = true;  // (host side: one-thread rollout kernels only)
 #else
 constexpr bool kParity = false;
 #endif
@@ -181,6 +181,21 @@ __device__ __forceinline__ void propagate(const T x[4], T acc, T steer, T dt, T 
                                           int ref_point, T out[4]) {
 #ifdef CILQR_PARITY
     // the reference's own sequence (src/utils.cpp:262-283)
+    const T beta = m_atan(m_tan(steer) / 2);
+    if (ref_point == 0) {
+        out[0] = x[0] + x[2] * m_cos(x[3]) * dt;
+        out[1] = x[1] + x[2] * m_sin(x[3]) * dt;
+        out[2] = x[2] + acc * dt;
+        out[3] = x[3] + x[2] * m_tan(steer) * dt / wheelbase;
+    } else {
+        out[0] = x[0] + x[2] * m_cos(beta + x[3]) * dt;
+        out[1] = x[1] + x[2] * m_sin(beta + x[3]) * dt;
+        out[2] = x[2] + acc * dt;
+        out[3] = x[3] + 2 * x[2] * m_sin(beta) * dt / wheelbase;
+    }
+#elif defined(CILQR_EXPERIMENT_DIRECT)
+    // development switch: the reference's sequence with libdevice transcendentals (measures what the shared-trig
+    // formulation below costs in accuracy)
     const T beta = m_atan(m_tan(steer) / 2);
     if (ref_point == 0) {
         out[0] = x[0] + x[2] * m_cos(x[3]) * dt;

@@ -20,6 +20,7 @@
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <cstring>
 #include <vector>
 
 #include "../../include/cilqr_b200.h"
@@ -127,11 +128,16 @@ class CILQRSolver {
     template <typename RefLine, typename Routing>
     std::tuple<MatrixX2d, MatrixX4d> solve(const Vector4d& x0, const RefLine& ref_waypoints, double ref_velo,
                                            const std::vector<Routing>& obs_preds, const Vector2d& road_boaders) {
-        if (ref_waypoints.x.data() != line_ptr_ || ref_waypoints.x.size() != line_len_) {
+        // the reference reads the line afresh on every solve(); the device copy is refreshed whenever the
+        // CONTENT differs from what was uploaded last (a line edited in place, or another line at the same
+        // address, must not be served from a stale copy)
+        if (!same_line(ref_waypoints.x, line_x_) || !same_line(ref_waypoints.y, line_y_) ||
+            !same_line(ref_waypoints.yaw, line_yaw_)) {
             check(cilqr_b200_set_template(h_, 0, nullptr, ref_waypoints.x.data(), ref_waypoints.y.data(),
                                           ref_waypoints.yaw.data(), int(ref_waypoints.x.size())));
-            line_ptr_ = ref_waypoints.x.data();
-            line_len_ = ref_waypoints.x.size();
+            line_x_.assign(ref_waypoints.x.begin(), ref_waypoints.x.end());
+            line_y_.assign(ref_waypoints.y.begin(), ref_waypoints.y.end());
+            line_yaw_.assign(ref_waypoints.yaw.begin(), ref_waypoints.yaw.end());
         }
         const int n = int(obs_preds.size());
         if (n > max_obs_) throw std::invalid_argument("cilqr_b200: more obstacles than max_obs");
@@ -174,14 +180,17 @@ class CILQRSolver {
     int horizon() const { return N_; }
 
   private:
+    template <typename V>
+    static bool same_line(const V& a, const std::vector<double>& b) {
+        return a.size() == b.size() && (b.empty() || std::memcmp(a.data(), b.data(), b.size() * sizeof(double)) == 0);
+    }
     static void check(int rc) {
         if (rc == CILQR_ERR_RANGE) throw std::out_of_range(cilqr_b200_last_error());
         if (rc != 0) throw std::runtime_error(std::string("cilqr_b200: ") + cilqr_b200_last_error());
     }
     cilqr_handle_t* h_ = nullptr;
     int N_ = 0, max_obs_ = 0;
-    const double* line_ptr_ = nullptr;
-    size_t line_len_ = 0;
+    std::vector<double> line_x_, line_y_, line_yaw_;  // the reference line as last uploaded
     std::vector<double> obs_, u_, x_;
     double J_[2] = {0, 0};
     int32_t iters_ = 0, exit_ = 0;
