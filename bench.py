@@ -43,6 +43,13 @@ ROOFLINE_BATCH = 262144
 # (profiles/r01b_ncu_full_summary.txt): 2.9676 GB read + 1.0291 GB written = 0.994 x the algorithmic
 # 4.0223 GB.  Only valid for that dtype / batch.
 ROOFLINE_TRAFFIC_BYTES = {"f64": 2.967610e9 + 1.029079e9}
+ROOFLINE_TRAFFIC_SOURCE = ("constant from the committed ncu --set full capture of this kernel at this batch "
+                           "(profiles/r01b_ncu_full_summary.txt), not measured in this run")
+# the other BASELINE configs, one GPU's share each, device-generated; (config, instances, dtype)
+EXTRA_CONFIGS = [("C1", 65536, "f64"), ("C1", 262144, "f64"), ("C2", 262144, "f64"), ("C3", 131072, "f64"),
+                 ("C4", 131072, "f32")]
+MULTI_GPU_C3_PER_RANK = 131072  # x 8 ranks = BASELINE config C3 (1 048 576 mixed instances)
+CHECK_SLICE = 4096
 
 
 def measured_peak():
@@ -191,6 +198,40 @@ def run_reference(args):
     }))
 
 
+def run_config(cb, cfg, B, dtype, device, first_id=0, reps=2, k5=True):
+    """One GPU's share of a BASELINE config, generated on the device: best-of-`reps` resident solve (wall clock
+    around cilqr_b200_solve_resident, which synchronises) and the backward-pass kernel alone on the records the
+    solve left behind (L2 flushed, CUDA events)."""
+    spec = cb.synth_spec(cfg)
+    N = spec.N
+    with cb.BatchSolver(spec.templates, B, N, spec.max_obs, dtype, device=device) as s:
+        s.generate(spec, B, first_id=first_id)
+        best = None
+        for _ in range(reps + 1):  # first solve = warm-up
+            t0 = time.perf_counter()
+            s.solve_resident(B)
+            dt = time.perf_counter() - t0
+            if _ > 0:
+                best = dt if best is None else min(best, dt)
+        c = s.counters()
+        head = s.download(min(B, CHECK_SLICE), want_gains=False)
+        iters = c["total_iters"] if c["total_iters"] else None
+        # total iterations of the whole batch: counters are filled by download (first `n` instances only), so
+        # read them from the device-side per-instance counts through a full-status download
+        import numpy as np
+        st = s.download_counts(B)
+        line = {"config": cfg, "instances": B, "N": N, "dtype": dtype, "solve_ms": round(best * 1e3, 2),
+                "iter_steps": int(st["iters"]), "iterations_per_s": round(st["iters"] / best),
+                "rounds": c["rounds"], "trials": c["total_trials"], "launches": c["launches"],
+                "exits": st["exits"], "data": "generated on the device (cilqr_b200_synth_generate)"}
+        if k5:
+            sz = 8 if dtype == "f64" else 4
+            ms, nbytes = s.bench_backward(B, 0.0, 8, True)
+            line["k5_GBps"] = round(nbytes / float(np.median(ms)) / 1e6)
+            line["k5_bytes_per_trajectory"] = (38 * N + 18) * sz
+    return line, head
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +242,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE configs / multi-GPU C3 leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -339,10 +381,49 @@ def main():
         achieved = nbytes / (float(np.mean(ms)) * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_backward<T, prefetch> (backward_pass Riccati recursion, cpp:383-440)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ROOFLINE_TRAFFIC_BYTES.get(args.dtype), "peak_source": peak_src,
+                    "traffic": ROOFLINE_TRAFFIC_BYTES.get(args.dtype),
+                    "traffic_source": ROOFLINE_TRAFFIC_SOURCE if args.dtype in ROOFLINE_TRAFFIC_BYTES else None,
+                    "peak_source": peak_src,
                     "bytes_per_launch": nbytes, "ms_per_launch": float(np.mean(ms)),
                     "batch": Br, "layout": "compact record, (38*N+18)*sizeof(T) bytes per trajectory",
                     "frac_of_nominal_8000": achieved / 8000.0}
+
+    # ---- the other BASELINE configs (rank 0, one GPU's share each) and, under N > 1, config C3 sharded over
+    # the ranks with a cross-rank bit-equality check -------------------------------------------------------
+    configs, multi = None, None
+    if not args.no_configs:
+        if rank == 0 and world == 1:
+            configs = []
+            for cfg, Bc, dt in EXTRA_CONFIGS:
+                try:
+                    configs.append(run_config(cb, cfg, Bc, dt, local)[0])
+                except Exception as e:  # e.g. not enough free HBM on a shared box
+                    configs.append({"config": cfg, "instances": Bc, "dtype": dt, "error": str(e)[:200]})
+        if world > 1:
+            per = MULTI_GPU_C3_PER_RANK
+            lo, hi = cb.shard.weak_range(per, rank)
+            barrier()
+            t0 = time.perf_counter()
+            line, head = run_config(cb, "C3", per, "f64", local, first_id=lo, reps=1, k5=False)
+            barrier()
+            mine = cb.shard.result_checksum(head)
+            # the neighbour's first CHECK_SLICE instances solved here as a small batch of their own
+            nlo = cb.shard.weak_range(per, (rank + 1) % world)[0]
+            _, nhead = run_config(cb, "C3", CHECK_SLICE, "f64", local, first_id=nlo, reps=1, k5=False)
+            theirs = cb.shard.result_checksum(nhead)
+            rows = cb.shard.gather_ints(dist, dev, [mine, theirs, line["iter_steps"], int(line["solve_ms"] * 1000)])
+            if rank == 0:
+                ok = all(rows[(r + 1) % world][0] == rows[r][1] for r in range(world))
+                t_solve = max(r[3] for r in rows) / 1e6
+                total_iters = sum(r[2] for r in rows)
+                multi = {"config": "C3", "instances": per * world, "instances_per_gpu": per, "N": 50, "dtype": "f64",
+                         "solve_ms": round(t_solve * 1e3, 2), "iter_steps": total_iters,
+                         "iterations_per_s": round(total_iters / t_solve),
+                         "slice_check": {"ok": bool(ok), "slice": CHECK_SLICE,
+                                         "what": "rank r re-solves the first %d instances of rank r+1's range as a "
+                                                 "batch of their own; 64-bit checksums of (x, u, J, iters) bits "
+                                                 "all-gathered and compared" % CHECK_SLICE},
+                         "data": "generated on the device, ids [rank*%d, (rank+1)*%d)" % (per, per)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -365,6 +446,8 @@ def main():
             "roofline": roofline,
             "in_step": in_step,
             "cpu_baseline": cpu,
+            "configs": configs,
+            "multi_gpu": multi,
         }
         print(json.dumps(line))
     if dist is not None:

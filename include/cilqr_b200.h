@@ -140,6 +140,47 @@ int cilqr_b200_simulate(cilqr_handle_t* h, int B, const double* x0, const double
                         const int32_t* tmpl, const int32_t* n_obs, const double* tracks, int track_len, int ticks,
                         double* ego_out, int32_t* iters_out, int32_t* status_out);
 
+/* ---- synthetic workloads (BASELINE.json configs C1..C4), generated in place on the device ----
+ * A batch is described by one small descriptor per scenario template (instance id i uses template
+ * i % n_tmpl) plus the centre lines the descriptors refer to; every number is a function of
+ * (seed, instance id, draw index) through a counter-based generator (splitmix64 finaliser), so any slice
+ * [first_id, first_id + B) of a batch can be generated on any GPU without data crossing PCIe.  The arithmetic
+ * is spelled out step by step in toy-example-of-ilqr_b200/scenario.py (generate_host), which produces the same
+ * arrays with numpy, bit for bit (tests/test_gpu_synth.py). */
+#define CILQR_B200_SYNTH_MAX_OBS 16
+typedef struct cilqr_synth_obstacle_t {
+    int32_t kind;      /* 0: follows lane table `lane` from start_s + U(draw; -8, 8) at max(speed + U(draw+1; -1, 1), 0.5),
+                          towards decreasing s with yaw + pi when `oncoming` (src/motion_planning.cpp:149-158);
+                          1: x = [ego x0 +] U(draw; x_lo, x_hi) + direction * v t, v = U(draw_v; v_lo, v_hi),
+                             y = y0 (or y1 when two_lanes and u01(draw_lane) >= 0.5), constant yaw */
+    int32_t lane, oncoming, draw;
+    double start_s, speed;
+    double x_lo, x_hi, v_lo, v_hi, y0, y1, yaw, direction;
+    int32_t rel_to_ego, two_lanes, draw_lane, draw_v;
+} cilqr_synth_obstacle_t;
+typedef struct cilqr_synth_template_t {
+    int32_t ego_kind;  /* 0: x0 = (U0(-5,5), U1(-.6,.6), U2(5,10), U3(-.05,.05)), ref_velo = U4(6,10);
+                          1: lane frame of ego_lane at ego_s + U0(-5,5), lateral U1(-.6,.6), v = max(ego_v + U2(-2,2), .5),
+                             yaw = lane yaw + U3(-.05,.05), ref_velo = target_velocity + U4(-2,2) */
+    int32_t ego_lane, n_obs, reserved;
+    double ego_s, ego_v, target_velocity, borders[2], dt;
+    cilqr_synth_obstacle_t obs[CILQR_B200_SYNTH_MAX_OBS];
+} cilqr_synth_template_t;
+/* Centre-line tables: lane l holds samples lane_off[l] .. lane_off[l+1]-1 of x, y, yaw, arc length and the
+ * left normal (nx, ny) = (-sin yaw, cos yaw) of each sample (ReferenceLine samples, src/utils.cpp:21-35). */
+int cilqr_b200_synth_set_lanes(cilqr_handle_t* h, int n_lanes, const int32_t* lane_off, const double* x,
+                               const double* y, const double* yaw, const double* lon, const double* nx,
+                               const double* ny);
+/* Generates instances [first_id, first_id + B) into the handle (as cilqr_b200_upload would leave them); follow
+ * with cilqr_b200_solve_resident.  keep_yaw != 0 leaves the obstacle yaw unconverted for cilqr_b200_synth_download
+ * (verification only: such a batch must not be solved). */
+int cilqr_b200_synth_generate(cilqr_handle_t* h, int B, uint64_t first_id, uint64_t seed, int n_tmpl,
+                              const cilqr_synth_template_t* tmpls, int keep_yaw);
+/* The resident problem data back in host layout; obs [B][max_obs][N+1][4] = the four device fields per sample:
+ * (x, y, sin yaw, cos yaw), or (x, y, yaw, 0) after a keep_yaw generation.  Any pointer may be NULL. */
+int cilqr_b200_synth_download(cilqr_handle_t* h, int B, double* x0, double* ref_velo, double* borders, int32_t* tmpl,
+                              int32_t* n_obs, double* obs);
+
 /* Counters of the last solve: total iter_step calls over the batch, line-search
  * trials (forward pass + cost) evaluated, device rounds run, kernels launched,
  * instances per exit reason. */

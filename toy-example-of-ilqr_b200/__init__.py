@@ -10,4 +10,5 @@ from .binding import (  # noqa: F401
     BatchSolver, CILQRSolver, CilqrError, CilqrParams, SolveResult, EXPORTS, LIB_PATH, STATUS_NAMES,
     EXIT_NAMES, load_library,
 )
-from .scenario import BatchProblem, Scenario, TemplateData, synthetic_batch, single_problem, get_scenario  # noqa: F401
+from .scenario import (BatchProblem, Scenario, TemplateData, synthetic_batch, single_problem, get_scenario,  # noqa: F401
+                       synth_spec, generate_host)

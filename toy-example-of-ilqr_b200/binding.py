@@ -36,6 +36,7 @@ EXPORTS = [
     "cilqr_b200_stage_init", "cilqr_b200_stage_ref_match", "cilqr_b200_stage_cost", "cilqr_b200_stage_derivs",
     "cilqr_b200_stage_backward", "cilqr_b200_stage_forward", "cilqr_b200_bench_backward",
     "cilqr_b200_bench_tile_records",
+    "cilqr_b200_synth_set_lanes", "cilqr_b200_synth_generate", "cilqr_b200_synth_download",
 ]
 
 
@@ -48,6 +49,23 @@ class CilqrParams(C.Structure):
         for n, t in PARAM_FIELDS:
             setattr(p, n, float(d[n]) if t == "d" else int(d[n]))
         return p
+
+
+SYNTH_MAX_OBS = 16
+
+
+class SynthObstacleC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("lane", C.c_int32), ("oncoming", C.c_int32), ("draw", C.c_int32),
+                ("start_s", C.c_double), ("speed", C.c_double),
+                ("x_lo", C.c_double), ("x_hi", C.c_double), ("v_lo", C.c_double), ("v_hi", C.c_double),
+                ("y0", C.c_double), ("y1", C.c_double), ("yaw", C.c_double), ("direction", C.c_double),
+                ("rel_to_ego", C.c_int32), ("two_lanes", C.c_int32), ("draw_lane", C.c_int32), ("draw_v", C.c_int32)]
+
+
+class SynthTemplateC(C.Structure):
+    _fields_ = [("ego_kind", C.c_int32), ("ego_lane", C.c_int32), ("n_obs", C.c_int32), ("reserved", C.c_int32),
+                ("ego_s", C.c_double), ("ego_v", C.c_double), ("target_velocity", C.c_double),
+                ("borders", C.c_double * 2), ("dt", C.c_double), ("obs", SynthObstacleC * SYNTH_MAX_OBS)]
 
 
 class Counters(C.Structure):
@@ -212,6 +230,42 @@ class BatchSolver:
         self._ck(self.lib.cilqr_b200_upload(self.h, pb.B, _dp(x0), _dp(rv), _dp(bd), _ip(tm), _ip(no), _dp(ob),
                                             int(pb.obs_len)))
 
+    # -- synthetic workloads generated on the device ------------------
+    def generate(self, spec, B, seed=None, first_id=0, keep_yaw=False):
+        """cilqr_b200_synth_generate: instances [first_id, first_id + B) of the SynthSpec (scenario.synth_spec),
+        the device twin of scenario.generate_host."""
+        from .scenario import DEFAULT_SEED
+        seed = DEFAULT_SEED if seed is None else seed
+        if getattr(self, "_synth_spec", None) is not spec:
+            off = np.zeros(len(spec.lanes) + 1, np.int32)
+            for i, tb in enumerate(spec.lanes):
+                off[i + 1] = off[i] + len(tb.x)
+            cat = [_f64(np.concatenate([getattr(tb, f) for tb in spec.lanes])) for f in ("x", "y", "yaw", "lon", "nx", "ny")]
+            self._ck(self.lib.cilqr_b200_synth_set_lanes(self.h, len(spec.lanes), _ip(off), *[_dp(a) for a in cat]))
+            arr = (SynthTemplateC * len(spec.synth))()
+            for t, st in enumerate(spec.synth):
+                c = arr[t]
+                c.ego_kind, c.ego_lane, c.n_obs = int(st.ego_kind), int(st.ego_lane), len(st.obstacles)
+                c.ego_s, c.ego_v, c.target_velocity = float(st.ego_s), float(st.ego_v), float(st.target_velocity)
+                c.borders[0], c.borders[1] = float(st.borders[0]), float(st.borders[1])
+                c.dt = float(spec.templates[t].params["dt"])
+                for j, ob in enumerate(st.obstacles):
+                    for name, ctype in SynthObstacleC._fields_:
+                        v = getattr(ob, name)
+                        setattr(c.obs[j], name, int(v) if ctype is C.c_int32 else float(v))
+            self._synth_spec, self._synth_arr = spec, arr
+        self._ck(self.lib.cilqr_b200_synth_generate(self.h, int(B), C.c_uint64(int(first_id)), C.c_uint64(int(seed)),
+                                                    len(spec.synth), self._synth_arr, int(bool(keep_yaw))))
+
+    def synth_download(self, B):
+        """The resident problem data: x0 [B][4], ref_velo [B], borders [B][2], tmpl [B], n_obs [B] and the obstacle
+        samples as stored on the device, [B][max_obs][N+1][4]."""
+        x0, rv, bd = np.empty((B, 4)), np.empty(B), np.empty((B, 2))
+        tm, no = np.empty(B, np.int32), np.empty(B, np.int32)
+        ob = np.empty((B, self.max_obs, self.N + 1, 4))
+        self._ck(self.lib.cilqr_b200_synth_download(self.h, int(B), _dp(x0), _dp(rv), _dp(bd), _ip(tm), _ip(no), _dp(ob)))
+        return x0, rv, bd, tm, no, ob
+
     def solve_resident(self, B):
         self._ck(self.lib.cilqr_b200_solve_resident(self.h, int(B)))
 
@@ -221,6 +275,12 @@ class BatchSolver:
                                               _dp(out.d), _dp(out.step_cost), _ip(out.status), _ip(out.iters),
                                               _ip(out.exit_reason)))
         return out
+
+    def download_counts(self, B):
+        """iter_step total and exit histogram of the first B resident instances (only the two int arrays cross PCIe)."""
+        it, ex = np.empty(B, np.int32), np.empty(B, np.int32)
+        self._ck(self.lib.cilqr_b200_download(self.h, int(B), None, None, None, None, None, None, None, _ip(it), _ip(ex)))
+        return {"iters": int(it.sum(dtype=np.int64)), "exits": dict(zip(EXIT_NAMES, np.bincount(ex, minlength=3)[:3].tolist()))}
 
     def solve(self, pb: BatchProblem, out=None, want_gains=True):
         """cilqr_b200_solve_batch: host buffers in, host buffers out, copies included."""

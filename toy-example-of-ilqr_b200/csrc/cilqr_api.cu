@@ -90,6 +90,12 @@ struct Impl : Base {
     int* hist_iters = nullptr;
     int* hist_status = nullptr;
     int hist_cap = 0;
+    // synthetic workloads: centre-line tables and template descriptors on the device
+    double* syn_tab = nullptr;  // x | y | yaw | lon | nx | ny, each syn_cap samples
+    size_t syn_cap = 0;
+    int* syn_off = nullptr;
+    int syn_lanes = 0;
+    cilqr_synth_template_t* syn_tm = nullptr;  // [CILQR_B200_MAX_TEMPLATES]
     DevParams<T>* dP = nullptr;
     T* d_wp = nullptr;  // wx | wy | wyaw, each kMaxWaypoints? (sized on demand)
     size_t wp_cap = 0;
@@ -1178,6 +1184,81 @@ int do_simulate(Impl<T>* h, int B, const double* x0, const double* ref_velo, con
 }
 
 template <typename T>
+int do_synth_set_lanes(Impl<T>* h, int n_lanes, const int32_t* off, const double* x, const double* y, const double* yaw,
+                       const double* lon, const double* nx, const double* ny) {
+    CK(cudaSetDevice(h->device));
+    const size_t total = size_t(off[n_lanes]);
+    if (total > h->syn_cap || !h->syn_off) {
+        double* q = nullptr;
+        CK(cudaMalloc(&q, std::max<size_t>(total, 1) * 6 * sizeof(double)));
+        h->allocs.push_back(q);
+        h->syn_tab = q;
+        h->syn_cap = std::max<size_t>(total, 1);
+        int* o = nullptr;
+        CK(cudaMalloc(&o, 1024 * sizeof(int)));
+        h->allocs.push_back(o);
+        h->syn_off = o;
+    }
+    const double* src[6] = {x, y, yaw, lon, nx, ny};
+    for (int i = 0; i < 6; ++i)
+        CK(cudaMemcpyAsync(h->syn_tab + size_t(i) * h->syn_cap, src[i], total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->syn_off, off, size_t(n_lanes + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->syn_lanes = n_lanes;
+    return 0;
+}
+
+template <typename T>
+int do_synth_generate(Impl<T>* h, int B, uint64_t first_id, uint64_t seed, int n_tmpl, const cilqr_synth_template_t* tmpls,
+                      int keep_yaw) {
+    CK(cudaSetDevice(h->device));
+    if (!h->syn_tm) {
+        int rc = dalloc(h, &h->syn_tm, CILQR_B200_MAX_TEMPLATES);
+        if (rc) return rc;
+    }
+    for (int t = 0; t < n_tmpl; ++t) {
+        if (!h->tmpl_set[t] || h->wp_len[t] <= 0)
+            return fail(CILQR_ERR_INVALID, "synthetic template %d has no solver template / reference line (cilqr_b200_set_template)", t);
+        const cilqr_synth_template_t& st = tmpls[t];
+        if (st.n_obs < 0 || st.n_obs > h->max_obs || st.n_obs > CILQR_B200_SYNTH_MAX_OBS)
+            return fail(CILQR_ERR_INVALID, "synthetic template %d has %d obstacles (max_obs %d)", t, st.n_obs, h->max_obs);
+        bool lanes_ok = st.ego_kind == 0 || (st.ego_lane >= 0 && st.ego_lane < h->syn_lanes);
+        for (int j = 0; j < st.n_obs; ++j)
+            lanes_ok = lanes_ok && (st.obs[j].kind != 0 || (st.obs[j].lane >= 0 && st.obs[j].lane < h->syn_lanes));
+        if (!lanes_ok) return fail(CILQR_ERR_INVALID, "synthetic template %d refers to a lane table that was not set", t);
+    }
+    CK(cudaMemcpyAsync(h->syn_tm, tmpls, size_t(n_tmpl) * sizeof(cilqr_synth_template_t), cudaMemcpyHostToDevice, h->stream));
+    h->D.obs = h->obs_plain;
+    h->D.obs_len = h->N + 1;
+    h->D.obs_off = 0;
+    SynthLanes L{h->syn_tab, h->syn_tab + h->syn_cap, h->syn_tab + 2 * h->syn_cap, h->syn_tab + 3 * h->syn_cap,
+                 h->syn_tab + 4 * h->syn_cap, h->syn_tab + 5 * h->syn_cap, h->syn_off};
+    LAUNCH(h, k_synth_instances<T>, gs1(B), 128, h->D, B, (unsigned long long)first_id, (unsigned long long)seed, n_tmpl, h->syn_tm, L);
+    if (h->max_obs > 0) {
+        LAUNCH(h, k_synth_obstacles<T>, gs2(B, h->max_obs * (h->N + 1)), 128, h->D, h->obs_plain, B, (unsigned long long)first_id,
+               (unsigned long long)seed, n_tmpl, h->syn_tm, L);
+        if (!keep_yaw) LAUNCH(h, k_obs_sincos<T>, gs2(B, h->max_obs * (h->N + 1)), 128, h->obs_plain, B, size_t(h->Bs));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename T>
+int do_synth_download(Impl<T>* h, int B, double* x0, double* ref_velo, double* borders, int32_t* tmpl, int32_t* n_obs, double* obs) {
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = unpack_to_host(h, h->D.x0, x0, B, 4))) return rc;
+    if ((rc = unpack_to_host(h, h->D.ref_velo, ref_velo, B, 1))) return rc;
+    if ((rc = unpack_to_host(h, h->D.borders, borders, B, 2))) return rc;
+    if ((rc = download_ints(h, h->D.tmpl, tmpl, B))) return rc;
+    if ((rc = download_ints(h, h->D.n_obs, n_obs, B))) return rc;
+    if (h->max_obs > 0 && (rc = unpack_to_host(h, h->obs_plain, obs, B, h->max_obs * (h->N + 1) * 4))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename T>
 int do_set_template(Impl<T>* h, int t, const cilqr_params_t* params, const double* wx, const double* wy,
                     const double* wyaw, int M) {
     CK(cudaSetDevice(h->device));
@@ -1424,6 +1505,33 @@ int cilqr_b200_simulate(cilqr_handle_t* h, int B, const double* x0, const double
     if (B == 0) return 0;
     return DISPATCH(h, do_simulate, B, x0, ref_velo, borders, tmpl, n_obs, tracks, track_len, ticks, ego_out,
                     iters_out, status_out);
+}
+
+int cilqr_b200_synth_set_lanes(cilqr_handle_t* h, int n_lanes, const int32_t* lane_off, const double* x, const double* y,
+                               const double* yaw, const double* lon, const double* nx, const double* ny) {
+    if (!h) return fail(CILQR_ERR_INVALID, "handle is NULL");
+    if (n_lanes < 1 || n_lanes > 1023 || !lane_off || !x || !y || !yaw || !lon || !nx || !ny)
+        return fail(CILQR_ERR_INVALID, "need 1..1023 lane tables and all six arrays");
+    for (int l = 0; l < n_lanes; ++l)
+        if (lane_off[l + 1] - lane_off[l] < 2) return fail(CILQR_ERR_INVALID, "lane table %d holds fewer than 2 samples", l);
+    return DISPATCH(h, do_synth_set_lanes, n_lanes, lane_off, x, y, yaw, lon, nx, ny);
+}
+
+int cilqr_b200_synth_generate(cilqr_handle_t* h, int B, uint64_t first_id, uint64_t seed, int n_tmpl,
+                              const cilqr_synth_template_t* tmpls, int keep_yaw) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!tmpls || n_tmpl < 1 || n_tmpl > CILQR_B200_MAX_TEMPLATES) return fail(CILQR_ERR_INVALID, "need 1..%d template descriptors", CILQR_B200_MAX_TEMPLATES);
+    return DISPATCH(h, do_synth_generate, B, first_id, seed, n_tmpl, tmpls, keep_yaw);
+}
+
+int cilqr_b200_synth_download(cilqr_handle_t* h, int B, double* x0, double* ref_velo, double* borders, int32_t* tmpl,
+                              int32_t* n_obs, double* obs) {
+    int rc = check_batch(base(h), B);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    return DISPATCH(h, do_synth_download, B, x0, ref_velo, borders, tmpl, n_obs, obs);
 }
 
 int cilqr_b200_stage_times(cilqr_handle_t* h, double* ms_out, int32_t* launches_out) {

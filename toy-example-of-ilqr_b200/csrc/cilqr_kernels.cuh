@@ -35,6 +35,7 @@
 // from the last list length it has seen (an upper bound: lists only shrink).
 #pragma once
 
+#include "../../include/cilqr_b200.h"
 #include "cilqr_model.cuh"
 
 namespace cilqr {
@@ -2335,6 +2336,135 @@ __global__ void __launch_bounds__(128) k_swap_records(Dev<T> D, const int* __res
             *pa = vb;
             *pb = va;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic workloads generated in place: the device twin of generate_host() in
+// toy-example-of-ilqr_b200/scenario.py.  Every floating-point step is an explicit round-to-nearest add / multiply
+// (__dadd_rn, __dmul_rn: never contracted into an FMA), floor, min, max or fmod, in the order the numpy code
+// performs them, so the arrays agree with the host's bit for bit.
+// ---------------------------------------------------------------------------
+struct SynthLanes {
+    const double* x;
+    const double* y;
+    const double* yaw;
+    const double* lon;
+    const double* nx;
+    const double* ny;
+    const int* off;  // [n_lanes + 1]
+};
+
+__device__ __forceinline__ unsigned long long sy_mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// counter-based uniform [0, 1): splitmix64 finaliser (twice) of (seed, instance id, draw index)
+__device__ __forceinline__ double sy_u01(unsigned long long seed, unsigned long long inst, int draw) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (inst * 64ull + (unsigned long long)draw + 1ull);
+    z = sy_mix64(sy_mix64(z));
+    return double(z >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double sy_uniform(unsigned long long seed, unsigned long long inst, int draw, double lo, double hi) {
+    return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), sy_u01(seed, inst, draw)));
+}
+// pose on a lane table at arc length s: linear interpolation of the line's own samples
+__device__ __forceinline__ int sy_lane_pose(const SynthLanes& L, int lane, double s, double* px, double* py, double* pyaw) {
+    const int o = L.off[lane], M = L.off[lane + 1] - o;
+    const double* lon = L.lon + o;
+    long long i = (long long)floor(__dmul_rn(__dsub_rn(s, lon[0]), 10.0));
+    i = i < 0 ? 0 : (i > M - 2 ? M - 2 : i);
+    const double f = __dmul_rn(__dsub_rn(s, lon[i]), 10.0);
+    const double *x = L.x + o, *y = L.y + o, *yaw = L.yaw + o;
+    *px = __dadd_rn(x[i], __dmul_rn(f, __dsub_rn(x[i + 1], x[i])));
+    *py = __dadd_rn(y[i], __dmul_rn(f, __dsub_rn(y[i + 1], y[i])));
+    *pyaw = __dadd_rn(yaw[i], __dmul_rn(f, __dsub_rn(yaw[i + 1], yaw[i])));
+    return int(i);
+}
+__device__ __forceinline__ void sy_ego(const cilqr_synth_template_t& st, const SynthLanes& L, unsigned long long seed,
+                                       unsigned long long id, double x0[4], double* ref_velo) {
+    if (st.ego_kind == 0) {
+        x0[0] = sy_uniform(seed, id, 0, -5.0, 5.0);
+        x0[1] = sy_uniform(seed, id, 1, -0.6, 0.6);
+        x0[2] = sy_uniform(seed, id, 2, 5.0, 10.0);
+        x0[3] = sy_uniform(seed, id, 3, -0.05, 0.05);
+        *ref_velo = sy_uniform(seed, id, 4, 6.0, 10.0);
+    } else {
+        const int o = L.off[st.ego_lane], M = L.off[st.ego_lane + 1] - o;
+        const double s = fmin(fmax(__dadd_rn(st.ego_s, sy_uniform(seed, id, 0, -5.0, 5.0)), L.lon[o]), L.lon[o + M - 1]);
+        const double dl = sy_uniform(seed, id, 1, -0.6, 0.6);
+        double px, py, pyaw;
+        const int i = sy_lane_pose(L, st.ego_lane, s, &px, &py, &pyaw);
+        x0[0] = __dadd_rn(px, __dmul_rn(dl, L.nx[o + i]));
+        x0[1] = __dadd_rn(py, __dmul_rn(dl, L.ny[o + i]));
+        x0[2] = fmax(__dadd_rn(st.ego_v, sy_uniform(seed, id, 2, -2.0, 2.0)), 0.5);
+        x0[3] = __dadd_rn(pyaw, sy_uniform(seed, id, 3, -0.05, 0.05));
+        *ref_velo = __dadd_rn(st.target_velocity, sy_uniform(seed, id, 4, -2.0, 2.0));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_synth_instances(Dev<T> D, int B, unsigned long long first_id, unsigned long long seed,
+                                                         int n_tmpl, const cilqr_synth_template_t* __restrict__ tm, SynthLanes L) {
+    const size_t Bs = D.Bs;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const unsigned long long id = first_id + (unsigned long long)b;
+        const int ti = int(id % (unsigned long long)n_tmpl);
+        const cilqr_synth_template_t& st = tm[ti];
+        double x0[4], rv;
+        sy_ego(st, L, seed, id, x0, &rv);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) D.x0[size_t(c) * Bs + b] = T(x0[c]);
+        D.ref_velo[b] = T(rv);
+        D.borders[b] = T(st.borders[0]);
+        D.borders[Bs + b] = T(st.borders[1]);
+        D.tmpl[b] = ti;
+        D.n_obs[b] = st.n_obs;
+    }
+}
+
+// one thread per (instance, obstacle j, tick k): grid.y = max_obs * (N + 1) rows
+template <typename T>
+__global__ void __launch_bounds__(128) k_synth_obstacles(Dev<T> D, T* obs, int B, unsigned long long first_id,
+                                                         unsigned long long seed, int n_tmpl,
+                                                         const cilqr_synth_template_t* __restrict__ tm, SynthLanes L) {
+    const size_t Bs = D.Bs;
+    const int row = blockIdx.y, j = row / (D.N + 1), k = row % (D.N + 1);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const unsigned long long id = first_id + (unsigned long long)b;
+        const cilqr_synth_template_t& st = tm[int(id % (unsigned long long)n_tmpl)];
+        double ox = 0, oy = 0, oyaw = 0;
+        if (j < st.n_obs) {
+            const cilqr_synth_obstacle_t& ob = st.obs[j];
+            const double t = __dmul_rn(double(k), st.dt);
+            if (ob.kind == 0) {
+                const int o = L.off[ob.lane], M = L.off[ob.lane + 1] - o;
+                const double lon0 = L.lon[o], lon1 = L.lon[o + M - 1];
+                const double ds = sy_uniform(seed, id, ob.draw, -8.0, 8.0);
+                const double v = fmax(__dadd_rn(ob.speed, sy_uniform(seed, id, ob.draw + 1, -1.0, 1.0)), 0.5);
+                const double s0 = __dadd_rn(ob.start_s, ds), tv = __dmul_rn(t, v);
+                const double s = ob.oncoming ? fmin(fmax(__dsub_rn(s0, tv), lon0), lon1) : fmax(fmin(__dadd_rn(s0, tv), lon1), lon0);
+                sy_lane_pose(L, ob.lane, s, &ox, &oy, &oyaw);
+                if (ob.oncoming) oyaw = fmod(__dadd_rn(oyaw, 3.141592653589793), 6.283185307179586);
+            } else {
+                ox = sy_uniform(seed, id, ob.draw, ob.x_lo, ob.x_hi);
+                if (ob.rel_to_ego) {
+                    double x0[4], rv;
+                    sy_ego(st, L, seed, id, x0, &rv);
+                    ox = __dadd_rn(x0[0], ox);
+                }
+                const double v = sy_uniform(seed, id, ob.draw_v, ob.v_lo, ob.v_hi);
+                oy = (ob.two_lanes && !(sy_u01(seed, id, ob.draw_lane) < 0.5)) ? ob.y1 : ob.y0;
+                ox = __dadd_rn(ox, __dmul_rn(ob.direction, __dmul_rn(t, v)));
+                oyaw = ob.yaw;
+            }
+        }
+        T* p = obs + (size_t(j) * (D.N + 1) + k) * 4 * Bs + b;
+        p[0] = T(ox);
+        p[Bs] = T(oy);
+        p[2 * Bs] = T(oyaw);
+        p[3 * Bs] = T(0);
     }
 }
 

@@ -325,106 +325,198 @@ def get_scenario(name):
     return _SCN_CACHE[name]
 
 
-def _jittered_tracks(scn, ids, N, seed, draw0, extra=()):
-    """Obstacle tracks of template `scn` for instances `ids`: every template obstacle shifted by
-    ds ~ U(-8, 8) m along its lane with speed v + U(-1, 1) clamped >= 0.5."""
-    t = np.arange(N + 1, dtype=np.float64) * scn.dt
-    n = len(scn.ic) - 1
-    obs = np.zeros((len(ids), n + len(extra), N + 1, 3))
-    for j in range(n):
-        ds = uniform(seed, ids, draw0 + 2 * j, -8.0, 8.0)
-        v = np.maximum(scn.ic[j + 1][2] + uniform(seed, ids, draw0 + 2 * j + 1, -1.0, 1.0), 0.5)
-        obs[:, j] = scn.track(j + 1, t[None, :], ds0=ds[:, None], speed=v[:, None])
-    return obs
+# ---------------------------------------------------------------------------
+# synthetic batches: a small descriptor per scenario template, expanded into problem arrays
+# either here (numpy) or in place on the device (cilqr_b200_synth_generate) — the same numbers bit for bit:
+# every floating-point step below is a single IEEE add / multiply / min / max / floor / fmod, and the device
+# kernel performs the same steps in the same order with contraction off.
+# ---------------------------------------------------------------------------
+@dataclass
+class LaneTable:
+    """A centre line as sampled by ReferenceLine (every 0.1 m): positions, yaw, arc length of each sample, and the
+    left normal (-sin yaw, cos yaw) of each sample.  Poses between samples are linear interpolations."""
+    x: np.ndarray
+    y: np.ndarray
+    yaw: np.ndarray
+    lon: np.ndarray
+    nx: np.ndarray
+    ny: np.ndarray
 
 
-def synthetic_batch(config, B, N=None, seed=DEFAULT_SEED, first_id=0):
-    """Synthetic batches of SURVEY §8d.  `first_id` lets a rank generate its own slice
-    [first_id, first_id + B) of a larger batch."""
-    ids = np.arange(first_id, first_id + B, dtype=np.uint64)
-    if config == "C1":
-        N = 50 if N is None else N
-        scn = get_scenario("two_straight")
-        tds = [template_data(scn)]
-        x0 = np.stack([uniform(seed, ids, 0, -5.0, 5.0), uniform(seed, ids, 1, -0.6, 0.6),
-                       uniform(seed, ids, 2, 5.0, 10.0), uniform(seed, ids, 3, -0.05, 0.05)], axis=1)
-        ref_velo = uniform(seed, ids, 4, 6.0, 10.0)
-        obs = _jittered_tracks(scn, ids, N, seed, 8)
-        tmpl = np.zeros(B, np.int32)
-        n_obs = np.full(B, obs.shape[1], np.int32)
-        borders = np.tile(scn.borders, (B, 1))
-    elif config == "C2":
-        N = 100 if N is None else N
-        scn = get_scenario("two_straight")
-        tds = [template_data(scn)]
-        x0 = np.stack([uniform(seed, ids, 0, -5.0, 5.0), uniform(seed, ids, 1, -0.6, 0.6),
-                       uniform(seed, ids, 2, 5.0, 10.0), uniform(seed, ids, 3, -0.05, 0.05)], axis=1)
-        ref_velo = uniform(seed, ids, 4, 6.0, 10.0)
-        t = np.arange(N + 1, dtype=np.float64) * scn.dt
-        obs = np.zeros((B, 3, N + 1, 3))
-        for j in range(3):
-            ox = x0[:, 0] + uniform(seed, ids, 8 + 3 * j, 10.0, 90.0)
-            lane = np.where(u01(seed, ids, 9 + 3 * j) < 0.5, 0.0, 3.6)
-            v = uniform(seed, ids, 10 + 3 * j, 0.0, 7.0)
-            obs[:, j, :, 0] = ox[:, None] + v[:, None] * t[None, :]
-            obs[:, j, :, 1] = lane[:, None]
-        tmpl = np.zeros(B, np.int32)
-        n_obs = np.full(B, 3, np.int32)
-        borders = np.tile(scn.borders, (B, 1))
-    elif config == "C3":
+def lane_table(cl):
+    return LaneTable(cl.x.copy(), cl.y.copy(), cl.yaw.copy(), cl.longitude.copy(), -np.sin(cl.yaw), np.cos(cl.yaw))
+
+
+def lane_pose(tb, s):
+    """(x, y, yaw, sample index) at arc length s: sample i = floor((s - lon[0]) * 10) clamped to [0, M-2],
+    f = (s - lon[i]) * 10, value = v[i] + f * (v[i+1] - v[i])."""
+    s = np.asarray(s, dtype=np.float64)
+    i = np.clip(np.floor((s - tb.lon[0]) * 10.0).astype(np.int64), 0, len(tb.lon) - 2)
+    f = (s - tb.lon[i]) * 10.0
+    return (tb.x[i] + f * (tb.x[i + 1] - tb.x[i]), tb.y[i] + f * (tb.y[i + 1] - tb.y[i]),
+            tb.yaw[i] + f * (tb.yaw[i + 1] - tb.yaw[i]), i)
+
+
+@dataclass
+class SynthObstacle:
+    kind: int = 0          # 0: follows a lane table; 1: straight line at constant y
+    # kind 0: starts at start_s + U(draw; -8, 8) on `lane`, speed max(speed + U(draw + 1; -1, 1), 0.5), drives
+    # towards decreasing s with yaw + pi when `oncoming` (src/motion_planning.cpp:149-158)
+    lane: int = 0
+    oncoming: int = 0
+    draw: int = 0
+    start_s: float = 0.0
+    speed: float = 0.0
+    # kind 1: x = [ego x0 +] U(draw; x_lo, x_hi) + direction * v t, v = U(draw_v; v_lo, v_hi),
+    # y = y0, or y1 when two_lanes and u01(draw_lane) >= 0.5; constant yaw
+    x_lo: float = 0.0
+    x_hi: float = 0.0
+    v_lo: float = 0.0
+    v_hi: float = 0.0
+    y0: float = 0.0
+    y1: float = 0.0
+    yaw: float = 0.0
+    direction: float = 1.0
+    rel_to_ego: int = 0
+    two_lanes: int = 0
+    draw_lane: int = 0
+    draw_v: int = 0
+
+
+@dataclass
+class SynthTemplate:
+    ego_kind: int = 0      # 0: x0 = (U0(-5,5), U1(-.6,.6), U2(5,10), U3(-.05,.05)), ref_velo = U4(6,10)
+    #                        1: lane frame: s = ego_s + U0(-5,5) on ego_lane, lateral U1(-.6,.6) along the sample's
+    #                           normal, v = max(ego_v + U2(-2,2), 0.5), yaw = lane yaw + U3(-.05,.05),
+    #                           ref_velo = target_velocity + U4(-2,2)
+    ego_lane: int = 0
+    ego_s: float = 0.0
+    ego_v: float = 0.0
+    target_velocity: float = 0.0
+    borders: tuple = (0.0, 0.0)
+    obstacles: list = field(default_factory=list)
+
+
+@dataclass
+class SynthSpec:
+    name: str
+    N: int
+    templates: list        # TemplateData per scenario template (instance i uses template i % len(templates))
+    synth: list            # SynthTemplate per scenario template
+    lanes: list            # LaneTable list the descriptors index into
+
+    @property
+    def max_obs(self):
+        return max(len(t.obstacles) for t in self.synth)
+
+
+def _lane_obstacles(scn, lane0, draw0):
+    out = []
+    for j in range(len(scn.ic) - 1):
+        veh = j + 1
+        out.append(SynthObstacle(kind=0, lane=lane0 + scn.lane_of[veh], oncoming=int(scn.ic[veh][3] > math.pi / 2),
+                                 draw=draw0 + 2 * j, start_s=float(scn.start_s[veh]), speed=float(scn.ic[veh][2])))
+    return out
+
+
+def synth_spec(config, N=None):
+    """Descriptor of BASELINE config C1..C4."""
+    if config in ("C1", "C2", "C4"):
+        scn = get_scenario("two_borrow" if config == "C4" else "two_straight")
+        lanes = [lane_table(cl) for cl in scn.center_lines]
+        st = SynthTemplate(ego_kind=0, target_velocity=float(scn.target_velocity), borders=tuple(scn.borders))
+        if config == "C1":
+            N = 50 if N is None else N
+            st.obstacles = _lane_obstacles(scn, 0, 8)
+        elif config == "C2":
+            N = 100 if N is None else N
+            st.obstacles = [SynthObstacle(kind=1, draw=8 + 3 * j, draw_lane=9 + 3 * j, draw_v=10 + 3 * j, x_lo=10.0,
+                                          x_hi=90.0, v_lo=0.0, v_hi=7.0, y0=0.0, y1=3.6, two_lanes=1, rel_to_ego=1)
+                            for j in range(3)]
+        else:
+            N = 200 if N is None else N
+            st.obstacles = _lane_obstacles(scn, 0, 8) + [
+                SynthObstacle(kind=1, draw=40, draw_v=41, x_lo=60.0, x_hi=160.0, v_lo=2.0, v_hi=8.0, y0=3.6,
+                              yaw=math.fmod(0.0 + math.pi, 2 * math.pi), direction=-1.0)]
+        return SynthSpec(config, N, [template_data(scn)], [st], lanes)
+    if config == "C3":
         N = 50 if N is None else N
         scns = [get_scenario(n) for n in T.TEMPLATE_ORDER]
         tds = [template_data(s) for s in scns]
-        for td in tds:  # first solve only: warm start off for all (SURVEY §8d C3)
+        for td in tds:  # first solve only: warm start off for all (SURVEY 8d C3)
             td.params = dict(td.params, use_last_solution=0)
-        max_obs = max(len(s.ic) - 1 for s in scns)
-        tmpl = (ids % np.uint64(4)).astype(np.int32)
-        x0 = np.zeros((B, 4))
-        ref_velo = np.zeros(B)
-        borders = np.zeros((B, 2))
-        n_obs = np.zeros(B, np.int32)
-        obs = np.zeros((B, max_obs, N + 1, 3))
-        for ti, s in enumerate(scns):
-            sel = np.nonzero(tmpl == ti)[0]
-            if len(sel) == 0:
-                continue
-            sid = ids[sel]
-            # ego jitter as C1, applied in the lane frame of the template's initial condition
-            ds = uniform(seed, sid, 0, -5.0, 5.0)
+        lanes, synth = [], []
+        for s in scns:
+            lane0 = len(lanes)
+            lanes += [lane_table(cl) for cl in s.center_lines]
+            synth.append(SynthTemplate(ego_kind=1, ego_lane=lane0 + s.lane_of[0], ego_s=float(s.start_s[0]),
+                                       ego_v=float(s.ic[0][2]), target_velocity=float(s.target_velocity),
+                                       borders=tuple(s.borders), obstacles=_lane_obstacles(s, lane0, 8)))
+        return SynthSpec(config, N, tds, synth, lanes)
+    raise ValueError("unknown synthetic config %r" % (config,))
+
+
+def generate_host(spec, B, seed=DEFAULT_SEED, first_id=0):
+    """Expands a SynthSpec into the problem arrays of instances [first_id, first_id + B) with numpy."""
+    ids = np.arange(first_id, first_id + B, dtype=np.uint64)
+    N, nt, max_obs = spec.N, len(spec.synth), spec.max_obs
+    tmpl = (ids % np.uint64(nt)).astype(np.int32)
+    x0, ref_velo, borders = np.zeros((B, 4)), np.zeros(B), np.zeros((B, 2))
+    n_obs = np.zeros(B, np.int32)
+    obs = np.zeros((B, max_obs, N + 1, 3))
+    for ti, st in enumerate(spec.synth):
+        sel = np.nonzero(tmpl == ti)[0]
+        if len(sel) == 0:
+            continue
+        sid = ids[sel]
+        dt = spec.templates[ti].params["dt"]
+        t = np.arange(N + 1, dtype=np.float64) * dt
+        if st.ego_kind == 0:
+            ex0 = np.stack([uniform(seed, sid, 0, -5.0, 5.0), uniform(seed, sid, 1, -0.6, 0.6),
+                            uniform(seed, sid, 2, 5.0, 10.0), uniform(seed, sid, 3, -0.05, 0.05)], axis=1)
+            rv = uniform(seed, sid, 4, 6.0, 10.0)
+        else:
+            tb = spec.lanes[st.ego_lane]
+            s_ego = np.minimum(np.maximum(st.ego_s + uniform(seed, sid, 0, -5.0, 5.0), tb.lon[0]), tb.lon[-1])
             dl = uniform(seed, sid, 1, -0.6, 0.6)
-            cl = s.center_lines[s.lane_of[0]]
-            s_ego = np.clip(s.start_s[0] + ds, cl.longitude[0], cl.longitude[-1])
-            ex, ey, eyaw = cl.calc_position(s_ego)
-            x0[sel, 0] = ex - dl * np.sin(eyaw)
-            x0[sel, 1] = ey + dl * np.cos(eyaw)
-            x0[sel, 2] = np.maximum(s.ic[0][2] + uniform(seed, sid, 2, -2.0, 2.0), 0.5)
-            x0[sel, 3] = eyaw + uniform(seed, sid, 3, -0.05, 0.05)
-            ref_velo[sel] = s.target_velocity + uniform(seed, sid, 4, -2.0, 2.0)
-            borders[sel] = s.borders
-            o = _jittered_tracks(s, sid, N, seed, 8)
-            obs[sel, : o.shape[1]] = o
-            n_obs[sel] = o.shape[1]
-    elif config == "C4":
-        N = 200 if N is None else N
-        scn = get_scenario("two_borrow")
-        tds = [template_data(scn)]
-        x0 = np.stack([uniform(seed, ids, 0, -5.0, 5.0), uniform(seed, ids, 1, -0.6, 0.6),
-                       uniform(seed, ids, 2, 5.0, 10.0), uniform(seed, ids, 3, -0.05, 0.05)], axis=1)
-        ref_velo = uniform(seed, ids, 4, 6.0, 10.0)
-        base = _jittered_tracks(scn, ids, N, seed, 8)
-        t = np.arange(N + 1, dtype=np.float64) * scn.dt
-        extra = np.zeros((B, 1, N + 1, 3))
-        ox = uniform(seed, ids, 40, 60.0, 160.0)
-        v = uniform(seed, ids, 41, 2.0, 8.0)
-        extra[:, 0, :, 0] = ox[:, None] - v[:, None] * t[None, :]
-        extra[:, 0, :, 1] = 3.6
-        extra[:, 0, :, 2] = math.fmod(0.0 + math.pi, 2 * math.pi)
-        obs = np.concatenate([base, extra], axis=1)
-        tmpl = np.zeros(B, np.int32)
-        n_obs = np.full(B, obs.shape[1], np.int32)
-        borders = np.tile(scn.borders, (B, 1))
-    else:
-        raise ValueError("unknown synthetic config %r" % (config,))
-    return BatchProblem(tds, N, np.ascontiguousarray(x0), np.ascontiguousarray(ref_velo),
-                        np.ascontiguousarray(borders), tmpl, n_obs, np.ascontiguousarray(obs), name=config,
+            px, py, pyaw, i = lane_pose(tb, s_ego)
+            ex0 = np.stack([px + dl * tb.nx[i], py + dl * tb.ny[i],
+                            np.maximum(st.ego_v + uniform(seed, sid, 2, -2.0, 2.0), 0.5),
+                            pyaw + uniform(seed, sid, 3, -0.05, 0.05)], axis=1)
+            rv = st.target_velocity + uniform(seed, sid, 4, -2.0, 2.0)
+        x0[sel], ref_velo[sel], borders[sel] = ex0, rv, np.asarray(st.borders)
+        n_obs[sel] = len(st.obstacles)
+        for j, ob in enumerate(st.obstacles):
+            if ob.kind == 0:
+                tb = spec.lanes[ob.lane]
+                ds = uniform(seed, sid, ob.draw, -8.0, 8.0)
+                v = np.maximum(ob.speed + uniform(seed, sid, ob.draw + 1, -1.0, 1.0), 0.5)
+                s0 = (ob.start_s + ds)[:, None]
+                tv = t[None, :] * v[:, None]
+                if ob.oncoming:
+                    sj = np.minimum(np.maximum(s0 - tv, tb.lon[0]), tb.lon[-1])
+                else:
+                    sj = np.maximum(np.minimum(s0 + tv, tb.lon[-1]), tb.lon[0])
+                px, py, pyaw, _ = lane_pose(tb, sj)
+                if ob.oncoming:
+                    pyaw = np.fmod(pyaw + math.pi, 2 * math.pi)
+                obs[sel, j, :, 0], obs[sel, j, :, 1], obs[sel, j, :, 2] = px, py, pyaw
+            else:
+                ox = uniform(seed, sid, ob.draw, ob.x_lo, ob.x_hi)
+                if ob.rel_to_ego:
+                    ox = ex0[:, 0] + ox
+                v = uniform(seed, sid, ob.draw_v, ob.v_lo, ob.v_hi)
+                y = np.full(len(sel), ob.y0)
+                if ob.two_lanes:
+                    y = np.where(u01(seed, sid, ob.draw_lane) < 0.5, ob.y0, ob.y1)
+                obs[sel, j, :, 0] = ox[:, None] + ob.direction * (t[None, :] * v[:, None])
+                obs[sel, j, :, 1] = y[:, None]
+                obs[sel, j, :, 2] = ob.yaw
+    return BatchProblem(spec.templates, N, x0, ref_velo, borders, tmpl, n_obs, obs, name=spec.name,
                         meta={"seed": seed, "first_id": first_id})
+
+
+def synthetic_batch(config, B, N=None, seed=DEFAULT_SEED, first_id=0):
+    """Synthetic batches of SURVEY 8d, generated on the host.  `first_id` lets a rank generate its own slice
+    [first_id, first_id + B) of a larger batch.  (BatchSolver.generate does the same on the device.)"""
+    return generate_host(synth_spec(config, N), B, seed, first_id)
