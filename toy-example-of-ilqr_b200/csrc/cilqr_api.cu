@@ -62,6 +62,8 @@ struct Base {
     int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
     int wide_step = 1; // bandwidth-bound rounds widen a line search step by step (2, 4, 8, 6 alphas) instead of all at once
     int repack = 1;    // survivors moved into a dense prefix whenever they are down to half of the slots in use
+    int tiles = 1;     // latency-bound batches of up to 148 tiles: the whole loop inside one CTA per tile (k_solve_tiles)
+    bool tiles_attr_set = false;
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
@@ -683,6 +685,30 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // the latency-regime kernels for its stragglers).
     int launched = 0;
     int level = 0, repack_bound[kRepackLevels], repack_off[kRepackLevels + 1] = {0};
+    // Latency-bound batches (and the stragglers of a large one, once they fit): the rest of the solve runs as one
+    // persistent CTA per tile of 32 instances (k_solve_tiles) instead of rounds of launches.
+    const bool tiles_ok = h->tiles && !kParity && !h->any_alm && N + 1 <= kPipeMaxSteps && h->D.Vs / kTileMaxTiles >= 32;
+    bool finished_in_tiles = false;
+    auto run_tiles = [&](int Bt) -> int {
+        const int n_tiles = (Bt + 31) / 32;
+        const int tile_slots = int(std::min<long long>(kTileGroups * kPipeTrials * 2, (long long)h->D.Vs / n_tiles));
+        const size_t smem = tile_smem_bytes<T>(N);
+        if (!h->tiles_attr_set) {
+            CK(cudaFuncSetAttribute(k_solve_tiles<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tile_smem_bytes<T>(kPipeMaxSteps - 1))));
+            h->tiles_attr_set = true;
+        }
+        h->D.wide_step = 0;
+        mark_stage(h, 1);
+        k_solve_tiles<T><<<n_tiles, kTileThreads, smem, h->stream>>>(h->D, Bt, tile_slots, h->max_rounds, launched);
+        h->launches++;
+        mark_stage(h, -1);
+        finished_in_tiles = true;
+        return 0;
+    };
+    if (tiles_ok && B <= kTileMaxTiles * 32) {
+        int rc = run_tiles(B);
+        if (rc) return rc;
+    }
     // the spin below must not outlive a device fault or a stalled kernel: every kSpinCheck polls the stream is
     // queried (a sticky error, or an idle stream whose progress words still say "rounds outstanding", ends the
     // solve with CILQR_ERR_CUDA), and a round that makes no progress for kStallSeconds is reported as a stall
@@ -691,7 +717,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     unsigned spins = 0;
     int last_done = -1;
     auto last_progress = std::chrono::steady_clock::now();
-    while (launched < h->max_rounds) {
+    while (!finished_in_tiles && launched < h->max_rounds) {
         const unsigned long long w = progress[0];
         const int done = int(w >> 32);
         if (done > 0 && unsigned(w) == 0u) break;
@@ -723,6 +749,22 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             repack_off[level + 1] = repack_off[level] + n_bound;  // <= B / 2 pairs per level: < Bs in total
             ++level;
             B = n_bound;
+        }
+        if (tiles_ok && n_bound <= kTileMaxTiles * 32 - 640 && level < kRepackLevels && h->repack) {
+            // the stragglers fit one tile per SM: move them into a dense prefix (unless they are one already) and
+            // let each tile finish on its own
+            if (n_bound < B) {
+                LAUNCH(h, k_plan_repack<T>, dim3(1), kPlanThreads, h->D, launched & 1, level, h->D.swap_src + repack_off[level],
+                       h->D.swap_dst + repack_off[level]);
+                swap_instances(h, level, repack_off[level], n_bound);
+                repack_bound[level] = n_bound;
+                repack_off[level + 1] = repack_off[level] + n_bound;
+                ++level;
+                B = n_bound;
+            }
+            int rc = run_tiles(B);
+            if (rc) return rc;
+            break;
         }
         const int trial_bound = int(std::min<long long>(h->D.Vs, (long long)n_bound * kNumAlphas));
         const bool lat = n_bound <= h->prefetch_below;
@@ -777,8 +819,8 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         mark_stage(h, -1);
         ++launched;
     }
-    // commit a step accepted in the last round
-    LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 1, launched & 1);
+    // commit a step accepted in the last round (the tile kernel has done that itself)
+    if (!finished_in_tiles) LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 1, launched & 1);
     // every instance back into its own slot
     while (level > 0) {
         --level;
@@ -1329,6 +1371,9 @@ int do_set_option(Impl<T>* h, int option, int value) {
             return 0;
         case CILQR_OPT_WIDE_STEP:
             h->wide_step = value ? 1 : 0;
+            return 0;
+        case CILQR_OPT_TILE_KERNEL:
+            h->tiles = value ? 1 : 0;
             return 0;
         case CILQR_OPT_REPACK:
             h->repack = value < 0 ? 0 : value;  // > 1: smallest batch that is still repacked (development)

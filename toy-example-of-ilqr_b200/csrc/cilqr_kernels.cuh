@@ -616,6 +616,306 @@ __device__ __forceinline__ void add_constraint_ref(bool alm, T c, const T* c_dot
 //     then differentiates only where the record is stale — the reference's
 //     cache rule for rejected steps (cpp:469-474).
 // ---------------------------------------------------------------------------
+// The work of one thread of the derivative stage: half `part` (0 = state terms l_x, l_xx; 1 = control terms and
+// model Jacobians l_u, l_uu, A, B) of step k of instance b.  masked != 0 (inside the solver): first commit an
+// accepted trial, then differentiate only where the record is stale.
+template <typename T, bool kAlm>
+__device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int part, int masked) {
+    const int N = D.N;
+    const size_t Bs = D.Bs, Vs = D.Vs;
+
+    T x[4], ua = 0, us = 0;
+    int ri = 0;
+    const int src = masked ? D.commit_src[b] : -1;
+    if (src >= 0) {
+        // the accepted trial becomes the current trajectory; part 1 reads the state from the
+        // trial slot too, so it never races with part 0's copy
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[c] = D.Xt[at(Vs, k, c, 4, src)];
+        if (part == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) D.X[at(Bs, k, c, 4, b)] = x[c];
+            ri = D.ridx_t[size_t(k) * Vs + src];
+            D.ridx[size_t(k) * Bs + b] = ri;
+            for (int p = 0; p < kScPlanes; ++p)
+                D.sc[(size_t(p) * (N + 1) + k) * Bs + b] = D.sc_t[(size_t(p) * (N + 1) + k) * Vs + src];
+        } else if (k < N) {
+            ua = D.Ut[at(Vs, k, 0, 2, src)];
+            us = D.Ut[at(Vs, k, 1, 2, src)];
+            D.U[at(Bs, k, 0, 2, b)] = ua;
+            D.U[at(Bs, k, 1, 2, b)] = us;
+        }
+    }
+    if (masked && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) return;
+    if (src < 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[c] = D.X[at(Bs, k, c, 4, b)];
+        if (part == 0) {
+            ri = D.ridx[size_t(k) * Bs + b];
+        } else if (k < N) {
+            ua = D.U[at(Bs, k, 0, 2, b)];
+            us = D.U[at(Bs, k, 1, 2, b)];
+        }
+    }
+    const DevParams<T>& P = D.P[D.tmpl[b]];
+    const bool alm = kAlm && P.solve_type == 1;
+    const T rho = alm ? D.rho[b] : T(0);
+    T* rec = rec_at(D, k, b);
+    if (part == 0) {
+    const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
+    const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
+#ifdef CILQR_PARITY
+    // the reference's accumulation, literally (cpp:497-689): velocity up / lo, border up / lo into the
+    // row, then per obstacle (front + rear) summed first and added to the row, the prime part last
+    T gx[4] = {0, 0, 0, 0};
+    T Hx[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (k >= 1) {
+        const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+        T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+        T d_sign, hyp;
+        const T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
+        const T cc4[4] = {x[2] - P.velo_max, P.velo_min - x[2], cur_d - (D.borders[b] - P.width / 2),
+                          (D.borders[Bs + b] + P.width / 2) - cur_d};
+        T cx[4][4] = {{0, 0, 1, 0}, {0, 0, -1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+        cx[2][0] = (x[0] - rx) / hyp;
+        cx[2][1] = (x[1] - ry) / hyp;
+        if (d_sign < 0)
+            for (int r = 0; r < 4; ++r) cx[2][r] = -1 * cx[2][r];
+        for (int r = 0; r < 4; ++r) cx[3][r] = -1 * cx[2][r];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            add_constraint_ref<T, 4>(alm, cc4[m], cx[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4 + m) * Bs] : T(0), gx, Hx);
+        if (alm)
+            for (int m = 0; m < 4; ++m)
+                mun[size_t(4 + m) * Bs] = std_min(std_max(mu[size_t(4 + m) * Bs] + rho * cc4[m], T(0)), P.max_mu);
+        const int no = D.n_obs[b];
+        if (no > 0) {
+            const EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
+            for (int j = 0; j < no; ++j) {
+                const T* ob = D.obs + (size_t(j) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
+                const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
+                T gfx, gfy, grx, gry;
+                const T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
+                const T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
+                // 4x2 centre Jacobians times the point gradients (utils.cpp:363-385, cpp:728-736)
+                const T gf[4] = {T(1) * gfx + T(0) * gfy, T(0) * gfx + T(1) * gfy, T(0) * gfx + T(0) * gfy,
+                                 e.jf0 * gfx + e.jf1 * gfy};
+                const T gr[4] = {T(1) * grx + T(0) * gry, T(0) * grx + T(1) * gry, T(0) * grx + T(0) * gry,
+                                 e.jr0 * grx + e.jr1 * gry};
+                T g2[4] = {0, 0, 0, 0};
+                T H2[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                add_constraint_ref<T, 4>(alm, cf, gf, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(8 + 2 * j) * Bs] : T(0), g2, H2);
+                add_constraint_ref<T, 4>(alm, cr, gr, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(9 + 2 * j) * Bs] : T(0), g2, H2);
+                for (int r = 0; r < 4; ++r) gx[r] += g2[r];
+                for (int r = 0; r < 16; ++r) Hx[r] += H2[r];
+                if (alm) {
+                    mun[size_t(8 + 2 * j) * Bs] = std_min(std_max(mu[size_t(8 + 2 * j) * Bs] + rho * cf, T(0)), P.max_mu);
+                    mun[size_t(9 + 2 * j) * Bs] = std_min(std_max(mu[size_t(9 + 2 * j) * Bs] + rho * cr, T(0)), P.max_mu);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Hx[c * 4 + c] = 2 * P.Q[c] + Hx[c * 4 + c];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) rec[(kRecLxx + c) * kRecFS] = Hx[c];
+#else
+    T gx[4] = {0, 0, 0, 0};
+    T H[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
+    if (k >= 1) {
+        const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+        T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
+        // velocity bounds: c_dot = (0,0,+-1,0)
+        T cv[2] = {x[2] - P.velo_max, P.velo_min - x[2]};
+        // zV / zB / zO: what the zero entries of a constraint's c_dot contribute in the reference, which forms
+        // every product (cpp:696-698): 0 for a finite barrier weight, NaN for one that overflowed (0 * inf).
+        // Summed per constraint family and added below to the entries that family does not otherwise touch,
+        // so that an overflowing barrier poisons the same entries as in the reference.
+        T zV = 0, zB = 0, zO = 0;
+        T g, h;
+        constraint_weights(alm, cv[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4) * Bs] : T(0), &g, &h);
+        gx[2] += g;
+        H[7] += h;
+        zV += g + h;
+        constraint_weights(alm, cv[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(5) * Bs] : T(0), &g, &h);
+        gx[2] += -g;
+        H[7] += h;
+        zV += g + h;
+        // road borders: c_dot = +-(px-rx, py-ry)/hypot, flipped when d_sign < 0 (cpp:527-533)
+        T d_sign, hyp;
+        T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
+        T cp[2] = {cur_d - (D.borders[b] - P.width / 2), (D.borders[Bs + b] + P.width / 2) - cur_d};
+        T n0 = (x[0] - rx) / hyp, n1 = (x[1] - ry) / hyp;
+        if (d_sign < 0) {
+            n0 = -n0;
+            n1 = -n1;
+        }
+        constraint_weights(alm, cp[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(6) * Bs] : T(0), &g, &h);
+        gx[0] += g * n0;
+        gx[1] += g * n1;
+        H[0] += h * (n0 * n0);
+        H[1] += h * (n0 * n1);
+        H[4] += h * (n1 * n1);
+        zB += g + h;
+        constraint_weights(alm, cp[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(7) * Bs] : T(0), &g, &h);
+        gx[0] += g * (-n0);
+        gx[1] += g * (-n1);
+        H[0] += h * (n0 * n0);
+        H[1] += h * (n0 * n1);
+        H[4] += h * (n1 * n1);
+        zB += g + h;
+        if (alm) {
+            mun[size_t(4) * Bs] = std_min(std_max(mu[size_t(4) * Bs] + rho * cv[0], T(0)), P.max_mu);
+            mun[size_t(5) * Bs] = std_min(std_max(mu[size_t(5) * Bs] + rho * cv[1], T(0)), P.max_mu);
+            mun[size_t(6) * Bs] = std_min(std_max(mu[size_t(6) * Bs] + rho * cp[0], T(0)), P.max_mu);
+            mun[size_t(7) * Bs] = std_min(std_max(mu[size_t(7) * Bs] + rho * cp[1], T(0)), P.max_mu);
+        }
+        // obstacles: front and rear circle against each ellipse (cpp:648-664)
+        const int no = D.n_obs[b];
+        if (no > 0) {
+            EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
+            // two obstacles per trip (independent exponentials interleave); accumulation in the
+            // reference's order
+            for (int j = 0; j < no; j += 2) {
+                const bool two = j + 1 < no;
+                T tg[2][3], tH[2][6];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int jj = (q && two) ? j + 1 : j;
+                    // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
+                    // evaluated once per upload (k_obs_sincos), not once per cost evaluation
+                    const T* ob = D.obs + (size_t(jj) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
+                    const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
+                    T gfx, gfy, grx, gry;
+                    T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
+                    T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
+                    // chain through the 4x2 centre Jacobians: (gx, gy, 0, yaw row)
+                    T f3 = e.jf0 * gfx + e.jf1 * gfy;
+                    T r3 = e.jr0 * grx + e.jr1 * gry;
+                    T gf, hf, gr, hr;
+                    constraint_weights(alm, cf, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(8 + 2 * jj) * Bs] : T(0), &gf, &hf);
+                    constraint_weights(alm, cr, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(9 + 2 * jj) * Bs] : T(0), &gr, &hr);
+                    // front + rear first, then into the row (cpp:662-664)
+                    tg[q][0] = gf * gfx + gr * grx;
+                    tg[q][1] = gf * gfy + gr * gry;
+                    tg[q][2] = gf * f3 + gr * r3;
+                    tH[q][0] = hf * (gfx * gfx) + hr * (grx * grx);
+                    tH[q][1] = hf * (gfx * gfy) + hr * (grx * gry);
+                    tH[q][2] = hf * (gfx * f3) + hr * (grx * r3);
+                    tH[q][3] = hf * (gfy * gfy) + hr * (gry * gry);
+                    tH[q][4] = hf * (gfy * f3) + hr * (gry * r3);
+                    tH[q][5] = hf * (f3 * f3) + hr * (r3 * r3);
+                    if (q == 0 || two) zO += (gf + hf) + (gr + hr);
+                    if (alm && (q == 0 || two)) {
+                        mun[size_t(8 + 2 * jj) * Bs] =
+                            std_min(std_max(mu[size_t(8 + 2 * jj) * Bs] + rho * cf, T(0)), P.max_mu);
+                        mun[size_t(9 + 2 * jj) * Bs] =
+                            std_min(std_max(mu[size_t(9 + 2 * jj) * Bs] + rho * cr, T(0)), P.max_mu);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (q == 0 || two) {
+                        gx[0] += tg[q][0];
+                        gx[1] += tg[q][1];
+                        gx[3] += tg[q][2];
+                        H[0] += tH[q][0];
+                        H[1] += tH[q][1];
+                        H[3] += tH[q][2];
+                        H[4] += tH[q][3];
+                        H[6] += tH[q][4];
+                        H[9] += tH[q][5];
+                    }
+                }
+            }
+        }
+        // velocity terms have c_dot = (0, 0, +-1, 0), border terms (n0, n1, 0, 0), obstacle terms (gx, gy, 0, g3)
+        zV *= T(0);
+        zB *= T(0);
+        zO *= T(0);
+        gx[0] += zV;
+        gx[1] += zV;
+        gx[2] += zB + zO;
+        gx[3] += zV + zB;
+        const T zVB = zV + zB, zAll = zVB + zO;
+        H[0] += zV;       // 00
+        H[1] += zV;       // 01
+        H[2] += zAll;     // 02
+        H[3] += zVB;      // 03
+        H[4] += zV;       // 11
+        H[5] += zAll;     // 12
+        H[6] += zVB;      // 13
+        H[7] += zB + zO;  // 22
+        H[8] += zAll;     // 23
+        H[9] += zVB;      // 33
+    }
+    // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
+#pragma unroll
+    for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
+    H[0] += 2 * P.Q[0];
+    H[4] += 2 * P.Q[1];
+    H[7] += 2 * P.Q[2];
+    H[9] += 2 * P.Q[3];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) rec[(kRecLxx + c) * kRecFS] = H[c];
+#endif
+    }  // part 0
+
+    if (part == 1 && k < N) {
+        T c[4];
+        ctrl_constraints(P, ua, us, c);
+        const T* mu = alm ? D.mu + size_t(k) * D.alm_cols * Bs + b : nullptr;
+#ifdef CILQR_PARITY
+        const T cu[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+        T gu[2] = {0, 0}, Hu[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            add_constraint_ref<T, 2>(alm, c[m], cu[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * Bs] : T(0), gu, Hu);
+        if (alm) {
+            T* mun = D.mu_next + size_t(k) * D.alm_cols * Bs + b;
+            for (int m = 0; m < 4; ++m)
+                mun[size_t(m) * Bs] = std_min(std_max(mu[size_t(m) * Bs] + rho * c[m], T(0)), P.max_mu);
+        }
+        rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu[0];
+        rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu[1];
+        rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + Hu[0];
+        rec[(kRecLuu + 1) * kRecFS] = Hu[1];
+        rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + Hu[3];
+#else
+        T g[4], h[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            constraint_weights(alm, c[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * Bs] : T(0), &g[m], &h[m]);
+        // (zA / zS: the zero entries of c_dot, as in the state half: an overflowed acceleration barrier
+        // poisons the steering entries and vice versa, both poison the off-diagonal)
+        const T zA = ((g[0] + h[0]) + (g[1] + h[1])) * T(0), zS = ((g[2] + h[2]) + (g[3] + h[3])) * T(0);
+        T gu0 = (g[0] + (-g[1])) + zS;
+        T gu1 = (g[2] + (-g[3])) + zA;
+        T hu0 = (h[0] + h[1]) + zS;
+        T hu1 = (h[2] + h[3]) + zA;
+        if (alm) {
+            T* mun = D.mu_next + size_t(k) * D.alm_cols * Bs + b;
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                mun[size_t(m) * Bs] = std_min(std_max(mu[size_t(m) * Bs] + rho * c[m], T(0)), P.max_mu);
+        }
+        rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu0;
+        rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu1;
+        rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + hu0;
+        rec[(kRecLuu + 1) * kRecFS] = zA + zS;
+        rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + hu1;
+#endif
+        T ja[5], jb[4];
+        model_jacobians(x[2], x[3], us, P.dt, P.wheelbase, P.ref_point, ja, jb);
+#pragma unroll
+        for (int c2 = 0; c2 < 5; ++c2) rec[(kRecA + c2) * kRecFS] = ja[c2];
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2) rec[(kRecB + c2) * kRecFS] = jb[c2];
+    }
+}
+
 template <typename T, int kPart, bool kAlm>
 // CTAs per SM of the two halves in the throughput regime: the state half at 6 (80 registers, 156 B of spills)
 // beats 8 (64 registers, 276 B) and 4 (128, none): 262144 instances 243.1 -> 234.7 ms; the control half stays at 8.
@@ -626,8 +926,7 @@ template <typename T, int kPart, bool kAlm>
 #define CILQR_DERIVS1_MINB 8
 #endif
 __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIVS0_MINB : CILQR_DERIVS1_MINB)) k_derivs(Dev<T> D, int B, int masked, int par) {
-    const int N = D.N;
-    const size_t Bs = D.Bs, Vs = D.Vs;
+    const size_t Bs = D.Bs;
     // two independent halves per (instance, step): part 0 = state terms (l_x, l_xx), part 1 = control
     // terms and model Jacobians (l_u, l_uu, A, B).  kPart < 0: one launch, the half taken from
     // blockIdx.y (latency-bound batches: one launch less per round).  kPart = 0 / 1: one launch per
@@ -638,299 +937,8 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
     // solver: only the instances on this round's work list (running, or with a step to commit)
     const int* list = masked ? D.act + size_t(par) * Bs : nullptr;
     const int n = masked ? D.ctl[CTL_NACT + par] : B;
-    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n; idx += gridDim.y * blockDim.x) {
-        const int b = list ? list[idx] : idx;
-        T x[4], ua = 0, us = 0;
-        int ri = 0;
-        const int src = masked ? D.commit_src[b] : -1;
-        if (src >= 0) {
-            // the accepted trial becomes the current trajectory; part 1 reads the state from the
-            // trial slot too, so it never races with part 0's copy
-#pragma unroll
-            for (int c = 0; c < 4; ++c) x[c] = D.Xt[at(Vs, k, c, 4, src)];
-            if (part == 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) D.X[at(Bs, k, c, 4, b)] = x[c];
-                ri = D.ridx_t[size_t(k) * Vs + src];
-                D.ridx[size_t(k) * Bs + b] = ri;
-                for (int p = 0; p < kScPlanes; ++p)
-                    D.sc[(size_t(p) * (N + 1) + k) * Bs + b] = D.sc_t[(size_t(p) * (N + 1) + k) * Vs + src];
-            } else if (k < N) {
-                ua = D.Ut[at(Vs, k, 0, 2, src)];
-                us = D.Ut[at(Vs, k, 1, 2, src)];
-                D.U[at(Bs, k, 0, 2, b)] = ua;
-                D.U[at(Bs, k, 1, 2, b)] = us;
-            }
-        }
-        if (masked && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) continue;
-        if (src < 0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) x[c] = D.X[at(Bs, k, c, 4, b)];
-            if (part == 0) {
-                ri = D.ridx[size_t(k) * Bs + b];
-            } else if (k < N) {
-                ua = D.U[at(Bs, k, 0, 2, b)];
-                us = D.U[at(Bs, k, 1, 2, b)];
-            }
-        }
-        const DevParams<T>& P = D.P[D.tmpl[b]];
-        const bool alm = kAlm && P.solve_type == 1;
-        const T rho = alm ? D.rho[b] : T(0);
-        T* rec = rec_at(D, k, b);
-        if (part == 0) {
-        const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
-        const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
-#ifdef CILQR_PARITY
-        // the reference's accumulation, literally (cpp:497-689): velocity up / lo, border up / lo into the
-        // row, then per obstacle (front + rear) summed first and added to the row, the prime part last
-        T gx[4] = {0, 0, 0, 0};
-        T Hx[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (k >= 1) {
-            const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
-            T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
-            T d_sign, hyp;
-            const T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
-            const T cc4[4] = {x[2] - P.velo_max, P.velo_min - x[2], cur_d - (D.borders[b] - P.width / 2),
-                              (D.borders[Bs + b] + P.width / 2) - cur_d};
-            T cx[4][4] = {{0, 0, 1, 0}, {0, 0, -1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-            cx[2][0] = (x[0] - rx) / hyp;
-            cx[2][1] = (x[1] - ry) / hyp;
-            if (d_sign < 0)
-                for (int r = 0; r < 4; ++r) cx[2][r] = -1 * cx[2][r];
-            for (int r = 0; r < 4; ++r) cx[3][r] = -1 * cx[2][r];
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-                add_constraint_ref<T, 4>(alm, cc4[m], cx[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4 + m) * Bs] : T(0), gx, Hx);
-            if (alm)
-                for (int m = 0; m < 4; ++m)
-                    mun[size_t(4 + m) * Bs] = std_min(std_max(mu[size_t(4 + m) * Bs] + rho * cc4[m], T(0)), P.max_mu);
-            const int no = D.n_obs[b];
-            if (no > 0) {
-                const EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
-                for (int j = 0; j < no; ++j) {
-                    const T* ob = D.obs + (size_t(j) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
-                    const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
-                    T gfx, gfy, grx, gry;
-                    const T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
-                    const T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
-                    // 4x2 centre Jacobians times the point gradients (utils.cpp:363-385, cpp:728-736)
-                    const T gf[4] = {T(1) * gfx + T(0) * gfy, T(0) * gfx + T(1) * gfy, T(0) * gfx + T(0) * gfy,
-                                     e.jf0 * gfx + e.jf1 * gfy};
-                    const T gr[4] = {T(1) * grx + T(0) * gry, T(0) * grx + T(1) * gry, T(0) * grx + T(0) * gry,
-                                     e.jr0 * grx + e.jr1 * gry};
-                    T g2[4] = {0, 0, 0, 0};
-                    T H2[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                    add_constraint_ref<T, 4>(alm, cf, gf, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(8 + 2 * j) * Bs] : T(0), g2, H2);
-                    add_constraint_ref<T, 4>(alm, cr, gr, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(9 + 2 * j) * Bs] : T(0), g2, H2);
-                    for (int r = 0; r < 4; ++r) gx[r] += g2[r];
-                    for (int r = 0; r < 16; ++r) Hx[r] += H2[r];
-                    if (alm) {
-                        mun[size_t(8 + 2 * j) * Bs] = std_min(std_max(mu[size_t(8 + 2 * j) * Bs] + rho * cf, T(0)), P.max_mu);
-                        mun[size_t(9 + 2 * j) * Bs] = std_min(std_max(mu[size_t(9 + 2 * j) * Bs] + rho * cr, T(0)), P.max_mu);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) Hx[c * 4 + c] = 2 * P.Q[c] + Hx[c * 4 + c];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) rec[(kRecLxx + c) * kRecFS] = Hx[c];
-#else
-        T gx[4] = {0, 0, 0, 0};
-        T H[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
-        if (k >= 1) {
-            const T* mu = alm ? D.mu + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
-            T* mun = alm ? D.mu_next + size_t(k - 1) * D.alm_cols * Bs + b : nullptr;
-            // velocity bounds: c_dot = (0,0,+-1,0)
-            T cv[2] = {x[2] - P.velo_max, P.velo_min - x[2]};
-            // zV / zB / zO: what the zero entries of a constraint's c_dot contribute in the reference, which forms
-            // every product (cpp:696-698): 0 for a finite barrier weight, NaN for one that overflowed (0 * inf).
-            // Summed per constraint family and added below to the entries that family does not otherwise touch,
-            // so that an overflowing barrier poisons the same entries as in the reference.
-            T zV = 0, zB = 0, zO = 0;
-            T g, h;
-            constraint_weights(alm, cv[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4) * Bs] : T(0), &g, &h);
-            gx[2] += g;
-            H[7] += h;
-            zV += g + h;
-            constraint_weights(alm, cv[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(5) * Bs] : T(0), &g, &h);
-            gx[2] += -g;
-            H[7] += h;
-            zV += g + h;
-            // road borders: c_dot = +-(px-rx, py-ry)/hypot, flipped when d_sign < 0 (cpp:527-533)
-            T d_sign, hyp;
-            T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
-            T cp[2] = {cur_d - (D.borders[b] - P.width / 2), (D.borders[Bs + b] + P.width / 2) - cur_d};
-            T n0 = (x[0] - rx) / hyp, n1 = (x[1] - ry) / hyp;
-            if (d_sign < 0) {
-                n0 = -n0;
-                n1 = -n1;
-            }
-            constraint_weights(alm, cp[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(6) * Bs] : T(0), &g, &h);
-            gx[0] += g * n0;
-            gx[1] += g * n1;
-            H[0] += h * (n0 * n0);
-            H[1] += h * (n0 * n1);
-            H[4] += h * (n1 * n1);
-            zB += g + h;
-            constraint_weights(alm, cp[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(7) * Bs] : T(0), &g, &h);
-            gx[0] += g * (-n0);
-            gx[1] += g * (-n1);
-            H[0] += h * (n0 * n0);
-            H[1] += h * (n0 * n1);
-            H[4] += h * (n1 * n1);
-            zB += g + h;
-            if (alm) {
-                mun[size_t(4) * Bs] = std_min(std_max(mu[size_t(4) * Bs] + rho * cv[0], T(0)), P.max_mu);
-                mun[size_t(5) * Bs] = std_min(std_max(mu[size_t(5) * Bs] + rho * cv[1], T(0)), P.max_mu);
-                mun[size_t(6) * Bs] = std_min(std_max(mu[size_t(6) * Bs] + rho * cp[0], T(0)), P.max_mu);
-                mun[size_t(7) * Bs] = std_min(std_max(mu[size_t(7) * Bs] + rho * cp[1], T(0)), P.max_mu);
-            }
-            // obstacles: front and rear circle against each ellipse (cpp:648-664)
-            const int no = D.n_obs[b];
-            if (no > 0) {
-                EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
-                // two obstacles per trip (independent exponentials interleave); accumulation in the
-                // reference's order
-                for (int j = 0; j < no; j += 2) {
-                    const bool two = j + 1 < no;
-                    T tg[2][3], tH[2][6];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int jj = (q && two) ? j + 1 : j;
-                        // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
-                        // evaluated once per upload (k_obs_sincos), not once per cost evaluation
-                        const T* ob = D.obs + (size_t(jj) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
-                        const T ox = ob[0], oy = ob[Bs], so = ob[2 * Bs], co = ob[3 * Bs];
-                        T gfx, gfy, grx, gry;
-                        T cf = ellipse_margin<T, true>(e.fx, e.fy, ox, oy, so, co, P.ell_a2, P.ell_b2, &gfx, &gfy);
-                        T cr = ellipse_margin<T, true>(e.rx, e.ry, ox, oy, so, co, P.ell_a2, P.ell_b2, &grx, &gry);
-                        // chain through the 4x2 centre Jacobians: (gx, gy, 0, yaw row)
-                        T f3 = e.jf0 * gfx + e.jf1 * gfy;
-                        T r3 = e.jr0 * grx + e.jr1 * gry;
-                        T gf, hf, gr, hr;
-                        constraint_weights(alm, cf, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(8 + 2 * jj) * Bs] : T(0), &gf, &hf);
-                        constraint_weights(alm, cr, P.obs_q1, P.obs_q2, rho, alm ? mu[size_t(9 + 2 * jj) * Bs] : T(0), &gr, &hr);
-                        // front + rear first, then into the row (cpp:662-664)
-                        tg[q][0] = gf * gfx + gr * grx;
-                        tg[q][1] = gf * gfy + gr * gry;
-                        tg[q][2] = gf * f3 + gr * r3;
-                        tH[q][0] = hf * (gfx * gfx) + hr * (grx * grx);
-                        tH[q][1] = hf * (gfx * gfy) + hr * (grx * gry);
-                        tH[q][2] = hf * (gfx * f3) + hr * (grx * r3);
-                        tH[q][3] = hf * (gfy * gfy) + hr * (gry * gry);
-                        tH[q][4] = hf * (gfy * f3) + hr * (gry * r3);
-                        tH[q][5] = hf * (f3 * f3) + hr * (r3 * r3);
-                        if (q == 0 || two) zO += (gf + hf) + (gr + hr);
-                        if (alm && (q == 0 || two)) {
-                            mun[size_t(8 + 2 * jj) * Bs] =
-                                std_min(std_max(mu[size_t(8 + 2 * jj) * Bs] + rho * cf, T(0)), P.max_mu);
-                            mun[size_t(9 + 2 * jj) * Bs] =
-                                std_min(std_max(mu[size_t(9 + 2 * jj) * Bs] + rho * cr, T(0)), P.max_mu);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (q == 0 || two) {
-                            gx[0] += tg[q][0];
-                            gx[1] += tg[q][1];
-                            gx[3] += tg[q][2];
-                            H[0] += tH[q][0];
-                            H[1] += tH[q][1];
-                            H[3] += tH[q][2];
-                            H[4] += tH[q][3];
-                            H[6] += tH[q][4];
-                            H[9] += tH[q][5];
-                        }
-                    }
-                }
-            }
-            // velocity terms have c_dot = (0, 0, +-1, 0), border terms (n0, n1, 0, 0), obstacle terms (gx, gy, 0, g3)
-            zV *= T(0);
-            zB *= T(0);
-            zO *= T(0);
-            gx[0] += zV;
-            gx[1] += zV;
-            gx[2] += zB + zO;
-            gx[3] += zV + zB;
-            const T zVB = zV + zB, zAll = zVB + zO;
-            H[0] += zV;       // 00
-            H[1] += zV;       // 01
-            H[2] += zAll;     // 02
-            H[3] += zVB;      // 03
-            H[4] += zV;       // 11
-            H[5] += zAll;     // 12
-            H[6] += zVB;      // 13
-            H[7] += zB + zO;  // 22
-            H[8] += zAll;     // 23
-            H[9] += zVB;      // 33
-        }
-        // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
-        H[0] += 2 * P.Q[0];
-        H[4] += 2 * P.Q[1];
-        H[7] += 2 * P.Q[2];
-        H[9] += 2 * P.Q[3];
-#pragma unroll
-        for (int c = 0; c < 10; ++c) rec[(kRecLxx + c) * kRecFS] = H[c];
-#endif
-        }  // part 0
-
-        if (part == 1 && k < N) {
-            T c[4];
-            ctrl_constraints(P, ua, us, c);
-            const T* mu = alm ? D.mu + size_t(k) * D.alm_cols * Bs + b : nullptr;
-#ifdef CILQR_PARITY
-            const T cu[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
-            T gu[2] = {0, 0}, Hu[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-                add_constraint_ref<T, 2>(alm, c[m], cu[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * Bs] : T(0), gu, Hu);
-            if (alm) {
-                T* mun = D.mu_next + size_t(k) * D.alm_cols * Bs + b;
-                for (int m = 0; m < 4; ++m)
-                    mun[size_t(m) * Bs] = std_min(std_max(mu[size_t(m) * Bs] + rho * c[m], T(0)), P.max_mu);
-            }
-            rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu[0];
-            rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu[1];
-            rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + Hu[0];
-            rec[(kRecLuu + 1) * kRecFS] = Hu[1];
-            rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + Hu[3];
-#else
-            T g[4], h[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-                constraint_weights(alm, c[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * Bs] : T(0), &g[m], &h[m]);
-            // (zA / zS: the zero entries of c_dot, as in the state half: an overflowed acceleration barrier
-            // poisons the steering entries and vice versa, both poison the off-diagonal)
-            const T zA = ((g[0] + h[0]) + (g[1] + h[1])) * T(0), zS = ((g[2] + h[2]) + (g[3] + h[3])) * T(0);
-            T gu0 = (g[0] + (-g[1])) + zS;
-            T gu1 = (g[2] + (-g[3])) + zA;
-            T hu0 = (h[0] + h[1]) + zS;
-            T hu1 = (h[2] + h[3]) + zA;
-            if (alm) {
-                T* mun = D.mu_next + size_t(k) * D.alm_cols * Bs + b;
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    mun[size_t(m) * Bs] = std_min(std_max(mu[size_t(m) * Bs] + rho * c[m], T(0)), P.max_mu);
-            }
-            rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu0;
-            rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu1;
-            rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + hu0;
-            rec[(kRecLuu + 1) * kRecFS] = zA + zS;
-            rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + hu1;
-#endif
-            T ja[5], jb[4];
-            model_jacobians(x[2], x[3], us, P.dt, P.wheelbase, P.ref_point, ja, jb);
-#pragma unroll
-            for (int c2 = 0; c2 < 5; ++c2) rec[(kRecA + c2) * kRecFS] = ja[c2];
-#pragma unroll
-            for (int c2 = 0; c2 < 4; ++c2) rec[(kRecB + c2) * kRecFS] = jb[c2];
-        }
-    }
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n; idx += gridDim.y * blockDim.x)
+        derivs_item<T, kAlm>(D, list ? list[idx] : idx, k, part, masked);
 }
 
 // solve()'s bookkeeping after an iter_step (cpp:113-141): lambda schedule,
@@ -1451,14 +1459,136 @@ __device__ __forceinline__ void bulk_load(unsigned dst_smem, const void* src, un
                  : "memory");
 }
 
+// Slot claiming for a tile that owns a private region [tile_base, tile_base + tile_slots) of the trial pool
+// (k_solve_tiles): same layout of the claims as claim_slots, no global counter.  Returns the slots in use.
+template <typename T>
+__device__ __forceinline__ int claim_slots_tile(const Dev<T>& D, int b, int want, int a0, int lane, int tile_base, int tile_slots) {
+    int incl = want;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (want > 0) {
+        const int off = incl - want;
+        const int room = tile_slots - off;
+        const int cnt = room <= 0 ? 0 : (want < room ? want : room);
+        D.t_first[b] = tile_base + off;
+        D.t_count[b] = cnt;
+        for (int i = 0; i < cnt; ++i) {
+            D.t_inst[tile_base + off + i] = b;
+            D.t_aidx[tile_base + off + i] = a0 + i;
+        }
+    }
+    return total < tile_slots ? total : tile_slots;
+}
+
+// Shared-memory state of the staged backward pass of one warp.
+template <typename T>
+struct StagedRing {
+    T (*stage)[kRecFields][32];     // [kStagedStages]
+    unsigned long long* full;       // [kStagedStages] mbarriers
+    unsigned issued, consumed;      // ring positions (steps), running over all tiles this warp handles
+};
+
+// The backward pass of tile `tile` (32 consecutive instances, lane = instance) by the calling warp; see
+// k_backward_staged.  tile_slots < 0: slots claimed from the global trial pool (claim_slots); otherwise from the
+// tile's private region and the number of slots in use is returned.
+template <typename T>
+__device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, int tile, int B, int solver, int lane,
+                                             int tile_base, int tile_slots) {
+    const int N = D.N;
+    const size_t Bs = D.Bs;
+    constexpr unsigned kStepBytes = kRecFields * 32 * sizeof(T);
+    const int b = tile * 32 + lane;
+    const bool in = b < B;
+    int ph = PH_DONE;
+    bool run = false;
+    if (in) {
+        if (!solver) {
+            run = true;
+        } else {
+            D.commit_src[b] = -1;  // consumed by the derivative stage just before
+            D.t_count[b] = 0;
+            ph = D.phase[b];
+            run = ph == PH_BACKWARD;
+        }
+    }
+    bool ok = true;
+    if (__any_sync(0xffffffffu, run)) {
+        const T* tile_rec = rec_at(D, 0, tile * 32);
+        // the tile's record of step `step` (one contiguous block) -> ring slot issued % kStagedStages
+        auto issue = [&](int step) {
+            const unsigned s = R.issued % kStagedStages;
+            if (lane == 0) {
+                const unsigned bar = smem_addr(&R.full[s]);
+                mbar_arrive_expect_tx(bar, kStepBytes);
+                bulk_load(smem_addr(&R.stage[s][0][0]), tile_rec + size_t(step) * kRecFields * Bs, kStepBytes, bar);
+            }
+            ++R.issued;
+        };
+        for (int j = 0; j < kStagedStages && j < N; ++j) issue(N - 1 - j);
+        const T lamb = run ? D.lamb[b] : T(0);
+        T Vx[4], V[kVN];
+        {
+            const T* rec = rec_at(D, N, in ? b : 0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Vx[c] = rec[(kRecLx + c) * kRecFS];
+            load_terminal_V(rec, V);
+        }
+        T dV0 = 0, dV1 = 0;
+        T* Kp = D.Kg + size_t(N) * 8 * Bs + (in ? b : 0);
+        T* dp = D.dg + size_t(N) * 2 * Bs + (in ? b : 0);
+        for (int i = N - 1; i >= 0; --i) {
+            const unsigned s = R.consumed % kStagedStages, parity = (R.consumed / kStagedStages) & 1u;
+            ++R.consumed;
+            Kp -= 8 * Bs;
+            dp -= 2 * Bs;
+            mbar_wait(smem_addr(&R.full[s]), parity);
+            if (run) {
+                T K[8] = {0, 0, 0, 0, 0, 0, 0, 0}, d0 = 0, d1 = 0;
+                if (ok) {
+                    T r[kRecFields];
+#pragma unroll
+                    for (int c = 0; c < kRecFields; ++c) r[c] = R.stage[s][c][lane];
+                    ok = riccati_step(r, lamb, Vx, V, dV0, dV1, K, d0, d1);
+                    if (!ok) {
+                        // rows not reached stay zero, as in the reference (cpp:392-393, :418)
+                        d0 = d1 = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) K[c] = 0;
+                    }
+                }
+                dp[0] = d0;
+                dp[Bs] = d1;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) Kp[size_t(c) * Bs] = K[c];
+            }
+            __syncwarp();  // every lane is done with slot s
+            if (i - kStagedStages >= 0) issue(i - kStagedStages);
+        }
+        if (run) {
+            D.dV[b] = dV0;
+            D.dV[Bs + b] = dV1;
+        }
+    }
+    if (in && !solver) D.status[b] = ok ? ST_RUNNING : ST_BWD_FAIL;
+    int want = 0, a0 = 0;
+    if (in && solver) after_backward(D, b, run, ok, ph, &want, &a0);
+    if (!solver) return 0;
+    if (tile_slots < 0) {
+        claim_slots(D, in ? b : 0, want, a0, lane);
+        return 0;
+    }
+    return claim_slots_tile(D, in ? b : 0, want, a0, lane, tile_base, tile_slots);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(32) k_backward_staged(Dev<T> D, int B, int solver) {
     __shared__ __align__(128) T stage[kStagedStages][kRecFields][32];
     __shared__ __align__(8) unsigned long long full[kStagedStages];
     const int lane = threadIdx.x;
-    const int N = D.N;
-    const size_t Bs = D.Bs;
-    constexpr unsigned kStepBytes = kRecFields * 32 * sizeof(T);
     static_assert(kRecTile == 32, "one warp per record tile");
     if (lane == 0) {
 #pragma unroll
@@ -1466,86 +1596,9 @@ __global__ void __launch_bounds__(32) k_backward_staged(Dev<T> D, int B, int sol
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    unsigned issued = 0, consumed = 0;  // ring positions (steps), running over all tiles of this warp
+    StagedRing<T> R{stage, full, 0u, 0u};
     const int n_tiles = (B + 31) / 32;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile * 32 + lane;
-        const bool in = b < B;
-        int ph = PH_DONE;
-        bool run = false;
-        if (in) {
-            if (!solver) {
-                run = true;
-            } else {
-                D.commit_src[b] = -1;  // consumed by the derivative stage just before
-                D.t_count[b] = 0;
-                ph = D.phase[b];
-                run = ph == PH_BACKWARD;
-            }
-        }
-        bool ok = true;
-        if (__any_sync(0xffffffffu, run)) {
-            const T* tile_rec = rec_at(D, 0, tile * 32);
-            // the tile's record of step `step` (one contiguous block) -> ring slot issued % kStagedStages
-            auto issue = [&](int step) {
-                const unsigned s = issued % kStagedStages;
-                if (lane == 0) {
-                    const unsigned bar = smem_addr(&full[s]);
-                    mbar_arrive_expect_tx(bar, kStepBytes);
-                    bulk_load(smem_addr(&stage[s][0][0]), tile_rec + size_t(step) * kRecFields * Bs, kStepBytes, bar);
-                }
-                ++issued;
-            };
-            for (int j = 0; j < kStagedStages && j < N; ++j) issue(N - 1 - j);
-            const T lamb = run ? D.lamb[b] : T(0);
-            T Vx[4], V[kVN];
-            {
-                const T* rec = rec_at(D, N, in ? b : 0);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) Vx[c] = rec[(kRecLx + c) * kRecFS];
-                load_terminal_V(rec, V);
-            }
-            T dV0 = 0, dV1 = 0;
-            T* Kp = D.Kg + size_t(N) * 8 * Bs + (in ? b : 0);
-            T* dp = D.dg + size_t(N) * 2 * Bs + (in ? b : 0);
-            for (int i = N - 1; i >= 0; --i) {
-                const unsigned s = consumed % kStagedStages, parity = (consumed / kStagedStages) & 1u;
-                ++consumed;
-                Kp -= 8 * Bs;
-                dp -= 2 * Bs;
-                mbar_wait(smem_addr(&full[s]), parity);
-                if (run) {
-                    T K[8] = {0, 0, 0, 0, 0, 0, 0, 0}, d0 = 0, d1 = 0;
-                    if (ok) {
-                        T r[kRecFields];
-#pragma unroll
-                        for (int c = 0; c < kRecFields; ++c) r[c] = stage[s][c][lane];
-                        ok = riccati_step(r, lamb, Vx, V, dV0, dV1, K, d0, d1);
-                        if (!ok) {
-                            // rows not reached stay zero, as in the reference (cpp:392-393, :418)
-                            d0 = d1 = 0;
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) K[c] = 0;
-                        }
-                    }
-                    dp[0] = d0;
-                    dp[Bs] = d1;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) Kp[size_t(c) * Bs] = K[c];
-                }
-                __syncwarp();  // every lane is done with slot s
-                if (i - kStagedStages >= 0) issue(i - kStagedStages);
-            }
-            if (run) {
-                D.dV[b] = dV0;
-                D.dV[Bs + b] = dV1;
-            }
-        }
-        if (in && !solver) D.status[b] = ok ? ST_RUNNING : ST_BWD_FAIL;
-        int want = 0, a0 = 0;
-        if (in && solver) after_backward(D, b, run, ok, ph, &want, &a0);
-        if (solver) claim_slots(D, b, want, a0, lane);
-    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) backward_tile(D, R, tile, B, solver, lane, 0, -1);
 }
 
 // ---------------------------------------------------------------------------
@@ -1748,144 +1801,341 @@ __global__ void __launch_bounds__(128) k_forward2(Dev<T> D, int B) {
 // (profiles/r01_pipeline_findings.txt).
 constexpr int kPipeTrials = 16;
 constexpr int kPipeMaxSteps = 128;
-constexpr unsigned kPipeBackoffNs = 100;  // waiting scan warps stay off the issue ports
 __host__ __device__ constexpr int pipe_threads(int G) { return 32 + kPipeTrials * G; }
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// One group of up to kPipeTrials trials [base, base + kPipeTrials) of the pool (count = slots in use overall): the
+// calling warp is either the group's roller (two lanes per trial) or scan warp number `scan_warp` (G lanes per
+// trial).  Positions travel through pos[step][trial][2]; step k is handed over by an arrival on the mbarrier
+// bars[k] (release) that the scan warps wait for (acquire) in phase `parity` — every barrier completes exactly
+// one phase per call, so the caller alternates parity and separates calls by a block-wide barrier.
+template <typename T, int G>
+__device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kPipeTrials][2], unsigned long long* bars,
+                                                    unsigned parity, int base, int count, bool roller, int scan_warp, int lane) {
+    const int N = D.N;
+    const size_t Bs = D.Bs, Vs = D.Vs;
+    // rollout lanes: slot = lane / 2, role = lane & 1; scan lanes: slot = (32 / G) scan_warp + lane / G
+    const int role = lane & 1;
+    const int sub = lane % G;
+    const int grp_shift = lane - sub;
+    const unsigned grp_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << grp_shift);
+    const int slot = roller ? (lane >> 1) : (scan_warp * (32 / G) + lane / G);
+    const int v = base + slot;
+    const bool live = v < count;
+    const int vv = live ? v : count - 1;
+    const int b = D.t_inst[vv];
+    const DevParams<T>* Pp = D.P + D.tmpl[b];
+    if (roller) {
+        const T p_dt = Pp->dt, p_dtw = Pp->dt / Pp->wheelbase;
+        const int p_ref = Pp->ref_point;
+        const bool mixed = __any_sync(0xffffffffu, p_ref != 0);
+        const T alpha = T(1) / T(1 << D.t_aidx[vv]);
+        // lane `role` of a pair owns control row `role`: its feedback row, u and d
+        T xn[4], cx[4], cK[4], cu, cd;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            cx[c] = D.X[at(Bs, 0, c, 4, b)];
+            xn[c] = cx[c];
+        }
+        if (role == 0) {
+            pos[0][slot][0] = xn[0];
+            pos[0][slot][1] = xn[1];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&bars[0]));
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (live && role == 0) D.Xt[at(Vs, 0, c, 4, v)] = xn[c];
+        cu = D.U[at(Bs, 0, role, 2, b)];
+        cd = D.dg[at(Bs, 0, role, 2, b)];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cK[c] = D.Kg[at(Bs, 0, role * 4 + c, 8, b)];
+        for (int i = 0; i < N; ++i) {
+            T nxx[4], nxK[4], nxu, nxd;
+            const int ip = i + 1 < N ? i + 1 : i;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) nxx[c] = ld_early(D.X + at(Bs, ip, c, 4, b));
+            nxu = ld_early(D.U + at(Bs, ip, role, 2, b));
+            nxd = ld_early(D.dg + at(Bs, ip, role, 2, b));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) nxK[c] = ld_early(D.Kg + at(Bs, ip, role * 4 + c, 8, b));
+            T fb = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) fb += cK[c] * (xn[c] - cx[c]);
+            const T mine = (cu + fb) + alpha * cd;  // u'[role]
+            const T other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const T acc = role ? other : mine;
+            T s_head, c_head, turn;
+            {
+                T sn, cs;
+                m_sincos(role ? mine : xn[3], &sn, &cs);
+                const T os = __shfl_xor_sync(0xffffffffu, sn, 1), oc = __shfl_xor_sync(0xffffffffu, cs, 1);
+                step_trig(p_ref, mixed, role ? os : sn, role ? oc : cs, role ? sn : os, role ? cs : oc, &s_head,
+                          &c_head, &turn);
+            }
+            T nx[4];
+            step_from_trig(xn, acc, p_dt, p_dtw, p_ref, s_head, c_head, turn, nx);
+            // hand the position over first, then this step's global stores
+            if (role == 0) {
+                pos[i + 1][slot][0] = nx[0];
+                pos[i + 1][slot][1] = nx[1];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_addr(&bars[i + 1]));
+            if (live) D.Ut[at(Vs, i, role, 2, v)] = mine;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                xn[c] = nx[c];
+                if (live && role == 0) D.Xt[at(Vs, i + 1, c, 4, v)] = nx[c];
+                cx[c] = nxx[c];
+            }
+            cu = nxu;
+            cd = nxd;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cK[c] = nxK[c];
+        }
+    } else {
+        const int M = Pp->wp_len;
+        const T* wx = D.wx + Pp->wp_off;
+        const T* wy = D.wy + Pp->wp_off;
+        int start = 0;
+        for (int k = 0; k <= N; ++k) {
+            mbar_wait(smem_addr(&bars[k]), parity);
+            const T px = pos[k][slot][0], py = pos[k][slot][1];
+            int found = -1;
+            bool done = !live;
+            while (!__all_sync(0xffffffffu, done)) {
+                int j = start + sub;
+                int jc = j < M ? j : M - 1;
+                T dj = wp_dist2(px, py, __ldg(wx + jc), __ldg(wy + jc));
+                T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
+                bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
+                unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
+                if (!done) {
+                    if (m) {
+                        found = start + (__ffs(m) - 1 - grp_shift);
+                        done = true;
+                    } else {
+                        start += G - 1;
+                    }
+                }
+            }
+            if (live) {
+                if (sub == 0) D.ridx_t[size_t(k) * Vs + v] = found;
+                start = found;
+            }
+        }
+    }
+}
 
 // G = scan lanes per trial: 16 (two blocks per SM) when the whole trial pool fits one wave that way,
 // 8 (four blocks per SM, a slower but still hidden scan) beyond that.
 template <typename T, int G>
 __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_match(Dev<T> D, int B) {
     __shared__ T pos[kPipeMaxSteps][kPipeTrials][2];
-    __shared__ int ready;  // positions of steps 0..ready are in the ring
-    const int N = D.N;
-    const size_t Bs = D.Bs, Vs = D.Vs;
+    __shared__ __align__(8) unsigned long long bars[kPipeMaxSteps];  // bars[k]: positions of step k are in the ring
     const int count = view_count(D, 1, B);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool roller = warp == 0;
-    // rollout lanes: slot = lane / 2, role = lane & 1; scan lanes: slot = (32 / G) (warp - 1) + lane / G
-    const int role = lane & 1;
-    const int sub = lane % G;
-    const int grp_shift = lane - sub;
-    const unsigned grp_mask = ((1u << G) - 1u) << grp_shift;
-    const int slot = roller ? (lane >> 1) : ((warp - 1) * (32 / G) + lane / G);
-    for (int base = blockIdx.x * kPipeTrials; base < count; base += gridDim.x * kPipeTrials) {
-        const int v = base + slot;
-        const bool live = v < count;
-        const int vv = live ? v : count - 1;
-        const int b = D.t_inst[vv];
-        const DevParams<T>* Pp = D.P + D.tmpl[b];
-        if (threadIdx.x == 0) ready = -1;
-        __syncthreads();
-        if (roller) {
-            const T p_dt = Pp->dt, p_dtw = Pp->dt / Pp->wheelbase;
-            const int p_ref = Pp->ref_point;
-            const bool mixed = __any_sync(0xffffffffu, p_ref != 0);
-            const T alpha = T(1) / T(1 << D.t_aidx[vv]);
-            // lane `role` of a pair owns control row `role`: its feedback row, u and d
-            T xn[4], cx[4], cK[4], cu, cd;
+    for (int k = threadIdx.x; k <= D.N; k += blockDim.x) mbar_init(smem_addr(&bars[k]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned parity = 0;
+    for (int base = blockIdx.x * kPipeTrials; base < count; base += gridDim.x * kPipeTrials, parity ^= 1u) {
+        rollout_match_group<T, G>(D, pos, bars, parity, base, count, warp == 0, warp - 1, lane);
+        __syncthreads();  // the ring is reused by the next group of trials
+    }
+}
+
+// The line-search verdict of one instance in PH_SEARCH over the cnt > 0 trial slots it evaluated this round, in alpha
+// order (iter_step cpp:356-380), followed by solve()'s bookkeeping (end_iteration).
+template <typename T>
+__device__ __forceinline__ void decide_instance(const Dev<T>& D, int b, int cnt) {
+    const size_t Bs = D.Bs;
+    const DevParams<T>& P = D.P[D.tmpl[b]];
+    const int v0 = D.t_first[b];
+    const int a0 = D.aidx[b];
+    const T J_cur = D.J_cur[b];
+    const T dV0 = D.dV[b], dV1 = D.dV[Bs + b];
+    bool ended = false;
+    T last_J = J_cur;  // cost of the last trial looked at: what iter_step returns when every alpha was rejected (cpp:380)
+    // trial costs four at a time (independent loads), then their verdicts in alpha order; the
+    // usual case is a single trial
+    for (int i0 = 0; i0 < cnt && !ended; i0 += 4) {
+    T Jt[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                cx[c] = D.X[at(Bs, 0, c, 4, b)];
-                xn[c] = cx[c];
-            }
-            if (role == 0) {
-                pos[0][slot][0] = xn[0];
-                pos[0][slot][1] = xn[1];
-            }
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                *(volatile int*)&ready = 0;
-            }
+    for (int q = 0; q < 4; ++q) Jt[q] = i0 + q < cnt ? D.J_t[v0 + i0 + q] : T(0);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (live && role == 0) D.Xt[at(Vs, 0, c, 4, v)] = xn[c];
-            cu = D.U[at(Bs, 0, role, 2, b)];
-            cd = D.dg[at(Bs, 0, role, 2, b)];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) cK[c] = D.Kg[at(Bs, 0, role * 4 + c, 8, b)];
-            for (int i = 0; i < N; ++i) {
-                T nxx[4], nxK[4], nxu, nxd;
-                const int ip = i + 1 < N ? i + 1 : i;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) nxx[c] = ld_early(D.X + at(Bs, ip, c, 4, b));
-                nxu = ld_early(D.U + at(Bs, ip, role, 2, b));
-                nxd = ld_early(D.dg + at(Bs, ip, role, 2, b));
-#pragma unroll
-                for (int c = 0; c < 4; ++c) nxK[c] = ld_early(D.Kg + at(Bs, ip, role * 4 + c, 8, b));
-                T fb = 0;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) fb += cK[c] * (xn[c] - cx[c]);
-                const T mine = (cu + fb) + alpha * cd;  // u'[role]
-                const T other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                const T acc = role ? other : mine;
-                T s_head, c_head, turn;
-                {
-                    T sn, cs;
-                    m_sincos(role ? mine : xn[3], &sn, &cs);
-                    const T os = __shfl_xor_sync(0xffffffffu, sn, 1), oc = __shfl_xor_sync(0xffffffffu, cs, 1);
-                    step_trig(p_ref, mixed, role ? os : sn, role ? oc : cs, role ? sn : os, role ? cs : oc, &s_head,
-                              &c_head, &turn);
-                }
-                T nx[4];
-                step_from_trig(xn, acc, p_dt, p_dtw, p_ref, s_head, c_head, turn, nx);
-                // hand the position over first, then this step's global stores (the fence waits
-                // only for stores issued before it)
-                if (role == 0) {
-                    pos[i + 1][slot][0] = nx[0];
-                    pos[i + 1][slot][1] = nx[1];
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence_block();
-                    *(volatile int*)&ready = i + 1;
-                }
-                if (live) D.Ut[at(Vs, i, role, 2, v)] = mine;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    xn[c] = nx[c];
-                    if (live && role == 0) D.Xt[at(Vs, i + 1, c, 4, v)] = nx[c];
-                    cx[c] = nxx[c];
-                }
-                cu = nxu;
-                cd = nxd;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) cK[c] = nxK[c];
-            }
+    for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q;
+        if (i >= cnt || ended) break;
+        const int v = v0 + i, a = a0 + i;
+        const T new_J = Jt[q];
+        last_J = new_J;
+        const T alpha = T(1) / T(1 << a);
+        const T actual = J_cur - new_J;
+        if (a == 0 && m_fabs(actual) < P.conv_thr) {
+            D.wide[b] = 0;
+            end_iteration(D, P, b, ST_CONVERGED, a, new_J);  // trial discarded (cpp:358-361)
+            ended = true;
         } else {
-            const int M = Pp->wp_len;
-            const T* wx = D.wx + Pp->wp_off;
-            const T* wy = D.wy + Pp->wp_off;
-            int start = 0;
-            for (int k = 0; k <= N; ++k) {
-                while (*(volatile int*)&ready < k) __nanosleep(kPipeBackoffNs);
-                __threadfence_block();
-                const T px = pos[k][slot][0], py = pos[k][slot][1];
-                int found = -1;
-                bool done = !live;
-                while (!__all_sync(0xffffffffu, done)) {
-                    int j = start + sub;
-                    int jc = j < M ? j : M - 1;
-                    T dj = wp_dist2(px, py, __ldg(wx + jc), __ldg(wy + jc));
-                    T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
-                    bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
-                    unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
-                    if (!done) {
-                        if (m) {
-                            found = start + (__ffs(m) - 1 - grp_shift);
-                            done = true;
-                        } else {
-                            start += G - 1;
-                        }
-                    }
-                }
-                if (live) {
-                    if (sub == 0) D.ridx_t[size_t(k) * Vs + v] = found;
-                    start = found;
-                }
+            const T approx = -(alpha * alpha * dV0 + alpha * dV1);
+            if (actual > T(0) && (approx < T(0) || actual / approx > P.accept_thr)) {
+                D.commit_src[b] = v;  // x, u <- new (cpp:113-116), copied by the next derivative stage
+                D.J_cur[b] = new_J;
+                D.rec_valid[b] = 0;
+                D.wide[b] = a > 0;
+                end_iteration(D, P, b, a == 0 ? ST_RUNNING : ST_SMALL_STEP, a, new_J);
+                ended = true;
             }
         }
-        __syncthreads();  // the ring is reused by the next group of trials
+    }
+    }
+    if (!ended) {
+        if (a0 + cnt >= kNumAlphas) {
+            if (P.solve_type == 1 && D.mu) {  // cpp:377-378
+                for (int i = 0; i < D.N * D.alm_cols; ++i)
+                    D.mu[size_t(i) * Bs + b] = D.mu_next[size_t(i) * Bs + b];
+                D.rho[b] = std_min((1 + P.alm_gamma) * D.rho[b], P.max_rho);
+                D.rec_valid[b] = 0;
+            }
+            D.wide[b] = 1;
+            end_iteration(D, P, b, ST_FWD_FAIL, -1, last_J);
+        } else {
+            D.aidx[b] = a0 + cnt;
+            D.wide[b] = 1;  // alpha = 1 was rejected: evaluate the remaining alphas together
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The whole solve loop of a tile of 32 consecutive instances inside ONE CTA (latency-bound batches: up to one
+// tile per SM, i.e. 148 * 32 instances).  A round of the host-driven loop is five dependent launches plus a
+// verdict kernel that synchronises the whole batch; here a tile iterates on its own — derivatives, backward pass,
+// rollouts + waypoint match, step costs, verdict, separated by block barriers — until its 32 instances have left
+// the solve, with no launch, no grid-wide dependency and no host involvement in between.  The phases are the
+// device functions the stage kernels are made of (derivs_item, backward_tile, rollout_match_group, step_cost_of,
+// decide_instance), so the results are bit-identical to the host-driven loop
+// (tests/test_gpu_solve.py::test_kernel_variants_return_the_same_bits).
+//   warp 0        backward pass of the tile (lane = instance; records through the bulk-copy ring), verdicts
+//   warps 0-3     rollers of up to four groups of 16 trials (two lanes per trial)
+//   warps 4-11    waypoint scan of those groups (four lanes per trial), trailing the rollers through mbarriers
+//   all warps     derivative records and step costs, one (instance or trial, step) item per thread and pass
+// The tile owns a private region of the trial pool (tile_slots slots from tile * tile_slots).
+// ---------------------------------------------------------------------------
+constexpr int kTileThreads = 384;  // 12 warps: 170 registers per thread, what the staged recursion needs
+constexpr int kTileGroups = 4;
+constexpr int kTileScanG = 4;      // (12 - 4) scan warps * 32 lanes / (4 groups * 16 trials)
+constexpr int kTileMaxTiles = 148;
+
+template <typename T>
+__host__ __device__ constexpr size_t tile_smem_bytes(int N) {
+    return size_t(kStagedStages) * kRecFields * 32 * sizeof(T) + 128 +
+           size_t(kTileGroups) * (N + 1) * kPipeTrials * 2 * sizeof(T) + size_t(kTileGroups) * (N + 1) * 8 + 128;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTileThreads, 1) k_solve_tiles(Dev<T> D, int B, int tile_slots, int max_rounds, int rounds_before) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    const int N = D.N;
+    const size_t Vs = D.Vs;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, b0 = tile * 32, tile_base = tile * tile_slots;
+    // carve the shared memory
+    unsigned char* p = tile_smem;
+    T(*stage)[kRecFields][32] = reinterpret_cast<T(*)[kRecFields][32]>(p);
+    p += size_t(kStagedStages) * kRecFields * 32 * sizeof(T);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(p);
+    p += 128;
+    T(*pos_all)[kPipeTrials][2] = reinterpret_cast<T(*)[kPipeTrials][2]>(p);
+    p += size_t(kTileGroups) * (N + 1) * kPipeTrials * 2 * sizeof(T);
+    unsigned long long* bars_all = reinterpret_cast<unsigned long long*>(p);
+    p += size_t(kTileGroups) * (N + 1) * 8;
+    int* s_ctl = reinterpret_cast<int*>(p);  // [0] trial slots in use this round, [1] instances still running
+    if (tid == 0) {
+        for (int q = 0; q < kStagedStages; ++q) mbar_init(smem_addr(&full[q]), 1);
+        for (int q = 0; q < kTileGroups * (N + 1); ++q) mbar_init(smem_addr(&bars_all[q]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    StagedRing<T> R{stage, full, 0u, 0u};
+    // my rollout group: rollers are warps 0..3, group g is scanned by warps 4 + 2g and 5 + 2g
+    const bool roller = warp < kTileGroups;
+    const int grp = roller ? warp : (warp - kTileGroups) >> 1;
+    const int scan_warp = (warp - kTileGroups) & 1;
+    T(*pos)[kPipeTrials][2] = pos_all + size_t(grp) * (N + 1);
+    unsigned long long* bars = bars_all + size_t(grp) * (N + 1);
+    unsigned parity = 0;  // of my group's step barriers
+    const View<T> VT = view_of(D, 1);
+    int rounds = 0;
+    long long trials = 0;
+    for (; rounds < max_rounds; ++rounds) {
+        // derivative records (and the commit of a step accepted in the previous round)
+        for (int item = tid; item < 32 * 2 * (N + 1); item += kTileThreads) {
+            const int b = b0 + (item & 31), kp = item >> 5;
+            if (b < B) derivs_item<T, false>(D, b, kp >> 1, kp & 1, 1);
+        }
+        __syncthreads();
+        // backward pass; the searching instances claim their trial slots
+        if (warp == 0) {
+            const int n = backward_tile(D, R, tile, B, 1, lane, tile_base, tile_slots);
+            if (lane == 0) s_ctl[0] = n;
+        }
+        __syncthreads();
+        const int ntr = s_ctl[0], tr_end = tile_base + ntr;
+        // rollouts + waypoint match, four groups of 16 trials at a time
+        for (int base = tile_base; base < tr_end; base += kTileGroups * kPipeTrials) {
+            const int gbase = base + grp * kPipeTrials;
+            if (gbase < tr_end) {
+                rollout_match_group<T, kTileScanG>(D, pos, bars, parity, gbase, tr_end, roller, scan_warp, lane);
+                parity ^= 1u;
+            }
+            __syncthreads();
+        }
+        // step costs of the trials (lane = trial slot), then their totals
+        for (int item = tid; item < ntr * (N + 1); item += kTileThreads) {
+            const int k = item / ntr, v = tile_base + item % ntr;
+            VT.sc[size_t(k) * Vs + v] = step_cost_of<T, false, 4>(D, VT, D.t_inst[v], v, k, VT.ridx[size_t(k) * Vs + v]);
+        }
+        __syncthreads();
+        for (int j = tid; j < ntr; j += kTileThreads) D.J_t[tile_base + j] = sum_step_costs<T, false>(D.sc_t, Vs, N, tile_base + j);
+        __syncthreads();
+        // verdicts
+        if (warp == 0) {
+            const int b = b0 + lane;
+            const bool in = b < B;
+            int ph = in ? D.phase[b] : PH_DONE;
+            const int cnt = in ? D.t_count[b] : 0;
+            if (ph == PH_SEARCH && cnt > 0) {
+                trials += cnt;
+                decide_instance(D, b, cnt);
+                ph = D.phase[b];
+            }
+            const unsigned running = __ballot_sync(0xffffffffu, ph != PH_DONE);
+            if (lane == 0) s_ctl[1] = running != 0u;
+        }
+        __syncthreads();
+        if (!s_ctl[1]) {
+            ++rounds;
+            break;
+        }
+    }
+    // commit a step accepted in the last round
+    for (int item = tid; item < 32 * 2 * (N + 1); item += kTileThreads) {
+        const int b = b0 + (item & 31), kp = item >> 5;
+        if (b < B) derivs_item<T, false>(D, b, kp >> 1, kp & 1, 1);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (b0 + lane < B) D.commit_src[b0 + lane] = -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) trials += __shfl_down_sync(0xffffffffu, trials, o);
+        if (lane == 0) {
+            atomicMax(&D.ctl[CTL_ROUND], rounds_before + rounds);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&D.ctl[CTL_TRIALS]), static_cast<unsigned long long>(trials));
+        }
     }
 }
 
@@ -1908,7 +2158,7 @@ __device__ __forceinline__ unsigned long long scan_word(unsigned epoch, unsigned
 
 template <typename T>
 __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsigned epoch) {
-    const size_t Bs = D.Bs, Vs = D.Vs;
+    const size_t Bs = D.Bs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int s_chunk, s_excl, s_wsum[4], s_active, s_trials;
     const int* list = D.act + size_t(par) * Bs;
@@ -1932,61 +2182,8 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
         int ph = in ? D.phase[b] : PH_DONE;
         const int cnt = in ? D.t_count[b] : 0;
         if (ph == PH_SEARCH && cnt > 0) {
-            const DevParams<T>& P = D.P[D.tmpl[b]];
-            const int v0 = D.t_first[b];
-            const int a0 = D.aidx[b];
-            const T J_cur = D.J_cur[b];
-            const T dV0 = D.dV[b], dV1 = D.dV[Bs + b];
-            bool ended = false;
-            T last_J = J_cur;  // cost of the last trial looked at: what iter_step returns when every alpha was rejected (cpp:380)
             my_trials += cnt;
-            // trial costs four at a time (independent loads), then their verdicts in alpha order; the
-            // usual case is a single trial
-            for (int i0 = 0; i0 < cnt && !ended; i0 += 4) {
-            T Jt[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) Jt[q] = i0 + q < cnt ? D.J_t[v0 + i0 + q] : T(0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i0 + q;
-                if (i >= cnt || ended) break;
-                const int v = v0 + i, a = a0 + i;
-                const T new_J = Jt[q];
-                last_J = new_J;
-                const T alpha = T(1) / T(1 << a);
-                const T actual = J_cur - new_J;
-                if (a == 0 && m_fabs(actual) < P.conv_thr) {
-                    D.wide[b] = 0;
-                    end_iteration(D, P, b, ST_CONVERGED, a, new_J);  // trial discarded (cpp:358-361)
-                    ended = true;
-                } else {
-                    const T approx = -(alpha * alpha * dV0 + alpha * dV1);
-                    if (actual > T(0) && (approx < T(0) || actual / approx > P.accept_thr)) {
-                        D.commit_src[b] = v;  // x, u <- new (cpp:113-116), copied by the next derivative stage
-                        D.J_cur[b] = new_J;
-                        D.rec_valid[b] = 0;
-                        D.wide[b] = a > 0;
-                        end_iteration(D, P, b, a == 0 ? ST_RUNNING : ST_SMALL_STEP, a, new_J);
-                        ended = true;
-                    }
-                }
-            }
-            }
-            if (!ended) {
-                if (a0 + cnt >= kNumAlphas) {
-                    if (P.solve_type == 1 && D.mu) {  // cpp:377-378
-                        for (int i = 0; i < D.N * D.alm_cols; ++i)
-                            D.mu[size_t(i) * Bs + b] = D.mu_next[size_t(i) * Bs + b];
-                        D.rho[b] = std_min((1 + P.alm_gamma) * D.rho[b], P.max_rho);
-                        D.rec_valid[b] = 0;
-                    }
-                    D.wide[b] = 1;
-                    end_iteration(D, P, b, ST_FWD_FAIL, -1, last_J);
-                } else {
-                    D.aidx[b] = a0 + cnt;
-                    D.wide[b] = 1;  // alpha = 1 was rejected: evaluate the remaining alphas together
-                }
-            }
+            decide_instance(D, b, cnt);
             ph = D.phase[b];
         }
         my_active += ph != PH_DONE;

@@ -254,6 +254,9 @@ class GlobalConfig {
         if (vis.find("y_lim")) config_map["visualization/y_lim"] = vec(*vis.find("y_lim"));
     }
 
+    // the flat "section/key" map (what the reference's GlobalConfig holds in its private config_map)
+    const std::unordered_map<std::string, std::any>& entries() const { return config_map; }
+
   private:
     static GlobalConfig*& instance() {
         static GlobalConfig* p = nullptr;
