@@ -221,10 +221,6 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *  CILQR_OPT_WIDE_STEP (default 1): in bandwidth-bound rounds an instance in a streak of rejected steps
  *      evaluates 2, 4, 8, 6 more alphas per round instead of all that remain (same decisions, ~18 % fewer
  *      trials; latency-bound rounds keep evaluating all of them at once).
- *  CILQR_OPT_TILE_KERNEL (default 1): a latency-bound batch of up to 148 * 32 instances — and the stragglers of a
- *      larger one once they fit, after a repack — runs the rest of its solve as one persistent CTA per tile of 32
- *      instances (derivatives, backward pass, rollouts + match, costs, verdict inside the CTA, no launches and no
- *      batch-wide synchronisation between iterations); 0 keeps the host-driven rounds throughout.
  *  The regime threshold (CILQR_OPT_PREFETCH_BELOW) is applied per round to the number of instances still
  *      running, so a large batch moves to the latency-regime kernels for its stragglers. */
 typedef enum cilqr_option_t {
@@ -236,8 +232,7 @@ typedef enum cilqr_option_t {
     CILQR_OPT_PIPELINE = 5,
     CILQR_OPT_STAGED_BACKWARD = 6,
     CILQR_OPT_REPACK = 7,
-    CILQR_OPT_WIDE_STEP = 8,
-    CILQR_OPT_TILE_KERNEL = 9
+    CILQR_OPT_WIDE_STEP = 8
 } cilqr_option_t;
 int cilqr_b200_set_option(cilqr_handle_t* h, int option, int value);
 

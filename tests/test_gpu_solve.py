@@ -108,15 +108,13 @@ def test_kernel_variants_return_the_same_bits(cfg, dtype):
     pb = cb.synthetic_batch(cfg, 333, N=50)
     outs = []
     with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, dtype) as s:
-        for threshold, pipe, staged, tiles in ((1 << 30, 0, 1, 0), (1 << 30, 16, 1, 0), (1 << 30, 8, 0, 0), (1 << 30, 1, 0, 0),
-                                               (1 << 30, 1, 1, 0), (0, 1, 1, 0), (100, 1, 1, 0), (1 << 30, 1, 1, 1), (0, 1, 1, 1)):
+        for threshold, pipe, staged in ((1 << 30, 0, 1), (1 << 30, 16, 1), (1 << 30, 8, 0), (1 << 30, 1, 0),
+                                        (1 << 30, 1, 1), (0, 1, 1), (100, 1, 1)):
             # threshold 100: the solve starts on the throughput kernels and moves to the latency ones
-            # (work-list variants) once fewer than 100 instances are still running; tiles: the persistent
-            # one-CTA-per-tile kernel runs the whole loop (the default for batches of this size)
+            # (work-list variants) once fewer than 100 instances are still running
             s.set_option(s.OPT_PREFETCH_BELOW, threshold)
             s.set_option(s.OPT_PIPELINE, pipe)
             s.set_option(s.OPT_STAGED_BACKWARD, staged)
-            s.set_option(s.OPT_TILE_KERNEL, tiles)
             outs.append(s.solve(pb))
     assert int(outs[0].iters.sum()) > pb.B
     for o in outs[1:]:

@@ -5,10 +5,13 @@
 #include "../../include/cilqr_b200.h"
 #include "cilqr_kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,6 +21,15 @@ using namespace cilqr;
 namespace {
 
 thread_local std::string g_err;
+
+// NVTX range for the lifetime of the object (header-only NVTX3: a no-op unless a profiler is attached).  The
+// ranges mark where the host issues each stage K0..K7 of a round, the whole solve, and the copies around it.
+struct Nvtx {
+    explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+    Nvtx(const Nvtx&) = delete;
+    Nvtx& operator=(const Nvtx&) = delete;
+};
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -62,8 +74,6 @@ struct Base {
     int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
     int wide_step = 1; // bandwidth-bound rounds widen a line search step by step (2, 4, 8, 6 alphas) instead of all at once
     int repack = 1;    // survivors moved into a dense prefix whenever they are down to half of the slots in use
-    int tiles = 1;     // latency-bound batches of up to 148 tiles: the whole loop inside one CTA per tile (k_solve_tiles)
-    bool tiles_attr_set = false;
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
@@ -378,6 +388,12 @@ int backward_variant(const Base* h, int n, int B, bool lat) {
     if (sizeof(T) == 4) return 1;
     return n >= 196608 ? 1 : 0;
 }
+// k_backward in the bandwidth regime: 64-thread CTAs.  The kernel is one resident wave (<= 4 CTAs of 128 threads per
+// SM at its register count), so its time is that of the fullest SM: 65536 trajectories in 128-thread CTAs are 512
+// CTAs = 3.46 per SM, i.e. some SMs stream 4 CTAs while the others idle after 3 (measured 0.84-0.91 of the copy
+// bandwidth at that batch against 0.97-1.04 at 262144); at 64 threads the imbalance is one CTA in seven.
+constexpr int kBwThreads = 64;
+inline dim3 bw_grid(int n) { return dim3(std::max(1, std::min((n + kBwThreads - 1) / kBwThreads, 2 * kGridCap))); }
 // k_backward_staged: one warp per tile of 32 instances, at most 16 warps per SM
 inline dim3 staged_grid(int B) { return dim3(std::max(1, std::min((B + 31) / 32, 148 * 16))); }
 // step-parallel stages (k_cost, k_derivs): x = step, y = blocks of trajectories
@@ -663,6 +679,7 @@ template <typename T>
 int do_solve_resident(Impl<T>* h, int Bfull) {
     CK(cudaSetDevice(h->device));
     if (Bfull == 0) return 0;
+    Nvtx solve_range("cilqr solve_resident");
     int B = Bfull;  // slots in use: shrinks when the survivors are repacked into a prefix
     const int N = h->N;
     h->launches = 0;
@@ -673,9 +690,12 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     progress[0] = static_cast<unsigned long long>(unsigned(B));
     progress[1] = static_cast<unsigned long long>(unsigned(B));
     CK(cudaMemsetAsync(h->D.ctl, 0, CTL_WORDS * sizeof(int), h->stream));
-    LAUNCH(h, k_init<T>, gs1(B), 128, h->D, B, -1, 1);
-    launch_cost(h, B, 0, B, B <= h->prefetch_below);
-    LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 0);
+    {
+        Nvtx r("K0 init trajectory + K1/K2 initial cost");
+        LAUNCH(h, k_init<T>, gs1(B), 128, h->D, B, -1, 1);
+        launch_cost(h, B, 0, B, B <= h->prefetch_below);
+        LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 0);
+    }
     // One round = one line-search step for every running instance.  The verdict kernel publishes
     // (rounds completed, instances still running, length of the next work list) into mapped host
     // memory; the host keeps at most run_ahead rounds queued beyond the last count it has seen and
@@ -685,30 +705,6 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // the latency-regime kernels for its stragglers).
     int launched = 0;
     int level = 0, repack_bound[kRepackLevels], repack_off[kRepackLevels + 1] = {0};
-    // Latency-bound batches (and the stragglers of a large one, once they fit): the rest of the solve runs as one
-    // persistent CTA per tile of 32 instances (k_solve_tiles) instead of rounds of launches.
-    const bool tiles_ok = h->tiles && !kParity && !h->any_alm && N + 1 <= kPipeMaxSteps && h->D.Vs / kTileMaxTiles >= 32;
-    bool finished_in_tiles = false;
-    auto run_tiles = [&](int Bt) -> int {
-        const int n_tiles = (Bt + 31) / 32;
-        const int tile_slots = int(std::min<long long>(kTileGroups * kPipeTrials * 2, (long long)h->D.Vs / n_tiles));
-        const size_t smem = tile_smem_bytes<T>(N);
-        if (!h->tiles_attr_set) {
-            CK(cudaFuncSetAttribute(k_solve_tiles<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tile_smem_bytes<T>(kPipeMaxSteps - 1))));
-            h->tiles_attr_set = true;
-        }
-        h->D.wide_step = 0;
-        mark_stage(h, 1);
-        k_solve_tiles<T><<<n_tiles, kTileThreads, smem, h->stream>>>(h->D, Bt, tile_slots, h->max_rounds, launched);
-        h->launches++;
-        mark_stage(h, -1);
-        finished_in_tiles = true;
-        return 0;
-    };
-    if (tiles_ok && B <= kTileMaxTiles * 32) {
-        int rc = run_tiles(B);
-        if (rc) return rc;
-    }
     // the spin below must not outlive a device fault or a stalled kernel: every kSpinCheck polls the stream is
     // queried (a sticky error, or an idle stream whose progress words still say "rounds outstanding", ends the
     // solve with CILQR_ERR_CUDA), and a round that makes no progress for kStallSeconds is reported as a stall
@@ -717,7 +713,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     unsigned spins = 0;
     int last_done = -1;
     auto last_progress = std::chrono::steady_clock::now();
-    while (!finished_in_tiles && launched < h->max_rounds) {
+    while (launched < h->max_rounds) {
         const unsigned long long w = progress[0];
         const int done = int(w >> 32);
         if (done > 0 && unsigned(w) == 0u) break;
@@ -750,26 +746,11 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             ++level;
             B = n_bound;
         }
-        if (tiles_ok && n_bound <= kTileMaxTiles * 32 - 640 && level < kRepackLevels && h->repack) {
-            // the stragglers fit one tile per SM: move them into a dense prefix (unless they are one already) and
-            // let each tile finish on its own
-            if (n_bound < B) {
-                LAUNCH(h, k_plan_repack<T>, dim3(1), kPlanThreads, h->D, launched & 1, level, h->D.swap_src + repack_off[level],
-                       h->D.swap_dst + repack_off[level]);
-                swap_instances(h, level, repack_off[level], n_bound);
-                repack_bound[level] = n_bound;
-                repack_off[level + 1] = repack_off[level] + n_bound;
-                ++level;
-                B = n_bound;
-            }
-            int rc = run_tiles(B);
-            if (rc) return rc;
-            break;
-        }
         const int trial_bound = int(std::min<long long>(h->D.Vs, (long long)n_bound * kNumAlphas));
         const bool lat = n_bound <= h->prefetch_below;
         const int par = launched & 1;  // which of the two work lists this round reads
         mark_stage(h, 0);
+        nvtxRangePushA("K3+K4 derivatives");
         if (lat) {
             LAUNCH_DERIVS(h, -1, gk(n_bound, 2 * (N + 1)), h->D, B, 1, par);
         } else {
@@ -780,19 +761,24 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             LAUNCH_COST(h, 4, gk(B, N + 1), h->D, B, 0);
             LAUNCH(h, k_sum_cost<T>, gs1(B), 128, h->D, B, 1);
         }
+        nvtxRangePop();
         mark_stage(h, 1);
+        nvtxRangePushA("K5 backward pass");
         h->D.wide_step = (!lat && h->wide_step) ? 1 : 0;
         switch (backward_variant<T>(h, n_bound, B, lat)) {
             case 2:  // small batch: one warp per tile of 32 instances, records staged through shared memory
                 LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 1);
                 break;
             case 1:  // a short work list is spread over one warp per scheduler (see k_backward)
-                LAUNCH(h, (k_backward<T, true>), gs1(lat ? std::max(n_bound, 148 * 128) : n_bound), 128, h->D, B, 1, par);
+                if (lat) LAUNCH(h, (k_backward<T, true>), gs1(std::max(n_bound, 148 * 128)), 128, h->D, B, 1, par);
+                else LAUNCH(h, (k_backward<T, true>), bw_grid(n_bound), kBwThreads, h->D, B, 1, par);
                 break;
             default:
-                LAUNCH(h, (k_backward<T, false>), gs1(n_bound), 128, h->D, B, 1, par);
+                LAUNCH(h, (k_backward<T, false>), bw_grid(n_bound), kBwThreads, h->D, B, 1, par);
         }
+        nvtxRangePop();
         mark_stage(h, 2);
+        nvtxRangePushA("K6+K1+K2 rollouts, waypoint match, trial costs");
         // (the parity build keeps to the one-thread rollout: the two-lane kernels split the step's trigonometry
         // in a way that is a few ulp from the reference's sequence)
         const bool piped = !kParity && lat && h->pipeline && N + 1 <= kPipeMaxSteps;
@@ -811,7 +797,9 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             LAUNCH(h, (k_forward<T, true>), gs1(trial_bound), 128, h->D, B, 1);  // rollout + waypoint match
         }
         launch_cost(h, B, 1, trial_bound, lat, piped || !lat || kParity);
+        nvtxRangePop();
         mark_stage(h, 5);
+        Nvtx r7("K7 verdict");
         h->scan_epoch = (h->scan_epoch % 0x3fffffffu) + 1u;
         // one CTA per chunk of the work list, never fewer (no striding): a CTA that went on to a second
         // chunk would wait, in the look-back, on chunks whose CTAs cannot start before it exits
@@ -819,8 +807,8 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         mark_stage(h, -1);
         ++launched;
     }
-    // commit a step accepted in the last round (the tile kernel has done that itself)
-    if (!finished_in_tiles) LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 1, launched & 1);
+    // commit a step accepted in the last round
+    LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 1, launched & 1);
     // every instance back into its own slot
     while (level > 0) {
         --level;
@@ -891,10 +879,21 @@ int do_download(Impl<T>* h, int B, double* u_out, double* x_out, double* J_out, 
     CK(cudaStreamSynchronize(h->stream));
     h->counters.total_iters = 0;
     h->counters.exits[0] = h->counters.exits[1] = h->counters.exits[2] = 0;
+    int it_max = 0;
     for (int b = 0; b < B; ++b) {
         h->counters.total_iters += it[b];
+        it_max = std::max(it_max, it[b]);
         if (ex[b] >= 0 && ex[b] < 3) h->counters.exits[ex[b]]++;
     }
+    // batch summary (the reference logs one line per solve, cpp:128-148; a batch gets one line in all), on request:
+    // CILQR_B200_LOG=1 in the environment
+    static const bool log_summary = [] { const char* e = getenv("CILQR_B200_LOG"); return e && *e && *e != '0'; }();
+    if (log_summary)
+        fprintf(stderr, "[cilqr_b200] %d solves (%s, N=%d): %lld iter_steps (mean %.1f, max %d), %lld line-search trials, "
+                "%d device rounds, %d launches; exits: %d converged, %d max_iter, %d max_lamb\n",
+                B, h->dtype == CILQR_F64 ? "fp64" : "fp32", h->N, (long long)h->counters.total_iters,
+                double(h->counters.total_iters) / std::max(B, 1), it_max, (long long)h->counters.total_trials, h->counters.rounds,
+                h->counters.launches, h->counters.exits[EX_CONVERGED], h->counters.exits[EX_MAX_ITER], h->counters.exits[EX_MAX_LAMB]);
     return 0;
 }
 
@@ -1055,9 +1054,9 @@ int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const 
         if (variant == 2) {
             LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
         } else if (variant == 1) {
-            LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0, 0);
+            LAUNCH(h, (k_backward<T, true>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
         } else {
-            LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
+            LAUNCH(h, (k_backward<T, false>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
         }
     }
     e = cudaStreamSynchronize(h->stream);
@@ -1110,9 +1109,9 @@ int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float
         if (variant == 2) {
             LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
         } else if (variant == 1) {
-            LAUNCH(h, (k_backward<T, true>), gs1(B), 128, h->D, B, 0, 0);
+            LAUNCH(h, (k_backward<T, true>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
         } else {
-            LAUNCH(h, (k_backward<T, false>), gs1(B), 128, h->D, B, 0, 0);
+            LAUNCH(h, (k_backward<T, false>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
         }
         CK(cudaEventRecord(h->t1, h->stream));
         CK(cudaEventSynchronize(h->t1));
@@ -1371,9 +1370,6 @@ int do_set_option(Impl<T>* h, int option, int value) {
             return 0;
         case CILQR_OPT_WIDE_STEP:
             h->wide_step = value ? 1 : 0;
-            return 0;
-        case CILQR_OPT_TILE_KERNEL:
-            h->tiles = value ? 1 : 0;
             return 0;
         case CILQR_OPT_REPACK:
             h->repack = value < 0 ? 0 : value;  // > 1: smallest batch that is still repacked (development)

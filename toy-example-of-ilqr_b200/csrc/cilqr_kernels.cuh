@@ -212,6 +212,23 @@ __device__ __forceinline__ size_t at(size_t stride, int step, int field, int nfi
     return (size_t(step) * nfields + field) * stride + i;
 }
 
+// The per-template solver scalars (2 KB for all templates) copied into shared memory at the start of a kernel:
+// every thread of the step-parallel stages reads a dozen of them behind the load of its instance's template id, and
+// from global memory that is one more level of dependent loads on kernels that are bound by exactly that
+// (ncu, k_derivs / k_cost at 262144 instances: long-scoreboard stalls, 35-45 % of the warps active).
+// Usage: `__shared__ DevParams<T> sP[CILQR_B200_MAX_TEMPLATES]; D.P = stage_params(D, sP);` (D is the kernel's own copy).
+template <typename T>
+__device__ __forceinline__ const DevParams<T>* stage_params(const Dev<T>& D, DevParams<T>* smem) {
+    constexpr int kWords = int(sizeof(DevParams<T>) * CILQR_B200_MAX_TEMPLATES / sizeof(unsigned));
+    static_assert(sizeof(DevParams<T>) % sizeof(unsigned) == 0, "word copy");
+    const unsigned* src = reinterpret_cast<const unsigned*>(D.P);
+    unsigned* dst = reinterpret_cast<unsigned*>(smem);
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x, nt = blockDim.x * blockDim.y;
+    for (int i = tid; i < kWords; i += nt) dst[i] = src[i];
+    __syncthreads();
+    return smem;
+}
+
 // Total cost of trajectory i from its per-step costs sc [kScPlanes][N+1][stride].  Default build: the step
 // totals in step order.  Parity build: the reference's three sums (states, controls, constraints: cpp:211-213,
 // :217-286) each in step order, then (states + controls) + constraints.  kCg: read through L2 (the values
@@ -507,6 +524,8 @@ __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int
 // fence and no atomic per thread).
 template <typename T, int kMinBlocks, bool kAlm>
 __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int trial) {
+    __shared__ DevParams<T> sP[CILQR_B200_MAX_TEMPLATES];
+    D.P = stage_params(D, sP);
     const View<T> V = view_of(D, trial);
     const int count = view_count(D, trial, B);
     const int N = D.N;
@@ -926,6 +945,8 @@ template <typename T, int kPart, bool kAlm>
 #define CILQR_DERIVS1_MINB 8
 #endif
 __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIVS0_MINB : CILQR_DERIVS1_MINB)) k_derivs(Dev<T> D, int B, int masked, int par) {
+    __shared__ DevParams<T> sP[CILQR_B200_MAX_TEMPLATES];
+    D.P = stage_params(D, sP);
     const size_t Bs = D.Bs;
     // two independent halves per (instance, step): part 0 = state terms (l_x, l_xx), part 1 = control
     // terms and model Jacobians (l_u, l_uu, A, B).  kPart < 0: one launch, the half taken from
@@ -1610,6 +1631,8 @@ __global__ void __launch_bounds__(32) k_backward_staged(Dev<T> D, int B, int sol
 // no second pass over the trial pool; the scan of a step is ~9 waypoints at the usual speeds).
 template <typename T, bool kMatch>
 __global__ void __launch_bounds__(128) k_forward(Dev<T> D, int B, int solver) {
+    __shared__ DevParams<T> sP[CILQR_B200_MAX_TEMPLATES];
+    D.P = stage_params(D, sP);
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
     const int count = solver ? view_count(D, 1, B) : B;
@@ -1902,15 +1925,26 @@ __device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kP
         const T* wx = D.wx + Pp->wp_off;
         const T* wy = D.wy + Pp->wp_off;
         int start = 0;
+        // the waypoints of the window a scan will look at next are fetched while it works on the current one: the
+        // scan of a step is a chain of probes, and with a narrow window every probe would otherwise wait for a new
+        // sector of the table (an L2 round trip per probe)
+        auto wp_load = [&](int j0, T* ox, T* oy) {
+            const int jc = j0 + sub < M ? j0 + sub : M - 1;
+            *ox = __ldg(wx + jc);
+            *oy = __ldg(wy + jc);
+        };
+        T cwx, cwy;
+        wp_load(0, &cwx, &cwy);
         for (int k = 0; k <= N; ++k) {
             mbar_wait(smem_addr(&bars[k]), parity);
             const T px = pos[k][slot][0], py = pos[k][slot][1];
             int found = -1;
             bool done = !live;
             while (!__all_sync(0xffffffffu, done)) {
+                T nwx, nwy;
+                wp_load(start + (G - 1), &nwx, &nwy);
                 int j = start + sub;
-                int jc = j < M ? j : M - 1;
-                T dj = wp_dist2(px, py, __ldg(wx + jc), __ldg(wy + jc));
+                T dj = wp_dist2(px, py, cwx, cwy);
                 T dn = __shfl_down_sync(0xffffffffu, dj, 1, G);
                 bool stop = !done && (sub < G - 1) && (j + 1 >= M || !(dn < dj));
                 unsigned m = __ballot_sync(0xffffffffu, stop) & grp_mask;
@@ -1920,9 +1954,12 @@ __device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kP
                         done = true;
                     } else {
                         start += G - 1;
+                        cwx = nwx;
+                        cwy = nwy;
                     }
                 }
             }
+            if (live && found != start) wp_load(found, &cwx, &cwy);  // the next step starts at the match
             if (live) {
                 if (sub == 0) D.ridx_t[size_t(k) * Vs + v] = found;
                 start = found;
@@ -2006,135 +2043,6 @@ __device__ __forceinline__ void decide_instance(const Dev<T>& D, int b, int cnt)
         } else {
             D.aidx[b] = a0 + cnt;
             D.wide[b] = 1;  // alpha = 1 was rejected: evaluate the remaining alphas together
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// The whole solve loop of a tile of 32 consecutive instances inside ONE CTA (latency-bound batches: up to one
-// tile per SM, i.e. 148 * 32 instances).  A round of the host-driven loop is five dependent launches plus a
-// verdict kernel that synchronises the whole batch; here a tile iterates on its own — derivatives, backward pass,
-// rollouts + waypoint match, step costs, verdict, separated by block barriers — until its 32 instances have left
-// the solve, with no launch, no grid-wide dependency and no host involvement in between.  The phases are the
-// device functions the stage kernels are made of (derivs_item, backward_tile, rollout_match_group, step_cost_of,
-// decide_instance), so the results are bit-identical to the host-driven loop
-// (tests/test_gpu_solve.py::test_kernel_variants_return_the_same_bits).
-//   warp 0        backward pass of the tile (lane = instance; records through the bulk-copy ring), verdicts
-//   warps 0-3     rollers of up to four groups of 16 trials (two lanes per trial)
-//   warps 4-11    waypoint scan of those groups (four lanes per trial), trailing the rollers through mbarriers
-//   all warps     derivative records and step costs, one (instance or trial, step) item per thread and pass
-// The tile owns a private region of the trial pool (tile_slots slots from tile * tile_slots).
-// ---------------------------------------------------------------------------
-constexpr int kTileThreads = 384;  // 12 warps: 170 registers per thread, what the staged recursion needs
-constexpr int kTileGroups = 4;
-constexpr int kTileScanG = 4;      // (12 - 4) scan warps * 32 lanes / (4 groups * 16 trials)
-constexpr int kTileMaxTiles = 148;
-
-template <typename T>
-__host__ __device__ constexpr size_t tile_smem_bytes(int N) {
-    return size_t(kStagedStages) * kRecFields * 32 * sizeof(T) + 128 +
-           size_t(kTileGroups) * (N + 1) * kPipeTrials * 2 * sizeof(T) + size_t(kTileGroups) * (N + 1) * 8 + 128;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kTileThreads, 1) k_solve_tiles(Dev<T> D, int B, int tile_slots, int max_rounds, int rounds_before) {
-    extern __shared__ __align__(128) unsigned char tile_smem[];
-    const int N = D.N;
-    const size_t Vs = D.Vs;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, b0 = tile * 32, tile_base = tile * tile_slots;
-    // carve the shared memory
-    unsigned char* p = tile_smem;
-    T(*stage)[kRecFields][32] = reinterpret_cast<T(*)[kRecFields][32]>(p);
-    p += size_t(kStagedStages) * kRecFields * 32 * sizeof(T);
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(p);
-    p += 128;
-    T(*pos_all)[kPipeTrials][2] = reinterpret_cast<T(*)[kPipeTrials][2]>(p);
-    p += size_t(kTileGroups) * (N + 1) * kPipeTrials * 2 * sizeof(T);
-    unsigned long long* bars_all = reinterpret_cast<unsigned long long*>(p);
-    p += size_t(kTileGroups) * (N + 1) * 8;
-    int* s_ctl = reinterpret_cast<int*>(p);  // [0] trial slots in use this round, [1] instances still running
-    if (tid == 0) {
-        for (int q = 0; q < kStagedStages; ++q) mbar_init(smem_addr(&full[q]), 1);
-        for (int q = 0; q < kTileGroups * (N + 1); ++q) mbar_init(smem_addr(&bars_all[q]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    StagedRing<T> R{stage, full, 0u, 0u};
-    // my rollout group: rollers are warps 0..3, group g is scanned by warps 4 + 2g and 5 + 2g
-    const bool roller = warp < kTileGroups;
-    const int grp = roller ? warp : (warp - kTileGroups) >> 1;
-    const int scan_warp = (warp - kTileGroups) & 1;
-    T(*pos)[kPipeTrials][2] = pos_all + size_t(grp) * (N + 1);
-    unsigned long long* bars = bars_all + size_t(grp) * (N + 1);
-    unsigned parity = 0;  // of my group's step barriers
-    const View<T> VT = view_of(D, 1);
-    int rounds = 0;
-    long long trials = 0;
-    for (; rounds < max_rounds; ++rounds) {
-        // derivative records (and the commit of a step accepted in the previous round)
-        for (int item = tid; item < 32 * 2 * (N + 1); item += kTileThreads) {
-            const int b = b0 + (item & 31), kp = item >> 5;
-            if (b < B) derivs_item<T, false>(D, b, kp >> 1, kp & 1, 1);
-        }
-        __syncthreads();
-        // backward pass; the searching instances claim their trial slots
-        if (warp == 0) {
-            const int n = backward_tile(D, R, tile, B, 1, lane, tile_base, tile_slots);
-            if (lane == 0) s_ctl[0] = n;
-        }
-        __syncthreads();
-        const int ntr = s_ctl[0], tr_end = tile_base + ntr;
-        // rollouts + waypoint match, four groups of 16 trials at a time
-        for (int base = tile_base; base < tr_end; base += kTileGroups * kPipeTrials) {
-            const int gbase = base + grp * kPipeTrials;
-            if (gbase < tr_end) {
-                rollout_match_group<T, kTileScanG>(D, pos, bars, parity, gbase, tr_end, roller, scan_warp, lane);
-                parity ^= 1u;
-            }
-            __syncthreads();
-        }
-        // step costs of the trials (lane = trial slot), then their totals
-        for (int item = tid; item < ntr * (N + 1); item += kTileThreads) {
-            const int k = item / ntr, v = tile_base + item % ntr;
-            VT.sc[size_t(k) * Vs + v] = step_cost_of<T, false, 4>(D, VT, D.t_inst[v], v, k, VT.ridx[size_t(k) * Vs + v]);
-        }
-        __syncthreads();
-        for (int j = tid; j < ntr; j += kTileThreads) D.J_t[tile_base + j] = sum_step_costs<T, false>(D.sc_t, Vs, N, tile_base + j);
-        __syncthreads();
-        // verdicts
-        if (warp == 0) {
-            const int b = b0 + lane;
-            const bool in = b < B;
-            int ph = in ? D.phase[b] : PH_DONE;
-            const int cnt = in ? D.t_count[b] : 0;
-            if (ph == PH_SEARCH && cnt > 0) {
-                trials += cnt;
-                decide_instance(D, b, cnt);
-                ph = D.phase[b];
-            }
-            const unsigned running = __ballot_sync(0xffffffffu, ph != PH_DONE);
-            if (lane == 0) s_ctl[1] = running != 0u;
-        }
-        __syncthreads();
-        if (!s_ctl[1]) {
-            ++rounds;
-            break;
-        }
-    }
-    // commit a step accepted in the last round
-    for (int item = tid; item < 32 * 2 * (N + 1); item += kTileThreads) {
-        const int b = b0 + (item & 31), kp = item >> 5;
-        if (b < B) derivs_item<T, false>(D, b, kp >> 1, kp & 1, 1);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        if (b0 + lane < B) D.commit_src[b0 + lane] = -1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) trials += __shfl_down_sync(0xffffffffu, trials, o);
-        if (lane == 0) {
-            atomicMax(&D.ctl[CTL_ROUND], rounds_before + rounds);
-            atomicAdd(reinterpret_cast<unsigned long long*>(&D.ctl[CTL_TRIALS]), static_cast<unsigned long long>(trials));
         }
     }
 }
