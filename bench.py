@@ -38,13 +38,13 @@ METRIC = "ilqr_iterations_per_sec"
 UNIT = "iterations/s"
 WORKLOAD = "C1: batch=4096 randomized scenario_two_straight instances per GPU, N=50, nx=4, nu=2"
 ROOFLINE_BATCH = 262144
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_backward<double,true> (the variant the
-# solver uses at this batch) at B=262144, N=50, from the committed `ncu --set full` capture
-# (profiles/r01b_ncu_full_summary.txt): 2.9676 GB read + 1.0291 GB written = 0.994 x the algorithmic
-# 4.0223 GB.  Only valid for that dtype / batch.
-ROOFLINE_TRAFFIC_BYTES = {"f64": 2.967610e9 + 1.029079e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_backward<T, true> (the variant the solver uses at this
+# batch) at B = 262144, N = 50, from the committed `ncu --set full` captures of this round's kernel
+# (profiles/r02_k5_ncu_summary.txt): fp64 2.9675 GB read + 1.0297 GB written = 0.994 x the algorithmic 4.0223 GB;
+# fp32 1.4941 + 0.5156 GB = 0.999 x 2.0112 GB.  Only valid for that batch.
+ROOFLINE_TRAFFIC_BYTES = {"f64": 3.9972e9, "f32": 2.0098e9}
 ROOFLINE_TRAFFIC_SOURCE = ("constant from the committed ncu --set full capture of this kernel at this batch "
-                           "(profiles/r01b_ncu_full_summary.txt), not measured in this run")
+                           "(profiles/r02_k5_ncu_summary.txt), not measured in this run")
 # the other BASELINE configs, one GPU's share each, device-generated; (config, instances, dtype)
 EXTRA_CONFIGS = [("C1", 65536, "f64"), ("C1", 262144, "f64"), ("C2", 262144, "f64"), ("C3", 131072, "f64"),
                  ("C4", 131072, "f32")]
@@ -366,11 +366,10 @@ def main():
     solver.close()
 
     # ---- roofline: K5 alone at a batch larger than L2 (rank 0) ---------------------------------------
-    roofline = None
-    if rank == 0 and not args.no_roofline:
+    def roofline_leg(dtype):
         peak, peak_src = measured_peak()
         Br = ROOFLINE_BATCH
-        rs = cb.BatchSolver(pb.templates, Br, N, pb.max_obs, args.dtype, device=local)
+        rs = cb.BatchSolver(pb.templates, Br, N, pb.max_obs, dtype, device=local)
         seed = cb.synthetic_batch("C1", 4096, N=N)
         u0, x0 = rs.stage_init(seed.x0, seed.tmpl)
         rs.stage_derivs(seed, u0, x0)          # real l_*, A, B of iteration 0 (K3 + K4)
@@ -379,14 +378,20 @@ def main():
         ms, nbytes = rs.bench_backward(Br, 0.0, 20, True)
         rs.close()
         achieved = nbytes / (float(np.mean(ms)) * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_backward<T, prefetch> (backward_pass Riccati recursion, cpp:383-440)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ROOFLINE_TRAFFIC_BYTES.get(args.dtype),
-                    "traffic_source": ROOFLINE_TRAFFIC_SOURCE if args.dtype in ROOFLINE_TRAFFIC_BYTES else None,
-                    "peak_source": peak_src,
-                    "bytes_per_launch": nbytes, "ms_per_launch": float(np.mean(ms)),
-                    "batch": Br, "layout": "compact record, (38*N+18)*sizeof(T) bytes per trajectory",
-                    "frac_of_nominal_8000": achieved / 8000.0}
+        return {"bound": "hbm", "kernel": "k_backward<T, prefetch> (backward_pass Riccati recursion, cpp:383-440)",
+                "dtype": dtype, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ROOFLINE_TRAFFIC_BYTES.get(dtype),
+                "traffic_source": ROOFLINE_TRAFFIC_SOURCE if dtype in ROOFLINE_TRAFFIC_BYTES else None,
+                "peak_source": peak_src,
+                "bytes_per_launch": nbytes, "ms_per_launch": float(np.mean(ms)),
+                "batch": Br, "layout": "compact record, (38*N+18)*sizeof(T) bytes per trajectory",
+                "frac_of_nominal_8000": achieved / 8000.0}
+
+    roofline = roofline_f32 = None
+    if rank == 0 and not args.no_roofline:
+        roofline = roofline_leg(args.dtype)
+        if args.dtype == "f64" and world == 1:
+            roofline_f32 = roofline_leg("f32")  # BASELINE's "roofline run" (C4) is fp32: the same kernel in that type
 
     # ---- the other BASELINE configs (rank 0, one GPU's share each) and, under N > 1, config C3 sharded over
     # the ranks with a cross-rank bit-equality check -------------------------------------------------------
@@ -444,6 +449,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": 1e3 * t_e2e / max(args.steps, 1)},
             "gpu_launches": launches,
             "roofline": roofline,
+            "roofline_f32": roofline_f32,
             "in_step": in_step,
             "cpu_baseline": cpu,
             "configs": configs,

@@ -61,7 +61,11 @@ def test_init_and_forward(cfg, B, N, dtype):
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 def test_ref_match_cost_derivs(cfg, B, N, dtype):
     pb = cb.synthetic_batch(cfg, B, N=N)
-    u, x = perturbed_trajectories(pb, seed=5)
+    # (fp32 on long horizons: gentler random controls, so that the trajectories stay within a few metres of the road and
+    # the fp32 barrier terms stay finite; overflowed terms — inf and the reference's 0 * inf = NaN entries — are
+    # compared in the fp64 runs of the same shapes)
+    g = min(1.0, 50.0 / N) if dtype == "f32" else 1.0
+    u, x = perturbed_trajectories(pb, seed=5, scale=(0.8 * g, 0.03 * g))
     with _solver(pb, dtype) as s:
         idx = s.stage_ref_match(x, pb.tmpl)
         J, sc = s.stage_cost(pb, u, x)

@@ -752,16 +752,19 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
         // every product (cpp:696-698): 0 for a finite barrier weight, NaN for one that overflowed (0 * inf).
         // Summed per constraint family and added below to the entries that family does not otherwise touch,
         // so that an overflowing barrier poisons the same entries as in the reference.
-        T zV = 0, zB = 0, zO = 0;
+        T zV = 0, zB = 0, zO = 0;     // gradient side (weights g)
+        T zVh = 0, zBh = 0, zOh = 0;  // Hessian side (weights h = q2 g can overflow where g has not)
         T g, h;
         constraint_weights(alm, cv[0], P.st_q1, P.st_q2, rho, alm ? mu[size_t(4) * Bs] : T(0), &g, &h);
         gx[2] += g;
         H[7] += h;
-        zV += g + h;
+        zV += g;
+        zVh += h;
         constraint_weights(alm, cv[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(5) * Bs] : T(0), &g, &h);
         gx[2] += -g;
         H[7] += h;
-        zV += g + h;
+        zV += g;
+        zVh += h;
         // road borders: c_dot = +-(px-rx, py-ry)/hypot, flipped when d_sign < 0 (cpp:527-533)
         T d_sign, hyp;
         T cur_d = lateral_offset(x[0], x[1], rx, ry, D.wsin[P.wp_off + ri], D.wcos[P.wp_off + ri], &d_sign, &hyp);
@@ -777,14 +780,16 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
         H[0] += h * (n0 * n0);
         H[1] += h * (n0 * n1);
         H[4] += h * (n1 * n1);
-        zB += g + h;
+        zB += g;
+        zBh += h;
         constraint_weights(alm, cp[1], P.st_q1, P.st_q2, rho, alm ? mu[size_t(7) * Bs] : T(0), &g, &h);
         gx[0] += g * (-n0);
         gx[1] += g * (-n1);
         H[0] += h * (n0 * n0);
         H[1] += h * (n0 * n1);
         H[4] += h * (n1 * n1);
-        zB += g + h;
+        zB += g;
+        zBh += h;
         if (alm) {
             mun[size_t(4) * Bs] = std_min(std_max(mu[size_t(4) * Bs] + rho * cv[0], T(0)), P.max_mu);
             mun[size_t(5) * Bs] = std_min(std_max(mu[size_t(5) * Bs] + rho * cv[1], T(0)), P.max_mu);
@@ -826,7 +831,10 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
                     tH[q][3] = hf * (gfy * gfy) + hr * (gry * gry);
                     tH[q][4] = hf * (gfy * f3) + hr * (gry * r3);
                     tH[q][5] = hf * (f3 * f3) + hr * (r3 * r3);
-                    if (q == 0 || two) zO += (gf + hf) + (gr + hr);
+                    if (q == 0 || two) {
+                        zO += gf + gr;
+                        zOh += hf + hr;
+                    }
                     if (alm && (q == 0 || two)) {
                         mun[size_t(8 + 2 * jj) * Bs] =
                             std_min(std_max(mu[size_t(8 + 2 * jj) * Bs] + rho * cf, T(0)), P.max_mu);
@@ -854,21 +862,24 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
         zV *= T(0);
         zB *= T(0);
         zO *= T(0);
+        zVh *= T(0);
+        zBh *= T(0);
+        zOh *= T(0);
         gx[0] += zV;
         gx[1] += zV;
         gx[2] += zB + zO;
         gx[3] += zV + zB;
-        const T zVB = zV + zB, zAll = zVB + zO;
-        H[0] += zV;       // 00
-        H[1] += zV;       // 01
-        H[2] += zAll;     // 02
-        H[3] += zVB;      // 03
-        H[4] += zV;       // 11
-        H[5] += zAll;     // 12
-        H[6] += zVB;      // 13
-        H[7] += zB + zO;  // 22
-        H[8] += zAll;     // 23
-        H[9] += zVB;      // 33
+        const T zVB = zVh + zBh, zAll = zVB + zOh;
+        H[0] += zVh;        // 00
+        H[1] += zVh;        // 01
+        H[2] += zAll;       // 02
+        H[3] += zVB;        // 03
+        H[4] += zVh;        // 11
+        H[5] += zAll;       // 12
+        H[6] += zVB;        // 13
+        H[7] += zBh + zOh;  // 22
+        H[8] += zAll;       // 23
+        H[9] += zVB;        // 33
     }
     // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
 #pragma unroll
@@ -909,11 +920,12 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             constraint_weights(alm, c[m], P.st_q1, P.st_q2, rho, alm ? mu[size_t(m) * Bs] : T(0), &g[m], &h[m]);
         // (zA / zS: the zero entries of c_dot, as in the state half: an overflowed acceleration barrier
         // poisons the steering entries and vice versa, both poison the off-diagonal)
-        const T zA = ((g[0] + h[0]) + (g[1] + h[1])) * T(0), zS = ((g[2] + h[2]) + (g[3] + h[3])) * T(0);
+        const T zA = (g[0] + g[1]) * T(0), zS = (g[2] + g[3]) * T(0);
+        const T zAh = (h[0] + h[1]) * T(0), zSh = (h[2] + h[3]) * T(0);
         T gu0 = (g[0] + (-g[1])) + zS;
         T gu1 = (g[2] + (-g[3])) + zA;
-        T hu0 = (h[0] + h[1]) + zS;
-        T hu1 = (h[2] + h[3]) + zA;
+        T hu0 = (h[0] + h[1]) + zSh;
+        T hu1 = (h[2] + h[3]) + zAh;
         if (alm) {
             T* mun = D.mu_next + size_t(k) * D.alm_cols * Bs + b;
 #pragma unroll
@@ -923,7 +935,7 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
         rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu0;
         rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu1;
         rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + hu0;
-        rec[(kRecLuu + 1) * kRecFS] = zA + zS;
+        rec[(kRecLuu + 1) * kRecFS] = zAh + zSh;
         rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + hu1;
 #endif
         T ja[5], jb[4];

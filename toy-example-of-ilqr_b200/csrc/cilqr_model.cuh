@@ -106,6 +106,12 @@ __device__ __forceinline__ float ld_early(const float* p) {
     return v;
 }
 
+__device__ __forceinline__ int ld_early(const int* p) {
+    int v;
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // std::max / std::min semantics (NaN in the first argument is kept), as the
 // reference uses them (cpp:82, :120, :378, :623).
 template <typename T>
