@@ -200,35 +200,42 @@ def run_reference(args):
 
 def run_config(cb, cfg, B, dtype, device, first_id=0, reps=2, k5=True):
     """One GPU's share of a BASELINE config, generated on the device: best-of-`reps` resident solve (wall clock
-    around cilqr_b200_solve_resident, which synchronises) and the backward-pass kernel alone on the records the
-    solve left behind (L2 flushed, CUDA events)."""
+    around cilqr_b200_solve_resident, which synchronises) and — k5 — the backward-pass kernel alone (L2 flushed, CUDA
+    events) on the derivative records of the FIRST iteration of that workload at lambda = 0, with the fraction of
+    instances whose recursion runs all N steps (the reference's recursion stops at a non-PD Q_uu, cpp:415-420: an
+    instance that stops early moves fewer bytes than the algorithmic count, so the GB/s of a config where many
+    stop is a lower bound on what the kernel streams)."""
     spec = cb.synth_spec(cfg)
     N = spec.N
+    line = {"config": cfg, "instances": B, "N": N, "dtype": dtype}
     with cb.BatchSolver(spec.templates, B, N, spec.max_obs, dtype, device=device) as s:
+        if k5:
+            for t, td in enumerate(spec.templates):
+                s.set_template(t, dict(td.params, max_iter=1))
+            s.generate(spec, B, first_id=first_id)
+            s.solve_resident(B)  # one iter_step: leaves the records of the initial trajectories
+            ms, nbytes = s.bench_backward(B, 0.0, 8, True)
+            done = s.download(B, want_gains=False).status
+            for t, td in enumerate(spec.templates):
+                s.set_template(t, td.params)
+            line["k5_GBps"] = round(nbytes / float(np.median(ms)) / 1e6)
+            line["k5_bytes_per_trajectory"] = (38 * N + 18) * (8 if dtype == "f64" else 4)
+            line["k5_full_recursions"] = round(float((done == 0).mean()), 4)
         s.generate(spec, B, first_id=first_id)
         best = None
-        for _ in range(reps + 1):  # first solve = warm-up
+        for i in range(reps + 1):  # first solve = warm-up
             t0 = time.perf_counter()
             s.solve_resident(B)
             dt = time.perf_counter() - t0
-            if _ > 0:
+            if i > 0:
                 best = dt if best is None else min(best, dt)
         c = s.counters()
         head = s.download(min(B, CHECK_SLICE), want_gains=False)
-        iters = c["total_iters"] if c["total_iters"] else None
-        # total iterations of the whole batch: counters are filled by download (first `n` instances only), so
-        # read them from the device-side per-instance counts through a full-status download
-        import numpy as np
         st = s.download_counts(B)
-        line = {"config": cfg, "instances": B, "N": N, "dtype": dtype, "solve_ms": round(best * 1e3, 2),
-                "iter_steps": int(st["iters"]), "iterations_per_s": round(st["iters"] / best),
-                "rounds": c["rounds"], "trials": c["total_trials"], "launches": c["launches"],
-                "exits": st["exits"], "data": "generated on the device (cilqr_b200_synth_generate)"}
-        if k5:
-            sz = 8 if dtype == "f64" else 4
-            ms, nbytes = s.bench_backward(B, 0.0, 8, True)
-            line["k5_GBps"] = round(nbytes / float(np.median(ms)) / 1e6)
-            line["k5_bytes_per_trajectory"] = (38 * N + 18) * sz
+        line.update({"solve_ms": round(best * 1e3, 2), "iter_steps": int(st["iters"]),
+                     "iterations_per_s": round(st["iters"] / best), "rounds": c["rounds"], "trials": c["total_trials"],
+                     "launches": c["launches"], "exits": st["exits"],
+                     "data": "generated on the device (cilqr_b200_synth_generate)"})
     return line, head
 
 

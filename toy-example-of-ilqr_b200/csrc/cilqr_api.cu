@@ -392,7 +392,7 @@ int backward_variant(const Base* h, int n, int B, bool lat) {
 // SM at its register count), so its time is that of the fullest SM: 65536 trajectories in 128-thread CTAs are 512
 // CTAs = 3.46 per SM, i.e. some SMs stream 4 CTAs while the others idle after 3 (measured 0.84-0.91 of the copy
 // bandwidth at that batch against 0.97-1.04 at 262144); at 64 threads the imbalance is one CTA in seven.
-constexpr int kBwThreads = 64;
+static const int kBwThreads = [] { const char* e = getenv("CILQR_BW_THREADS"); const int v = e ? atoi(e) : 0; return (v == 32 || v == 64 || v == 128) ? v : 64; }();
 inline dim3 bw_grid(int n) { return dim3(std::max(1, std::min((n + kBwThreads - 1) / kBwThreads, 2 * kGridCap))); }
 // k_backward_staged: one warp per tile of 32 instances, at most 16 warps per SM
 inline dim3 staged_grid(int B) { return dim3(std::max(1, std::min((B + 31) / 32, 148 * 16))); }

@@ -70,7 +70,23 @@ constexpr int kScPlanes = 4;  // plane 0: step total; 1: state term; 2: control 
 // arithmetic), a warp of consecutive instances still reads a fully coalesced row per field, and one
 // step's record of a whole tile is one contiguous 28 * 32 * sizeof(T) block — one bulk copy.
 constexpr int kRecTile = 32;
-constexpr int kRecFS = kRecTile;  // field stride in scalars
+// fp64: field c of an instance sits rf(c) = 32 c scalars after its field 0 (a warp reads one 256-byte row per field).
+// fp32 (fast build): fields are interleaved in groups of four — [field quad][instance][4] — so that a lane fetches four
+// fields of its instance with ONE 128-bit load and a warp still reads contiguous 512-byte rows: the fp32 recursion is
+// bound by its instruction stream (ncu: issue slots 55 % active at 76 % of DRAM throughput with 4-byte loads), and this
+// quarters its load instructions.  28 fields = 7 quads.  rl() = scalars between consecutive instances of a tile.
+template <typename T>
+__host__ __device__ constexpr bool rec_quads() {
+#ifdef CILQR_PARITY
+    return false;
+#else
+    return sizeof(T) == 4;
+#endif
+}
+template <typename T>
+__host__ __device__ constexpr int rl() { return rec_quads<T>() ? 4 : 1; }
+template <typename T>
+__host__ __device__ constexpr int rf(int c) { return rec_quads<T>() ? (c >> 2) * (4 * kRecTile) + (c & 3) : c * kRecTile; }
 
 constexpr int kNumAlphas = 20;  // alpha = 2^0 .. 2^-19  (cpp:354)
 constexpr int kRepackLevels = 10;
@@ -201,11 +217,11 @@ __device__ __forceinline__ int view_count(const Dev<T>& D, int trial, int B) {
     return nv < D.Vs ? nv : D.Vs;
 }
 
-// field 0 of the record of step k of instance b; field c is kRecFS * c scalars further on, the same
+// field 0 of the record of step k of instance b; field c is rf<T>(c) scalars further on, the same
 // instance's step k - 1 is kRecFields * Bs scalars back
 template <typename T>
 __device__ __forceinline__ T* rec_at(const Dev<T>& D, int k, int b) {
-    return D.rec + (size_t(k) * (D.Bs / kRecTile) + size_t(b / kRecTile)) * (kRecFields * kRecTile) + (b % kRecTile);
+    return D.rec + (size_t(k) * (D.Bs / kRecTile) + size_t(b / kRecTile)) * (kRecFields * kRecTile) + (b % kRecTile) * rl<T>();
 }
 
 __device__ __forceinline__ size_t at(size_t stride, int step, int field, int nfields, int i) {
@@ -735,11 +751,11 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
         }
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
+    for (int c = 0; c < 4; ++c) rec[rf<T>(kRecLx + c)] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
 #pragma unroll
     for (int c = 0; c < 4; ++c) Hx[c * 4 + c] = 2 * P.Q[c] + Hx[c * 4 + c];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) rec[(kRecLxx + c) * kRecFS] = Hx[c];
+    for (int c = 0; c < 16; ++c) rec[rf<T>(kRecLxx + c)] = Hx[c];
 #else
     T gx[4] = {0, 0, 0, 0};
     T H[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 00 01 02 03 11 12 13 22 23 33
@@ -883,13 +899,13 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
     }
     // prime objective: l_x = 2 (x - ref) Q, l_xx = 2 Q (cpp:493-494), summed with the constraint part
 #pragma unroll
-    for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
+    for (int c = 0; c < 4; ++c) rec[rf<T>(kRecLx + c)] = 2 * (x[c] - ref[c]) * P.Q[c] + gx[c];
     H[0] += 2 * P.Q[0];
     H[4] += 2 * P.Q[1];
     H[7] += 2 * P.Q[2];
     H[9] += 2 * P.Q[3];
 #pragma unroll
-    for (int c = 0; c < 10; ++c) rec[(kRecLxx + c) * kRecFS] = H[c];
+    for (int c = 0; c < 10; ++c) rec[rf<T>(kRecLxx + c)] = H[c];
 #endif
     }  // part 0
 
@@ -908,11 +924,11 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             for (int m = 0; m < 4; ++m)
                 mun[size_t(m) * Bs] = std_min(std_max(mu[size_t(m) * Bs] + rho * c[m], T(0)), P.max_mu);
         }
-        rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu[0];
-        rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu[1];
-        rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + Hu[0];
-        rec[(kRecLuu + 1) * kRecFS] = Hu[1];
-        rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + Hu[3];
+        rec[rf<T>(kRecLu + 0)] = 2 * (ua * P.R[0]) + gu[0];
+        rec[rf<T>(kRecLu + 1)] = 2 * (us * P.R[1]) + gu[1];
+        rec[rf<T>(kRecLuu + 0)] = 2 * P.R[0] + Hu[0];
+        rec[rf<T>(kRecLuu + 1)] = Hu[1];
+        rec[rf<T>(kRecLuu + 2)] = 2 * P.R[1] + Hu[3];
 #else
         T g[4], h[4];
 #pragma unroll
@@ -932,18 +948,18 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             for (int m = 0; m < 4; ++m)
                 mun[size_t(m) * Bs] = std_min(std_max(mu[size_t(m) * Bs] + rho * c[m], T(0)), P.max_mu);
         }
-        rec[(kRecLu + 0) * kRecFS] = 2 * (ua * P.R[0]) + gu0;
-        rec[(kRecLu + 1) * kRecFS] = 2 * (us * P.R[1]) + gu1;
-        rec[(kRecLuu + 0) * kRecFS] = 2 * P.R[0] + hu0;
-        rec[(kRecLuu + 1) * kRecFS] = zAh + zSh;
-        rec[(kRecLuu + 2) * kRecFS] = 2 * P.R[1] + hu1;
+        rec[rf<T>(kRecLu + 0)] = 2 * (ua * P.R[0]) + gu0;
+        rec[rf<T>(kRecLu + 1)] = 2 * (us * P.R[1]) + gu1;
+        rec[rf<T>(kRecLuu + 0)] = 2 * P.R[0] + hu0;
+        rec[rf<T>(kRecLuu + 1)] = zAh + zSh;
+        rec[rf<T>(kRecLuu + 2)] = 2 * P.R[1] + hu1;
 #endif
         T ja[5], jb[4];
         model_jacobians(x[2], x[3], us, P.dt, P.wheelbase, P.ref_point, ja, jb);
 #pragma unroll
-        for (int c2 = 0; c2 < 5; ++c2) rec[(kRecA + c2) * kRecFS] = ja[c2];
+        for (int c2 = 0; c2 < 5; ++c2) rec[rf<T>(kRecA + c2)] = ja[c2];
 #pragma unroll
-        for (int c2 = 0; c2 < 4; ++c2) rec[(kRecB + c2) * kRecFS] = jb[c2];
+        for (int c2 = 0; c2 < 4; ++c2) rec[rf<T>(kRecB + c2)] = jb[c2];
     }
 }
 
@@ -1009,19 +1025,19 @@ __device__ __forceinline__ void end_iteration(const Dev<T>& D, const DevParams<T
     }
 }
 
-// V_xx at the horizon = l_xx[N] (cpp:395-396), from the record's l_xx fields (stride kRecFS)
+// V_xx at the horizon = l_xx[N] (cpp:395-396), from the record's l_xx fields (offsets rf<T>)
 template <typename T>
 __device__ __forceinline__ void load_terminal_V(const T* rec, T* V) {
 #ifdef CILQR_PARITY
 #pragma unroll
-    for (int c = 0; c < 16; ++c) V[c] = rec[(kRecLxx + c) * kRecFS];
+    for (int c = 0; c < 16; ++c) V[c] = rec[rf<T>(kRecLxx + c)];
 #else
     int e = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = r; c < 4; ++c, ++e) {
-            const T v = rec[(kRecLxx + e) * kRecFS];
+            const T v = rec[rf<T>(kRecLxx + e)];
             V[r * 4 + c] = v;
             V[c * 4 + r] = v;
         }
@@ -1296,6 +1312,31 @@ __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T&
 
 #endif
 
+// The 28 (34) fields of one record into registers, from global or shared memory (p = the instance's field 0).
+// fp32 quad layout: seven 128-bit loads.  kEarly: issued where written (software prefetch, see ld_early).
+__device__ __forceinline__ float4 ld_early4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+template <typename T, bool kEarly>
+__device__ __forceinline__ void load_record(const T* p, T* r) {
+    if constexpr (rec_quads<T>()) {
+        static_assert(!rec_quads<T>() || kRecFields % 4 == 0, "whole quads");
+#pragma unroll
+        for (int q = 0; q < kRecFields / 4; ++q) {
+            const float4 v = kEarly ? ld_early4(p + q * (4 * kRecTile)) : *reinterpret_cast<const float4*>(p + q * (4 * kRecTile));
+            r[4 * q + 0] = v.x;
+            r[4 * q + 1] = v.y;
+            r[4 * q + 2] = v.z;
+            r[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < kRecFields; ++c) r[c] = kEarly ? ld_early(p + rf<T>(c)) : p[rf<T>(c)];
+    }
+}
+
 // The Riccati recursion of one trajectory.  Streams the 28-scalar record of each
 // step (l_x 4, l_xx 10, l_u 2, l_uu 3, A 5, B 4) and writes K (8) and d (2):
 // (38 N + 18) * sizeof(T) algorithmic bytes per trajectory.  Q_uu + lambda*I is
@@ -1309,17 +1350,13 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
     const T* rec = rec_at(D, N, b);
     T Vx[4], V[kVN];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) Vx[c] = rec[(kRecLx + c) * kRecFS];
+    for (int c = 0; c < 4; ++c) Vx[c] = rec[rf<T>(kRecLx + c)];
     load_terminal_V(rec, V);
     T dV0 = 0, dV1 = 0;
     bool failed = false;
     int i = N - 1;
     T nxt[kRecFields];
-    if (kPrefetch) {
-        const T* p = rec - size_t(kRecFields) * Bs;
-#pragma unroll
-        for (int c = 0; c < kRecFields; ++c) nxt[c] = ld_early(p + c * kRecFS);
-    }
+    if (kPrefetch) load_record<T, true>(rec - size_t(kRecFields) * Bs, nxt);
     for (; i >= 0; --i) {
         rec -= size_t(kRecFields) * Bs;
         T r[kRecFields];
@@ -1327,12 +1364,9 @@ __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
             // record of step i was fetched during step i+1; fetch step i-1 now (latency-bound batches)
 #pragma unroll
             for (int c = 0; c < kRecFields; ++c) r[c] = nxt[c];
-            const T* p = rec - size_t(i > 0 ? kRecFields : 0) * Bs;
-#pragma unroll
-            for (int c = 0; c < kRecFields; ++c) nxt[c] = ld_early(p + c * kRecFS);
+            load_record<T, true>(rec - size_t(i > 0 ? kRecFields : 0) * Bs, nxt);
         } else {
-#pragma unroll
-            for (int c = 0; c < kRecFields; ++c) r[c] = rec[c * kRecFS];
+            load_record<T, false>(rec, r);
         }
         T K[8], d0, d1;
         if (!riccati_step(r, lamb, Vx, V, dV0, dV1, K, d0, d1)) {
@@ -1567,7 +1601,7 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
         {
             const T* rec = rec_at(D, N, in ? b : 0);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) Vx[c] = rec[(kRecLx + c) * kRecFS];
+            for (int c = 0; c < 4; ++c) Vx[c] = rec[rf<T>(kRecLx + c)];
             load_terminal_V(rec, V);
         }
         T dV0 = 0, dV1 = 0;
@@ -1583,8 +1617,7 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
                 T K[8] = {0, 0, 0, 0, 0, 0, 0, 0}, d0 = 0, d1 = 0;
                 if (ok) {
                     T r[kRecFields];
-#pragma unroll
-                    for (int c = 0; c < kRecFields; ++c) r[c] = R.stage[s][c][lane];
+                    load_record<T, false>(&R.stage[s][0][0] + lane * rl<T>(), r);
                     ok = riccati_step(r, lamb, Vx, V, dV0, dV1, K, d0, d1);
                     if (!ok) {
                         // rows not reached stay zero, as in the reference (cpp:392-393, :418)
@@ -2261,33 +2294,33 @@ __global__ void k_records_from_dense(Dev<T> D, int B, const double* lx, const do
     T* rec = rec_at(D, k, b);
     const double* px = lx + (size_t(b) * (N + 1) + k) * 4;
     const double* pxx = lxx + (size_t(b) * (N + 1) + k) * 16;
-    for (int c = 0; c < 4; ++c) rec[(kRecLx + c) * kRecFS] = T(px[c]);
+    for (int c = 0; c < 4; ++c) rec[rf<T>(kRecLx + c)] = T(px[c]);
 #ifdef CILQR_PARITY
-    for (int e = 0; e < 16; ++e) rec[(kRecLxx + e) * kRecFS] = T(pxx[e]);
+    for (int e = 0; e < 16; ++e) rec[rf<T>(kRecLxx + e)] = T(pxx[e]);
 #else
     int e = 0;
     for (int r = 0; r < 4; ++r)
-        for (int c = r; c < 4; ++c, ++e) rec[(kRecLxx + e) * kRecFS] = T(pxx[r * 4 + c]);
+        for (int c = r; c < 4; ++c, ++e) rec[rf<T>(kRecLxx + e)] = T(pxx[r * 4 + c]);
 #endif
     if (k < N) {
         const double* pu = lu + (size_t(b) * N + k) * 2;
         const double* puu = luu + (size_t(b) * N + k) * 4;
         const double* pa = A + (size_t(b) * N + k) * 16;
         const double* pb = Bm + (size_t(b) * N + k) * 8;
-        rec[(kRecLu + 0) * kRecFS] = T(pu[0]);
-        rec[(kRecLu + 1) * kRecFS] = T(pu[1]);
-        rec[(kRecLuu + 0) * kRecFS] = T(puu[0]);
-        rec[(kRecLuu + 1) * kRecFS] = T(puu[1]);
-        rec[(kRecLuu + 2) * kRecFS] = T(puu[3]);
-        rec[(kRecA + 0) * kRecFS] = T(pa[0 * 4 + 2]);
-        rec[(kRecA + 1) * kRecFS] = T(pa[0 * 4 + 3]);
-        rec[(kRecA + 2) * kRecFS] = T(pa[1 * 4 + 2]);
-        rec[(kRecA + 3) * kRecFS] = T(pa[1 * 4 + 3]);
-        rec[(kRecA + 4) * kRecFS] = T(pa[3 * 4 + 2]);
-        rec[(kRecB + 0) * kRecFS] = T(pb[0 * 2 + 1]);
-        rec[(kRecB + 1) * kRecFS] = T(pb[1 * 2 + 1]);
-        rec[(kRecB + 2) * kRecFS] = T(pb[2 * 2 + 0]);
-        rec[(kRecB + 3) * kRecFS] = T(pb[3 * 2 + 1]);
+        rec[rf<T>(kRecLu + 0)] = T(pu[0]);
+        rec[rf<T>(kRecLu + 1)] = T(pu[1]);
+        rec[rf<T>(kRecLuu + 0)] = T(puu[0]);
+        rec[rf<T>(kRecLuu + 1)] = T(puu[1]);
+        rec[rf<T>(kRecLuu + 2)] = T(puu[3]);
+        rec[rf<T>(kRecA + 0)] = T(pa[0 * 4 + 2]);
+        rec[rf<T>(kRecA + 1)] = T(pa[0 * 4 + 3]);
+        rec[rf<T>(kRecA + 2)] = T(pa[1 * 4 + 2]);
+        rec[rf<T>(kRecA + 3)] = T(pa[1 * 4 + 3]);
+        rec[rf<T>(kRecA + 4)] = T(pa[3 * 4 + 2]);
+        rec[rf<T>(kRecB + 0)] = T(pb[0 * 2 + 1]);
+        rec[rf<T>(kRecB + 1)] = T(pb[1 * 2 + 1]);
+        rec[rf<T>(kRecB + 2)] = T(pb[2 * 2 + 0]);
+        rec[rf<T>(kRecB + 3)] = T(pb[3 * 2 + 1]);
     }
 }
 
@@ -2302,14 +2335,14 @@ __global__ void k_records_to_dense(Dev<T> D, int B, double* lx, double* lu, doub
     const T* rec = rec_at(D, k, b);
     double* px = lx + (size_t(b) * (N + 1) + k) * 4;
     double* pxx = lxx + (size_t(b) * (N + 1) + k) * 16;
-    for (int c = 0; c < 4; ++c) px[c] = double(rec[(kRecLx + c) * kRecFS]);
+    for (int c = 0; c < 4; ++c) px[c] = double(rec[rf<T>(kRecLx + c)]);
 #ifdef CILQR_PARITY
-    for (int e = 0; e < 16; ++e) pxx[e] = double(rec[(kRecLxx + e) * kRecFS]);
+    for (int e = 0; e < 16; ++e) pxx[e] = double(rec[rf<T>(kRecLxx + e)]);
 #else
     int e = 0;
     for (int r = 0; r < 4; ++r)
         for (int c = r; c < 4; ++c, ++e) {
-            double v = double(rec[(kRecLxx + e) * kRecFS]);
+            double v = double(rec[rf<T>(kRecLxx + e)]);
             pxx[r * 4 + c] = v;
             pxx[c * 4 + r] = v;
         }
@@ -2319,23 +2352,23 @@ __global__ void k_records_to_dense(Dev<T> D, int B, double* lx, double* lu, doub
         double* puu = luu + (size_t(b) * N + k) * 4;
         double* pa = A + (size_t(b) * N + k) * 16;
         double* pb = Bm + (size_t(b) * N + k) * 8;
-        pu[0] = double(rec[(kRecLu + 0) * kRecFS]);
-        pu[1] = double(rec[(kRecLu + 1) * kRecFS]);
-        puu[0] = double(rec[(kRecLuu + 0) * kRecFS]);
-        puu[1] = puu[2] = double(rec[(kRecLuu + 1) * kRecFS]);
-        puu[3] = double(rec[(kRecLuu + 2) * kRecFS]);
+        pu[0] = double(rec[rf<T>(kRecLu + 0)]);
+        pu[1] = double(rec[rf<T>(kRecLu + 1)]);
+        puu[0] = double(rec[rf<T>(kRecLuu + 0)]);
+        puu[1] = puu[2] = double(rec[rf<T>(kRecLuu + 1)]);
+        puu[3] = double(rec[rf<T>(kRecLuu + 2)]);
         for (int r = 0; r < 4; ++r)
             for (int c = 0; c < 4; ++c) pa[r * 4 + c] = (r == c) ? 1.0 : 0.0;
-        pa[0 * 4 + 2] = double(rec[(kRecA + 0) * kRecFS]);
-        pa[0 * 4 + 3] = double(rec[(kRecA + 1) * kRecFS]);
-        pa[1 * 4 + 2] = double(rec[(kRecA + 2) * kRecFS]);
-        pa[1 * 4 + 3] = double(rec[(kRecA + 3) * kRecFS]);
-        pa[3 * 4 + 2] = double(rec[(kRecA + 4) * kRecFS]);
+        pa[0 * 4 + 2] = double(rec[rf<T>(kRecA + 0)]);
+        pa[0 * 4 + 3] = double(rec[rf<T>(kRecA + 1)]);
+        pa[1 * 4 + 2] = double(rec[rf<T>(kRecA + 2)]);
+        pa[1 * 4 + 3] = double(rec[rf<T>(kRecA + 3)]);
+        pa[3 * 4 + 2] = double(rec[rf<T>(kRecA + 4)]);
         for (int c = 0; c < 8; ++c) pb[c] = 0.0;
-        pb[0 * 2 + 1] = double(rec[(kRecB + 0) * kRecFS]);
-        pb[1 * 2 + 1] = double(rec[(kRecB + 1) * kRecFS]);
-        pb[2 * 2 + 0] = double(rec[(kRecB + 2) * kRecFS]);
-        pb[3 * 2 + 1] = double(rec[(kRecB + 3) * kRecFS]);
+        pb[0 * 2 + 1] = double(rec[rf<T>(kRecB + 0)]);
+        pb[1 * 2 + 1] = double(rec[rf<T>(kRecB + 1)]);
+        pb[2 * 2 + 0] = double(rec[rf<T>(kRecB + 2)]);
+        pb[3 * 2 + 1] = double(rec[rf<T>(kRecB + 3)]);
     }
 }
 
@@ -2346,7 +2379,7 @@ __global__ void k_tile_records(Dev<T> D, int B0, int B) {
     int row = blockIdx.y;  // (step, field) flattened
     if (b >= B || b < B0) return;
     const int k = row / kRecFields, c = row % kRecFields;
-    rec_at(D, k, b)[c * kRecFS] = rec_at(D, k, b % B0)[c * kRecFS];
+    rec_at(D, k, b)[rf<T>(c)] = rec_at(D, k, b % B0)[rf<T>(c)];
 }
 
 // ---------------------------------------------------------------------------
@@ -2447,8 +2480,8 @@ __global__ void __launch_bounds__(128) k_swap_records(Dev<T> D, const int* __res
         const int a = src[j], b = dst[j];
         for (int row = blockIdx.y; row < rows; row += gridDim.y) {
             const int k = row / kRecFields, c = row % kRecFields;
-            T* pa = rec_at(D, k, a) + c * kRecFS;
-            T* pb = rec_at(D, k, b) + c * kRecFS;
+            T* pa = rec_at(D, k, a) + rf<T>(c);
+            T* pb = rec_at(D, k, b) + rf<T>(c);
             const T va = *pa, vb = *pb;
             *pa = vb;
             *pb = va;
