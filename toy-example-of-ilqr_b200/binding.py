@@ -192,6 +192,7 @@ class BatchSolver:
     OPT_STAGED_BACKWARD = 6
     OPT_REPACK = 7
     OPT_WIDE_STEP = 8
+    OPT_LOOKAHEAD = 9
     STAGES = ["derivs", "backward", "forward", "ref_match", "cost", "decide"]
 
     def stage_times(self):

@@ -55,6 +55,9 @@ constexpr int kGridCap = 148 * 32;  // grid-stride kernels: at most 32 CTAs of 1
 // smallest batch that is still repacked: below it a round is a latency chain whatever the slots'
 // order (measured: 8192 instances 20.7 -> 19.5 ms with repacks down to 4096, 4096 unchanged)
 constexpr int kRepackMinBatch = 4096;
+// largest handle that gets the spare gains / the doubled trial pool of the look-ahead rounds (the latency regime
+// ends at prefetch_below = 16384 instances)
+constexpr int kLookaheadMaxBatch = 16384;
 
 // Type-erased part of a handle; the typed buffers live in Impl<T>.
 struct Base {
@@ -74,6 +77,14 @@ struct Base {
     int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
     int wide_step = 1; // bandwidth-bound rounds widen a line search step by step (2, 4, 8, 6 alphas) instead of all at once
     int repack = 1;    // survivors moved into a dense prefix whenever they are down to half of the slots in use
+    // look-ahead rounds (k_adopt): batches up to lookahead_below run next iteration's backward pass alongside the
+    // line search's cost / verdict kernels, on a second stream
+    int lookahead = 1;
+    int lookahead_below = 0;  // set at create: min(kLookaheadMaxBatch, max_batch) when the spare buffers exist
+    cudaStream_t stream_b = nullptr;
+    cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> prof_ev_b;  // stage profile of the second stream
+    std::vector<int> prof_stage_b;
     // optional in-step stage profile: CUDA events around every stage launch of one solve
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
@@ -273,6 +284,12 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         D.Bs = h->Bs;
         // trial pool: room for every instance's single trial plus wide searches of the stragglers
         D.Vs = int(std::min<size_t>(size_t(h->Bs) * 4, size_t(h->Bs) + (size_t(1) << 21)));
+        const bool la = max_batch <= kLookaheadMaxBatch;
+        if (la) D.Vs *= 2;  // a look-ahead solve alternates between two halves of the pool
+        D.spec = 0;
+        D.pool_base = 0;
+        D.pool_cap = D.Vs;
+        D.round_id = 0;
         D.max_obs = max_obs;
         D.alm_cols = 8 + 2 * max_obs;
         D.wide_mode = 1;
@@ -321,9 +338,23 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
         if ((r = dalloc(h, &D.swap_src, Bs + 8))) return r;
         if ((r = dalloc(h, &D.swap_dst, Bs + 8))) return r;
         if ((r = dalloc(h, &D.rec, size_t(N + 1) * kRecFields * Bs))) return r;
-        if ((r = dalloc(h, &D.Kg, size_t(N) * 8 * Bs))) return r;
-        if ((r = dalloc(h, &D.dg, size_t(N) * 2 * Bs))) return r;
-        if ((r = dalloc(h, &D.dV, 2 * Bs))) return r;
+        if ((r = dalloc(h, &D.Kg, size_t(N) * 8 * Bs * (la ? 2 : 1)))) return r;
+        if ((r = dalloc(h, &D.dg, size_t(N) * 2 * Bs * (la ? 2 : 1)))) return r;
+        if ((r = dalloc(h, &D.dV, 2 * Bs * (la ? 2 : 1)))) return r;
+        if (la) {
+            if ((r = dalloc(h, &D.gsel, Bs))) return r;
+            if ((r = dalloc(h, &D.job_round, Bs))) return r;
+            if ((r = dalloc(h, &D.job_src, Bs))) return r;
+            if ((r = dalloc(h, &D.job_lamb, Bs))) return r;
+            if ((r = dalloc(h, &D.job_ok, Bs))) return r;
+            if ((r = dalloc(h, &D.cur_src, Bs))) return r;
+            CK(cudaStreamCreateWithFlags(&h->stream_b, cudaStreamNonBlocking));
+            for (int i = 0; i < 4; ++i) {
+                CK(cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+            }
+            h->lookahead_below = kLookaheadMaxBatch;
+        }
         if ((r = dalloc(h, &D.lamb, Bs))) return r;
         if ((r = dalloc(h, &D.J_cur, Bs))) return r;
         if ((r = dalloc(h, &D.J_init, Bs))) return r;
@@ -405,6 +436,12 @@ inline void launch_kernel(Base* h, void (*kernel)(KArgs...), dim3 grid, dim3 blo
     h->launches++;
 }
 #define LAUNCH(h, kernel, grid, block, ...) launch_kernel(h, kernel, grid, block, __VA_ARGS__)
+template <typename... KArgs, typename... Args>
+inline void launch_kernel_on(Base* h, cudaStream_t st, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args&&... args) {
+    kernel<<<grid, block, 0, st>>>(std::forward<Args>(args)...);
+    h->launches++;
+}
+#define LAUNCH_ON(h, st, kernel, grid, block, ...) launch_kernel_on(h, st, kernel, grid, block, __VA_ARGS__)
 // cost / derivative kernels: the ALM paths are compiled in only when a template asks for them
 #define LAUNCH_COST(h, minb, grid, ...)                                     \
     do {                                                                    \
@@ -590,6 +627,19 @@ inline void mark_stage(Base* h, int id) {
     h->prof_stage.push_back(id);
 }
 
+// the same on the second stream of a look-ahead solve (its own event list)
+inline void mark_stage_b(Base* h, int id) {
+    if (!h->profile) return;
+    size_t i = h->prof_stage_b.size();
+    if (i >= h->prof_ev_b.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->prof_ev_b.push_back(e);
+    }
+    cudaEventRecord(h->prof_ev_b[i], h->stream_b);
+    h->prof_stage_b.push_back(id);
+}
+
 // `count`: an upper bound of the trajectories the launch has to cover (all B instances, or the slots of
 // the trial pool that can be in use this round); `lat`: latency-regime kernel variants.
 template <typename T>
@@ -705,6 +755,23 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // the latency-regime kernels for its stragglers).
     int launched = 0;
     int level = 0, repack_bound[kRepackLevels], repack_off[kRepackLevels + 1] = {0};
+    // Look-ahead rounds (see k_adopt): the whole solve of a latency-bound batch.  Needs the piped rollout and the
+    // staged backward pass (their look-ahead forms are the ones written), no augmented-Lagrangian template (its
+    // multiplier updates re-cost the current trajectory between iterations) and the spare buffers of create.
+    const bool la = !kParity && h->lookahead && Bfull <= h->lookahead_below && Bfull <= h->prefetch_below && h->staged &&
+                    h->pipeline && N + 1 <= kPipeMaxSteps && !h->any_alm;
+    Dev<T> Dl = h->D;  // the launch arguments of a look-ahead round
+    static const int la_serial = getenv("CILQR_LA_SERIAL") ? atoi(getenv("CILQR_LA_SERIAL")) : 0;  // debugging: 1 = everything on one stream
+    const cudaStream_t sb = la_serial ? h->stream : h->stream_b;
+    if (la) {
+        Dl.spec = 1;
+        Dl.pool_cap = h->D.Vs / 2;
+        Dl.wide_step = 0;
+        // jobs of round 0: every instance needs the backward pass of its initial trajectory
+        Dl.round_id = 0;
+        Dl.pool_base = 0;
+        LAUNCH(h, k_adopt<T>, gs1(B), 128, Dl, 0);
+    }
     // the spin below must not outlive a device fault or a stalled kernel: every kSpinCheck polls the stream is
     // queried (a sticky error, or an idle stream whose progress words still say "rounds outstanding", ends the
     // solve with CILQR_ERR_CUDA), and a round that makes no progress for kStallSeconds is reported as a stall
@@ -737,7 +804,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         const int n_bound = std::max(1, std::min(B, int(unsigned(progress[1]))));
         // Repack: the survivors of a large batch have thinned out to half of the slots in use -> move
         // them into a dense prefix (swap_instances) and carry on as a batch of that size.
-        if (h->repack && level < kRepackLevels && B > (h->repack > 1 ? h->repack : kRepackMinBatch) && size_t(n_bound) * 2 <= size_t(B)) {
+        if (!la && h->repack && level < kRepackLevels && B > (h->repack > 1 ? h->repack : kRepackMinBatch) && size_t(n_bound) * 2 <= size_t(B)) {
             LAUNCH(h, k_plan_repack<T>, dim3(1), kPlanThreads, h->D, launched & 1, level, h->D.swap_src + repack_off[level],
                    h->D.swap_dst + repack_off[level]);
             swap_instances(h, level, repack_off[level], n_bound);
@@ -746,9 +813,51 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             ++level;
             B = n_bound;
         }
+        const int par = launched & 1;  // which of the two work lists this round reads
+        if (la) {
+            // stream S: rollouts + match | costs, verdict |        adopt
+            // stream B:                  | derivatives, recursion /
+            const int trial_bound = int(std::min<long long>(Dl.pool_cap, (long long)n_bound * kNumAlphas));
+            const int e = launched & 3;
+            Dl.round_id = launched;
+            Dl.pool_base = par * Dl.pool_cap;
+            mark_stage(h, 2);
+            nvtxRangePushA("K6+K1 rollouts, waypoint match");
+            if (launched > 0) {  // (round 0 has no trials: every instance starts with a backward job)
+                const int blocks = std::max(1, std::min((trial_bound + kPipeTrials - 1) / kPipeTrials, kGridCap));
+                const bool narrow = h->pipeline == 8 || (h->pipeline == 1 && trial_bound > 2 * 148 * kPipeTrials);
+                if (narrow) LAUNCH(h, (k_rollout_match<T, 8>), dim3(blocks), pipe_threads(8), Dl, B);
+                else LAUNCH(h, (k_rollout_match<T, 16>), dim3(blocks), pipe_threads(16), Dl, B);
+            }
+            nvtxRangePop();
+            CK(cudaEventRecord(h->ev_fork[e], h->stream));
+            CK(cudaStreamWaitEvent(sb, h->ev_fork[e], 0));
+            nvtxRangePushA("K3+K4+K5 backward jobs (second stream)");
+            mark_stage_b(h, 0);
+            LAUNCH_ON(h, sb, (k_derivs<T, -1, false>), gk(n_bound, 2 * (N + 1)), 128, Dl, B, 2, par);
+            mark_stage_b(h, 1);
+            LAUNCH_ON(h, sb, k_backward_staged<T>, staged_grid(B), 32, Dl, B, 2);
+            if (la_serial == 2) CK(cudaDeviceSynchronize());
+            mark_stage_b(h, -1);
+            CK(cudaEventRecord(h->ev_join[e], sb));
+            nvtxRangePop();
+            nvtxRangePushA("K2 trial costs, K7 verdict, adopt");
+            mark_stage(h, 4);
+            if (launched > 0) LAUNCH(h, (k_cost<T, 4, false>), gk(trial_bound, N + 1), 128, Dl, B, 1);
+            mark_stage(h, 5);
+            h->scan_epoch = (h->scan_epoch % 0x3fffffffu) + 1u;
+            LAUNCH(h, k_decide<T>, dim3((n_bound + 127) / 128), 128, Dl, B, par, h->scan_epoch);
+            CK(cudaStreamWaitEvent(h->stream, h->ev_join[e], 0));
+            Dl.round_id = launched + 1;
+            Dl.pool_base = (par ^ 1) * Dl.pool_cap;
+            LAUNCH(h, k_adopt<T>, gs1(n_bound), 128, Dl, par ^ 1);
+            nvtxRangePop();
+            mark_stage(h, -1);
+            ++launched;
+            continue;
+        }
         const int trial_bound = int(std::min<long long>(h->D.Vs, (long long)n_bound * kNumAlphas));
         const bool lat = n_bound <= h->prefetch_below;
-        const int par = launched & 1;  // which of the two work lists this round reads
         mark_stage(h, 0);
         nvtxRangePushA("K3+K4 derivatives");
         if (lat) {
@@ -808,7 +917,16 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         ++launched;
     }
     // commit a step accepted in the last round
-    LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 1, launched & 1);
+    if (la) {
+        // (every instance is done: no jobs left, only trial slots waiting to be copied; then the current copy of
+        // the gains goes back into the first one)
+        Dl.round_id = launched;
+        LAUNCH(h, (k_derivs<T, -1, false>), gk(B, 2 * (N + 1)), 128, Dl, B, 2, launched & 1);
+        LAUNCH(h, k_gains_home<T>, gs2(B, N * 10 + 2), 128, Dl, B);
+        LAUNCH(h, k_pack_int, grid1(B), 128, static_cast<const int*>(nullptr), h->D.gsel, B, 0);
+    } else {
+        LAUNCH_DERIVS(h, -1, gk(B, 2 * (N + 1)), h->D, B, 1, launched & 1);
+    }
     // every instance back into its own slot
     while (level > 0) {
         --level;
@@ -833,6 +951,16 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             }
         }
         h->prof_stage.clear();
+        for (size_t i = 0; i + 1 < h->prof_stage_b.size(); ++i) {
+            int id = h->prof_stage_b[i];
+            if (id < 0) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->prof_ev_b[i], h->prof_ev_b[i + 1]) == cudaSuccess) {
+                h->stage_ms[id] += ms;
+                h->stage_launches[id] += 1;
+            }
+        }
+        h->prof_stage_b.clear();
     }
     int ctl[CTL_WORDS];
     CK(cudaMemcpy(ctl, h->D.ctl, sizeof ctl, cudaMemcpyDeviceToHost));
@@ -1374,6 +1502,9 @@ int do_set_option(Impl<T>* h, int option, int value) {
         case CILQR_OPT_REPACK:
             h->repack = value < 0 ? 0 : value;  // > 1: smallest batch that is still repacked (development)
             return 0;
+        case CILQR_OPT_LOOKAHEAD:
+            h->lookahead = value ? 1 : 0;
+            return 0;
         case CILQR_OPT_BENCH_PREFETCH:
             h->bench_prefetch = value < 0 ? -1 : (value > 2 ? 2 : value);
             return 0;
@@ -1423,6 +1554,12 @@ int do_destroy(Impl<T>* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_ctl) cudaFreeHost(const_cast<int*>(h->h_ctl));
     for (auto& e : h->prof_ev) cudaEventDestroy(e);
+    for (auto& e : h->prof_ev_b) cudaEventDestroy(e);
+    for (int i = 0; i < 4; ++i) {
+        if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->stream_b) cudaStreamDestroy(h->stream_b);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -184,6 +184,19 @@ struct Dev {
     // loop control
     int* ctl;             // [CTL_WORDS]
     volatile int* h_ctl;  // mapped pinned host memory, two 64-bit words: rounds completed << 32 | {instances running, next list length}
+    // Look-ahead rounds (latency-bound batches, see k_adopt): the backward pass an instance will need next is run
+    // one round early, next to the cost / verdict kernels of the line search it depends on, and adopted when the
+    // verdict turns out as expected.
+    int spec;        // 1 inside a look-ahead solve
+    int pool_base;   // first slot of the half of the trial pool this round uses (0 outside look-ahead solves)
+    int pool_cap;    // slots in it (Vs outside look-ahead solves)
+    int* gsel;       // [Bs] which copy of the gains (Kg, dg, dV: allocated twice) is the instance's current one
+    int round_id;    // the round a launch belongs to (k_adopt: the round its jobs are for)
+    int* job_round;  // [Bs] the round the instance's job is for (an instance dropped from the work list keeps a stale one)
+    int* job_src;    // [Bs] the trajectory this round's backward job differentiates: -2 no job, -1 the current one, >= 0 a trial slot
+    T* job_lamb;     // [Bs] the regularisation the job runs with
+    int* job_ok;     // [Bs] the job's recursion met no non-PD Q_uu
+    int* cur_src;    // [Bs] trial slot (other half of the pool) still holding the current trajectory, -1 once it is copied
     // optional per-iteration trace, [trace_cap][Bs]
     int* tr_status;
     int* tr_alpha;
@@ -214,7 +227,7 @@ template <typename T>
 __device__ __forceinline__ int view_count(const Dev<T>& D, int trial, int B) {
     if (!trial) return B;
     int nv = D.ctl[CTL_NV];
-    return nv < D.Vs ? nv : D.Vs;
+    return nv < D.pool_cap ? nv : D.pool_cap;
 }
 
 // field 0 of the record of step k of instance b; field c is rf<T>(c) scalars further on, the same
@@ -227,6 +240,19 @@ __device__ __forceinline__ T* rec_at(const Dev<T>& D, int k, int b) {
 __device__ __forceinline__ size_t at(size_t stride, int step, int field, int nfields, int i) {
     return (size_t(step) * nfields + field) * stride + i;
 }
+
+// The instance's current copy of the gains: 0 outside look-ahead solves (k_adopt flips it when a job is adopted).
+template <typename T>
+__device__ __forceinline__ int gains_sel(const Dev<T>& D, int b) { return D.spec ? D.gsel[b] : 0; }
+// this round's backward job of instance b (look-ahead solves), -2 = none
+template <typename T>
+__device__ __forceinline__ int job_of(const Dev<T>& D, int b) { return D.job_round[b] == D.round_id ? D.job_src[b] : -2; }
+template <typename T>
+__device__ __forceinline__ T* Kg_of(const Dev<T>& D, int sel) { return D.Kg + size_t(sel) * D.N * 8 * D.Bs; }
+template <typename T>
+__device__ __forceinline__ T* dg_of(const Dev<T>& D, int sel) { return D.dg + size_t(sel) * D.N * 2 * D.Bs; }
+template <typename T>
+__device__ __forceinline__ T* dV_of(const Dev<T>& D, int sel) { return D.dV + size_t(sel) * 2 * D.Bs; }
 
 // The per-template solver scalars (2 KB for all templates) copied into shared memory at the start of a kernel:
 // every thread of the step-parallel stages reads a dozen of them behind the load of its instance's template id, and
@@ -326,6 +352,13 @@ __global__ void __launch_bounds__(128) k_init(Dev<T> D, int B, int force_warm, i
             D.t_count[b] = 0;
             D.dV[b] = 0;
             D.dV[Bs + b] = 0;
+            if (D.gsel) {
+                D.gsel[b] = 0;
+                D.job_src[b] = -2;
+                D.job_round[b] = -1;
+                D.job_ok[b] = 0;
+                D.cur_src[b] = -1;
+            }
             // round 0 works on every instance
             D.act[b] = b;
             if (b == 0) {
@@ -548,7 +581,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_cost(Dev<T> D, int B, int t
     // grid: x = step, y = blocks of trajectories (so the blocks that have work are dispatched first
     // when only the head of the trial pool is in use)
     const int k = blockIdx.x;
-    for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < count; v += gridDim.y * blockDim.x) {
+    const int v_first = trial ? D.pool_base : 0, v_end = v_first + count;
+    for (int v = v_first + blockIdx.y * blockDim.x + threadIdx.x; v < v_end; v += gridDim.y * blockDim.x) {
         const int b = V.inst ? V.inst[v] : v;
 #ifdef CILQR_PARITY
         T parts[3];
@@ -576,7 +610,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) k_sum_trials(Dev<T> D, int B) {
     const int count = view_count(D, 1, B);
     const size_t Vs = D.Vs;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += gridDim.x * blockDim.x) {
+    for (int v = D.pool_base + blockIdx.x * blockDim.x + threadIdx.x; v < D.pool_base + count; v += gridDim.x * blockDim.x) {
         D.J_t[v] = sum_step_costs<T, false>(D.sc_t, Vs, D.N, v);
     }
 }
@@ -661,7 +695,20 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
 
     T x[4], ua = 0, us = 0;
     int ri = 0;
-    const int src = masked ? D.commit_src[b] : -1;
+    // src: trial slot to commit; tsrc: trial slot to differentiate (-1 = the current trajectory's own arrays).
+    // masked == 2 (look-ahead rounds): the slot to commit is the one k_adopt took over from the verdict kernel, and
+    // what is differentiated is this round's job: a trial of the running line search (speculation), or the current
+    // trajectory where its record is stale.
+    int src = -1, tsrc = -1;
+    bool diff = true;
+    if (masked == 1) {
+        src = tsrc = D.commit_src[b];
+    } else if (masked == 2) {
+        src = D.cur_src[b];
+        const int job = job_of(D, b);
+        diff = job >= 0 || (job == -1 && !D.rec_valid[b]);
+        tsrc = job >= 0 ? job : src;
+    }
     if (src >= 0) {
         // the accepted trial becomes the current trajectory; part 1 reads the state from the
         // trial slot too, so it never races with part 0's copy
@@ -681,8 +728,9 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             D.U[at(Bs, k, 1, 2, b)] = us;
         }
     }
-    if (masked && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) return;
-    if (src < 0) {
+    if (masked == 1 && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) return;
+    if (masked == 2 && !diff) return;
+    if (tsrc < 0) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) x[c] = D.X[at(Bs, k, c, 4, b)];
         if (part == 0) {
@@ -690,6 +738,15 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
         } else if (k < N) {
             ua = D.U[at(Bs, k, 0, 2, b)];
             us = D.U[at(Bs, k, 1, 2, b)];
+        }
+    } else if (tsrc != src) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[c] = D.Xt[at(Vs, k, c, 4, tsrc)];
+        if (part == 0) {
+            ri = D.ridx_t[size_t(k) * Vs + tsrc];
+        } else if (k < N) {
+            ua = D.Ut[at(Vs, k, 0, 2, tsrc)];
+            us = D.Ut[at(Vs, k, 1, 2, tsrc)];
         }
     }
     const DevParams<T>& P = D.P[D.tmpl[b]];
@@ -1406,9 +1463,10 @@ __device__ __forceinline__ void claim_slots(const Dev<T>& D, int b, int want, in
     if (lane == 31 && total > 0) base = atomicAdd(&D.ctl[CTL_NV], total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (want > 0) {
-        int v0 = base + incl - want;
-        int room = D.Vs - v0;
-        int cnt = room <= 0 ? 0 : (want < room ? want : room);
+        const int r0 = base + incl - want;  // position inside this round's (half of the) pool
+        const int room = D.pool_cap - r0;
+        const int cnt = room <= 0 ? 0 : (want < room ? want : room);
+        const int v0 = D.pool_base + r0;
         D.t_first[b] = v0;
         D.t_count[b] = cnt;
         for (int i = 0; i < cnt; ++i) {
@@ -1575,6 +1633,8 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
     if (in) {
         if (!solver) {
             run = true;
+        } else if (solver == 2) {
+            run = job_of(D, b) != -2;  // look-ahead rounds: this round's job, into the spare copy of the gains
         } else {
             D.commit_src[b] = -1;  // consumed by the derivative stage just before
             D.t_count[b] = 0;
@@ -1582,6 +1642,7 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
             run = ph == PH_BACKWARD;
         }
     }
+    const int gs = (solver == 2 && in) ? (D.gsel[b] ^ 1) : 0;
     bool ok = true;
     if (__any_sync(0xffffffffu, run)) {
         const T* tile_rec = rec_at(D, 0, tile * 32);
@@ -1596,7 +1657,7 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
             ++R.issued;
         };
         for (int j = 0; j < kStagedStages && j < N; ++j) issue(N - 1 - j);
-        const T lamb = run ? D.lamb[b] : T(0);
+        const T lamb = run ? (solver == 2 ? D.job_lamb[b] : D.lamb[b]) : T(0);
         T Vx[4], V[kVN];
         {
             const T* rec = rec_at(D, N, in ? b : 0);
@@ -1605,8 +1666,8 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
             load_terminal_V(rec, V);
         }
         T dV0 = 0, dV1 = 0;
-        T* Kp = D.Kg + size_t(N) * 8 * Bs + (in ? b : 0);
-        T* dp = D.dg + size_t(N) * 2 * Bs + (in ? b : 0);
+        T* Kp = Kg_of(D, gs) + size_t(N) * 8 * Bs + (in ? b : 0);
+        T* dp = dg_of(D, gs) + size_t(N) * 2 * Bs + (in ? b : 0);
         for (int i = N - 1; i >= 0; --i) {
             const unsigned s = R.consumed % kStagedStages, parity = (R.consumed / kStagedStages) & 1u;
             ++R.consumed;
@@ -1635,11 +1696,16 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
             if (i - kStagedStages >= 0) issue(i - kStagedStages);
         }
         if (run) {
-            D.dV[b] = dV0;
-            D.dV[Bs + b] = dV1;
+            T* dVp = dV_of(D, gs);
+            dVp[b] = dV0;
+            dVp[Bs + b] = dV1;
         }
     }
     if (in && !solver) D.status[b] = ok ? ST_RUNNING : ST_BWD_FAIL;
+    if (solver == 2) {
+        if (run) D.job_ok[b] = ok;
+        return 0;
+    }
     int want = 0, a0 = 0;
     if (in && solver) after_backward(D, b, run, ok, ph, &want, &a0);
     if (!solver) return 0;
@@ -1901,11 +1967,21 @@ __device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kP
         const int p_ref = Pp->ref_point;
         const bool mixed = __any_sync(0xffffffffu, p_ref != 0);
         const T alpha = T(1) / T(1 << D.t_aidx[vv]);
+        // the trajectory the search starts from: the instance's own arrays or, in a look-ahead solve, the trial
+        // slot of the previous round that was accepted and is being copied there meanwhile; its gains: the
+        // instance's current copy
+        const int cs = D.spec ? D.cur_src[b] : -1;
+        const T* Xc = cs >= 0 ? D.Xt + cs : D.X + b;
+        const T* Uc = cs >= 0 ? D.Ut + cs : D.U + b;
+        const size_t xs = cs >= 0 ? Vs : Bs;
+        const int gs = gains_sel(D, b);
+        const T* Kc = Kg_of(D, gs) + b;
+        const T* dc = dg_of(D, gs) + b;
         // lane `role` of a pair owns control row `role`: its feedback row, u and d
         T xn[4], cx[4], cK[4], cu, cd;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            cx[c] = D.X[at(Bs, 0, c, 4, b)];
+            cx[c] = Xc[size_t(c) * xs];
             xn[c] = cx[c];
         }
         if (role == 0) {
@@ -1917,19 +1993,19 @@ __device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kP
 #pragma unroll
         for (int c = 0; c < 4; ++c)
             if (live && role == 0) D.Xt[at(Vs, 0, c, 4, v)] = xn[c];
-        cu = D.U[at(Bs, 0, role, 2, b)];
-        cd = D.dg[at(Bs, 0, role, 2, b)];
+        cu = Uc[size_t(role) * xs];
+        cd = dc[size_t(role) * Bs];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) cK[c] = D.Kg[at(Bs, 0, role * 4 + c, 8, b)];
+        for (int c = 0; c < 4; ++c) cK[c] = Kc[size_t(role * 4 + c) * Bs];
         for (int i = 0; i < N; ++i) {
             T nxx[4], nxK[4], nxu, nxd;
             const int ip = i + 1 < N ? i + 1 : i;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) nxx[c] = ld_early(D.X + at(Bs, ip, c, 4, b));
-            nxu = ld_early(D.U + at(Bs, ip, role, 2, b));
-            nxd = ld_early(D.dg + at(Bs, ip, role, 2, b));
+            for (int c = 0; c < 4; ++c) nxx[c] = ld_early(Xc + size_t(ip * 4 + c) * xs);
+            nxu = ld_early(Uc + size_t(ip * 2 + role) * xs);
+            nxd = ld_early(dc + size_t(ip * 2 + role) * Bs);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) nxK[c] = ld_early(D.Kg + at(Bs, ip, role * 4 + c, 8, b));
+            for (int c = 0; c < 4; ++c) nxK[c] = ld_early(Kc + size_t(ip * 8 + role * 4 + c) * Bs);
             T fb = 0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) fb += cK[c] * (xn[c] - cx[c]);
@@ -2025,8 +2101,10 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     unsigned parity = 0;
-    for (int base = blockIdx.x * kPipeTrials; base < count; base += gridDim.x * kPipeTrials, parity ^= 1u) {
-        rollout_match_group<T, G>(D, pos, bars, parity, base, count, warp == 0, warp - 1, lane);
+    // (slots are absolute: a look-ahead solve alternates between the two halves of the pool)
+    const int v_end = D.pool_base + count;
+    for (int base = D.pool_base + blockIdx.x * kPipeTrials; base < v_end; base += gridDim.x * kPipeTrials, parity ^= 1u) {
+        rollout_match_group<T, G>(D, pos, bars, parity, base, v_end, warp == 0, warp - 1, lane);
         __syncthreads();  // the ring is reused by the next group of trials
     }
 }
@@ -2040,7 +2118,8 @@ __device__ __forceinline__ void decide_instance(const Dev<T>& D, int b, int cnt)
     const int v0 = D.t_first[b];
     const int a0 = D.aidx[b];
     const T J_cur = D.J_cur[b];
-    const T dV0 = D.dV[b], dV1 = D.dV[Bs + b];
+    const T* dVc = dV_of(D, gains_sel(D, b));
+    const T dV0 = dVc[b], dV1 = dVc[Bs + b];
     bool ended = false;
     T last_J = J_cur;  // cost of the last trial looked at: what iter_step returns when every alpha was rejected (cpp:380)
     // trial costs four at a time (independent loads), then their verdicts in alpha order; the
@@ -2211,7 +2290,9 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
             *tally = 0ull;
             D.ctl[CTL_NV] = 0;
             D.ctl[CTL_CHUNK] = 0;
-            D.ctl[CTL_NACT + par] = 0;  // consumed; the verdict kernel of the next round refills it
+            // consumed; the verdict kernel of the next round refills it (look-ahead solves: the derivative kernel of
+            // this round, on the other stream, may still be reading it — k_adopt clears it)
+            if (!D.spec) D.ctl[CTL_NACT + par] = 0;
             // two independent 64-bit words (rounds completed << 32 | instances still running, and
             // rounds completed << 32 | length of the next work list): the host reads each with one
             // load and either may be stale (both counts only ever shrink), so no system-scope fence
@@ -2220,6 +2301,81 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
             hw[1] = (static_cast<unsigned long long>(unsigned(round)) << 32) | unsigned(n_next);
             hw[0] = (static_cast<unsigned long long>(unsigned(round)) << 32) | unsigned(active);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Look-ahead rounds (latency-bound batches).  An iteration of the reference is a chain
+//     derivatives -> backward pass -> rollout -> cost -> verdict -> derivatives of the accepted trajectory -> ...
+// and for small batches every link is a latency chain of its own (~140 us per iteration on B200).  But the
+// derivatives and the backward pass of the NEXT iteration depend on the verdict only through WHICH trajectory was
+// accepted and the regularisation that follows from it, and 96 % of the iterations of the slowest instances accept
+// the full step (alpha = 1, lambda *= decay).  So a round runs, next to the cost and verdict kernels of its trials
+// (stream A), a backward "job" per instance on a second stream (B): derivatives (k_derivs, masked = 2) and the
+// recursion (k_backward_staged, solver = 2) of
+//     * the alpha = 1 trial of the running line search, with lambda * decay  (speculation), or
+//     * the current trajectory with the current lambda, for an instance that has nothing to roll out this round
+//       (first iteration, after a rejected / shortened step, after a failed backward pass),
+// writing into the spare copy of the gains.  k_adopt joins the two streams: where the verdict asks for exactly the
+// backward pass the job ran (same trajectory, same lambda — bitwise), the spare copy becomes the current one and
+// the instance goes straight on to its next line search; otherwise the instance gets a job for what it needs and
+// sits the next round out.  Every instance performs the reference's sequence of operations on the same values —
+// the result bits do not depend on the mode — but an iteration costs rollout + derivatives + recursion instead of
+// the whole chain.  The derivative records of a speculated trial overwrite the instance's (rec_valid = 0 on a
+// miss: the reference's cache of cpp:469-474 is recomputed, same bits); accepted trials are copied into the
+// instance's arrays by the next round's derivative kernel while the rollouts read them from the slot (cur_src),
+// which is why a look-ahead solve alternates between two halves of the trial pool.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_adopt(Dev<T> D, int par_next) {
+    const size_t Bs = D.Bs;
+    const int lane = threadIdx.x & 31;
+    const int* list = D.act + size_t(par_next) * Bs;
+    const int n = D.ctl[CTL_NACT + par_next];
+    const int n_pad = (n + 31) & ~31;  // whole warps: claim_slots is a warp collective
+    if (blockIdx.x == 0 && threadIdx.x == 0) D.ctl[CTL_NACT + (par_next ^ 1)] = 0;  // the list this round consumed
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_pad; idx += gridDim.x * blockDim.x) {
+        const bool in = idx < n;
+        const int b = in ? list[idx] : 0;
+        int want = 0, a0 = 0;
+        if (in) {
+            const int cs = D.commit_src[b];  // accepted this round (a slot of this round's half), or -1
+            D.cur_src[b] = cs;
+            D.commit_src[b] = -1;
+            D.t_count[b] = 0;
+            int ph = D.phase[b];
+            const int job = D.job_round[b] == D.round_id - 1 ? D.job_src[b] : -2;  // the round that just ended
+            D.job_round[b] = D.round_id;
+            // the backward pass the verdict asks for: over trajectory cs (-1 = the unchanged current one) with lamb[b]
+            const bool hit = ph == PH_BACKWARD && job != -2 && job == cs && D.job_lamb[b] == D.lamb[b];
+            if (hit) D.gsel[b] ^= 1;
+            else if (job >= 0) D.rec_valid[b] = 0;  // the speculated trial's record replaced the current trajectory's
+            after_backward(D, b, hit, hit && D.job_ok[b] != 0, ph, &want, &a0);
+            ph = D.phase[b];
+            D.job_src[b] = ph == PH_BACKWARD ? -1 : -2;
+            if (ph == PH_BACKWARD) D.job_lamb[b] = D.lamb[b];
+        }
+        claim_slots(D, b, want, a0, lane);  // D.pool_base / pool_cap: the half of the pool the next round uses
+        if (in && want > 0 && a0 == 0 && D.t_count[b] > 0) {
+            // speculate on the full step: accepted with status RUNNING, lambda *= decay (end_iteration)
+            D.job_src[b] = D.t_first[b];
+            D.job_lamb[b] = D.lamb[b] * D.P[D.tmpl[b]].lamb_decay;
+        }
+    }
+}
+
+// End of a look-ahead solve: the current copy of the gains back into the first one (the only one the rest of the
+// library knows about); the selectors are cleared by the caller afterwards.  grid.y = rows of K + d + dV.
+template <typename T>
+__global__ void __launch_bounds__(128) k_gains_home(Dev<T> D, int B) {
+    const size_t Bs = D.Bs;
+    const int N = D.N;
+    const int row = blockIdx.y;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        if (!D.gsel[b]) continue;
+        if (row < N * 8) D.Kg[size_t(row) * Bs + b] = Kg_of(D, 1)[size_t(row) * Bs + b];
+        else if (row < N * 10) D.dg[size_t(row - N * 8) * Bs + b] = dg_of(D, 1)[size_t(row - N * 8) * Bs + b];
+        else D.dV[size_t(row - N * 10) * Bs + b] = dV_of(D, 1)[size_t(row - N * 10) * Bs + b];
     }
 }
 
