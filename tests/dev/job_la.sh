@@ -1,1 +1,3 @@
-for m in 0 1; do echo "== CILQR_LA_SERIAL=$m"; CILQR_LA_SERIAL=$m timeout 300 python tests/dev/lookahead_dbg.py C1:16384:f64 C2:2048:f64 C1:16384:f64 2>&1 | grep "la rep\|repeatable" ; done
+timeout 300 python tests/dev/lookahead_dbg.py C1:4096:f64 C3:4096:f64 C1:4096:f32 C2:2048:f64 2>&1 | grep -v "^    " 
+timeout 300 python tests/dev/lookahead_ab.py C1:4096:f64 C1:1024:f64 C3:4096:f64 C1:256:f64 2>&1
+python tests/dev/la_stages.py C1:4096:f64 2>&1 | tail -1; python tests/dev/la_stages.py C1:1024:f64 2>&1 | tail -1

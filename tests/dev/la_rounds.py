@@ -1,0 +1,33 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np
+import cilqr_b200 as cb
+spec = sys.argv[1] if len(sys.argv) > 1 else "C1:1024:f64"
+la = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+cfg, B, dt = spec.split(":"); B = int(B)
+N = {"C2": 100, "C4": 200}.get(cfg, 50)
+pb = cb.synthetic_batch(cfg, B, N=N)
+path = "/tmp/prof_dump.txt"
+os.environ["CILQR_PROFILE_DUMP"] = path
+with cb.BatchSolver(pb.templates, B, N, pb.max_obs, dt) as s:
+    s.upload(pb)
+    s.set_option(s.OPT_LOOKAHEAD, 16384 if la else 0)
+    s.solve_resident(B)
+    s.set_option(s.OPT_PROFILE_STAGES, 1)
+    s.solve_resident(B)
+rows = np.loadtxt(path)
+names = {0: "derivs", 1: "backward", 2: "forward", 3: "ref_match", 4: "cost", 5: "decide"}
+S = rows[rows[:, 0] == 0]; Bm = rows[rows[:, 0] == 1]
+first = 2 if la else 0
+starts = np.where(S[:, 1] == first)[0]
+print("%s la=%d rounds=%d total %.2f ms" % (spec, la, len(starts), (S[-1, 2] + S[-1, 3]) / 1e3))
+for r, i0 in enumerate(starts):
+    i1 = starts[r + 1] if r + 1 < len(starts) else len(S)
+    d = {names[int(x[1])]: x[3] for x in S[i0:i1]}
+    t0 = S[i0, 2]; t1 = S[i1, 2] if i1 < len(S) else S[-1, 2] + S[-1, 3]
+    if la:
+        bb = Bm[2 * r: 2 * r + 2]
+        d.update({"B:" + names[int(x[1])]: x[3] for x in bb})
+        if len(bb): d["B:start"] = bb[0, 2] - t0
+    if r < 6 or r % 10 == 0 or r > len(starts) - 4:
+        print("  round %3d: %.1f us  " % (r, t1 - t0), {k: round(float(v), 1) for k, v in d.items()})

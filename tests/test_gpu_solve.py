@@ -122,6 +122,26 @@ def test_kernel_variants_return_the_same_bits(cfg, dtype):
             assert np.array_equal(getattr(outs[0], f), getattr(o, f), equal_nan=True), f
 
 
+@pytest.mark.parametrize("cfg,B,dtype", [("C1", 333, "f64"), ("C3", 700, "f64"), ("C2", 200, "f64"), ("C3", 333, "f32"), ("C1", 2500, "f64")])
+def test_lookahead_rounds_return_the_same_bits(cfg, B, dtype):
+    """Look-ahead rounds (next iteration's derivatives + backward pass speculated one round early on a second
+    stream, adopted when the verdict asks for exactly that pass: k_adopt) are an execution strategy: the same bits as
+    the sequential rounds, on repeated solves of the same handle, whichever way the races between the two streams go."""
+    pb = cb.synthetic_batch(cfg, B, N={"C2": 100}.get(cfg, 50))
+    with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, dtype) as s:
+        s.set_option(s.OPT_LOOKAHEAD, 0)
+        ref = s.solve(pb)
+        rounds_ref = s.counters()["rounds"]
+        s.set_option(s.OPT_LOOKAHEAD, 16384)  # (an explicit bound: by default only batches up to 512 use them)
+        for rep in range(3):
+            s.reset()
+            out = s.solve(pb)
+            for f in ("u", "x", "J", "K", "d", "iters", "status", "exit_reason", "step_cost"):
+                assert np.array_equal(getattr(ref, f), getattr(out, f), equal_nan=True), (f, rep)
+            # every outcome of a line search has a job, so an iteration still costs about one round
+            assert s.counters()["rounds"] <= rounds_ref * 1.35 + 4
+
+
 def test_fp32_first_iteration_vs_fp32_oracle():
     """fp32 amplifies the same sensitivity ~1e9 x more (SURVEY hard part 3), so the fp32 solve is held
     to the fp32 oracle in lockstep over the first iter_step only, where decisions still agree."""

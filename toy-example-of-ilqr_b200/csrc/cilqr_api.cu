@@ -58,6 +58,8 @@ constexpr int kRepackMinBatch = 4096;
 // largest handle that gets the spare gains / the doubled trial pool of the look-ahead rounds (the latency regime
 // ends at prefetch_below = 16384 instances)
 constexpr int kLookaheadMaxBatch = 16384;
+// batches up to this size use them by default (measured: profiles/r02_lookahead.txt)
+constexpr int kLookaheadDefault = 512;
 
 // Type-erased part of a handle; the typed buffers live in Impl<T>.
 struct Base {
@@ -348,6 +350,13 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
             if ((r = dalloc(h, &D.job_lamb, Bs))) return r;
             if ((r = dalloc(h, &D.job_ok, Bs))) return r;
             if ((r = dalloc(h, &D.cur_src, Bs))) return r;
+            if ((r = dalloc(h, &D.t_job, Vs))) return r;
+            if ((r = dalloc(h, &D.jlamb_t, Vs))) return r;
+            if ((r = dalloc(h, &D.jok_t, Vs))) return r;
+            if ((r = dalloc(h, &D.rec_t, size_t(N + 1) * kRecFields * Vs))) return r;
+            if ((r = dalloc(h, &D.Kg_t, size_t(N) * 8 * Vs))) return r;
+            if ((r = dalloc(h, &D.dg_t, size_t(N) * 2 * Vs))) return r;
+            if ((r = dalloc(h, &D.dV_t, 2 * Vs))) return r;
             CK(cudaStreamCreateWithFlags(&h->stream_b, cudaStreamNonBlocking));
             for (int i = 0; i < 4; ++i) {
                 CK(cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming));
@@ -450,8 +459,8 @@ inline void launch_kernel_on(Base* h, cudaStream_t st, void (*kernel)(KArgs...),
     } while (0)
 #define LAUNCH_DERIVS(h, part, grid, ...)                                   \
     do {                                                                    \
-        if ((h)->any_alm) LAUNCH(h, (k_derivs<T, part, true>), grid, 128, __VA_ARGS__);  \
-        else LAUNCH(h, (k_derivs<T, part, false>), grid, 128, __VA_ARGS__); \
+        if ((h)->any_alm) LAUNCH(h, (k_derivs<T, part, true>), grid, 128, __VA_ARGS__, 0);  \
+        else LAUNCH(h, (k_derivs<T, part, false>), grid, 128, __VA_ARGS__, 0); \
     } while (0)
 
 // host layout (double [B][E_src rows]) -> device SoA, chunked through the staging buffer.
@@ -758,7 +767,8 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // Look-ahead rounds (see k_adopt): the whole solve of a latency-bound batch.  Needs the piped rollout and the
     // staged backward pass (their look-ahead forms are the ones written), no augmented-Lagrangian template (its
     // multiplier updates re-cost the current trajectory between iterations) and the spare buffers of create.
-    const bool la = !kParity && h->lookahead && Bfull <= h->lookahead_below && Bfull <= h->prefetch_below && h->staged &&
+    const bool la = !kParity && h->lookahead && Bfull <= std::min(h->lookahead_below, h->lookahead > 1 ? h->lookahead : kLookaheadDefault) &&
+                    Bfull <= h->prefetch_below && h->staged &&
                     h->pipeline && N + 1 <= kPipeMaxSteps && !h->any_alm;
     Dev<T> Dl = h->D;  // the launch arguments of a look-ahead round
     static const int la_serial = getenv("CILQR_LA_SERIAL") ? atoi(getenv("CILQR_LA_SERIAL")) : 0;  // debugging: 1 = everything on one stream
@@ -767,6 +777,8 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         Dl.spec = 1;
         Dl.pool_cap = h->D.Vs / 2;
         Dl.wide_step = 0;
+        static const int spec_all_env = getenv("CILQR_LA_SPEC_ALL") ? atoi(getenv("CILQR_LA_SPEC_ALL")) : 1024;
+        Dl.spec_all_below = spec_all_env;
         // jobs of round 0: every instance needs the backward pass of its initial trajectory
         Dl.round_id = 0;
         Dl.pool_base = 0;
@@ -826,17 +838,24 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             if (launched > 0) {  // (round 0 has no trials: every instance starts with a backward job)
                 const int blocks = std::max(1, std::min((trial_bound + kPipeTrials - 1) / kPipeTrials, kGridCap));
                 const bool narrow = h->pipeline == 8 || (h->pipeline == 1 && trial_bound > 2 * 148 * kPipeTrials);
-                if (narrow) LAUNCH(h, (k_rollout_match<T, 8>), dim3(blocks), pipe_threads(8), Dl, B);
-                else LAUNCH(h, (k_rollout_match<T, 16>), dim3(blocks), pipe_threads(16), Dl, B);
+                if (narrow) LAUNCH(h, (k_rollout_match<T, 8, true>), dim3(blocks), pipe_threads(8), Dl, B);
+                else LAUNCH(h, (k_rollout_match<T, 16, true>), dim3(blocks), pipe_threads(16), Dl, B);
             }
             nvtxRangePop();
             CK(cudaEventRecord(h->ev_fork[e], h->stream));
             CK(cudaStreamWaitEvent(sb, h->ev_fork[e], 0));
             nvtxRangePushA("K3+K4+K5 backward jobs (second stream)");
             mark_stage_b(h, 0);
-            LAUNCH_ON(h, sb, (k_derivs<T, -1, false>), gk(n_bound, 2 * (N + 1)), 128, Dl, B, 2, par);
+            {
+                // blocks [0, y_list): the work list (copies of accepted trials, the instances' own jobs); from y_list
+                // on: the speculative jobs of this round's trial slots
+                const int y_list = std::max(1, std::min((n_bound + 127) / 128, kGridCap / 2));
+                // (grid-stride over the slots in use, which the host does not know: usually one per instance)
+                const int y_slots = launched > 0 ? std::max(1, std::min((trial_bound + 127) / 128, 2 * y_list + 8)) : 0;
+                LAUNCH_ON(h, sb, (k_derivs<T, -1, false>), dim3(2 * (N + 1), y_list + y_slots), 128, Dl, B, 2, par, y_list);
+            }
             mark_stage_b(h, 1);
-            LAUNCH_ON(h, sb, k_backward_staged<T>, staged_grid(B), 32, Dl, B, 2);
+            LAUNCH_ON(h, sb, k_backward_staged<T>, staged_grid(B + (launched > 0 ? std::min(trial_bound, 2 * n_bound + 1024) : 0)), 32, Dl, B, 2);
             if (la_serial == 2) CK(cudaDeviceSynchronize());
             mark_stage_b(h, -1);
             CK(cudaEventRecord(h->ev_join[e], sb));
@@ -921,7 +940,8 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         // (every instance is done: no jobs left, only trial slots waiting to be copied; then the current copy of
         // the gains goes back into the first one)
         Dl.round_id = launched;
-        LAUNCH(h, (k_derivs<T, -1, false>), gk(B, 2 * (N + 1)), 128, Dl, B, 2, launched & 1);
+        const dim3 g_fin = gk(B, 2 * (N + 1));
+        LAUNCH(h, (k_derivs<T, -1, false>), g_fin, 128, Dl, B, 2, launched & 1, int(g_fin.y));
         LAUNCH(h, k_gains_home<T>, gs2(B, N * 10 + 2), 128, Dl, B);
         LAUNCH(h, k_pack_int, grid1(B), 128, static_cast<const int*>(nullptr), h->D.gsel, B, 0);
     } else {
@@ -940,6 +960,22 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         for (int i = 0; i < 6; ++i) {
             h->stage_ms[i] = 0;
             h->stage_launches[i] = 0;
+        }
+        if (const char* dump = getenv("CILQR_PROFILE_DUMP")) {  // development: every stage interval of the solve, in order
+            if (FILE* f = fopen(dump, "w")) {
+                for (int st = 0; st < 2; ++st) {
+                    const auto& ev = st ? h->prof_ev_b : h->prof_ev;
+                    const auto& id = st ? h->prof_stage_b : h->prof_stage;
+                    for (size_t i = 0; i + 1 < id.size(); ++i) {
+                        float ms = 0, t0 = 0;
+                        if (id[i] < 0) continue;
+                        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+                        cudaEventElapsedTime(&t0, h->prof_ev[0], ev[i]);
+                        fprintf(f, "%d %d %.2f %.2f\n", st, id[i], t0 * 1e3f, ms * 1e3f);
+                    }
+                }
+                fclose(f);
+            }
         }
         for (size_t i = 0; i + 1 < h->prof_stage.size(); ++i) {
             int id = h->prof_stage[i];
@@ -1502,8 +1538,8 @@ int do_set_option(Impl<T>* h, int option, int value) {
         case CILQR_OPT_REPACK:
             h->repack = value < 0 ? 0 : value;  // > 1: smallest batch that is still repacked (development)
             return 0;
-        case CILQR_OPT_LOOKAHEAD:
-            h->lookahead = value ? 1 : 0;
+        case CILQR_OPT_LOOKAHEAD:  // 0 off, 1 the default batch bound, > 1 an explicit one
+            h->lookahead = value < 0 ? 0 : value;
             return 0;
         case CILQR_OPT_BENCH_PREFETCH:
             h->bench_prefetch = value < 0 ? -1 : (value > 2 ? 2 : value);

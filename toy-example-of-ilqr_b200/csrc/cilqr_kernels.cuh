@@ -101,6 +101,8 @@ enum Ctl : int {
     CTL_CHUNK = 7,  // next chunk of the work list to hand out in the verdict kernel
     CTL_TALLY = 8,  // [2 words, one 64-bit counter] verdict kernel: blocks done << 48 | trials << 24 | running
     CTL_TRIALS = 10,  // [2 words, one 64-bit counter] line-search trials evaluated over the whole solve
+    CTL_NV2 = 12,     // [2] look-ahead solves: trial slots in use, by round parity (the kernels of round r still read
+                      // theirs while the verdict kernel of round r re-arms the other one for round r + 1's claims)
     CTL_NSWAP = 16,  // [kRepackLevels] slot pairs exchanged by each repack of the solve
     CTL_WORDS = 32
 };
@@ -190,13 +192,23 @@ struct Dev {
     int spec;        // 1 inside a look-ahead solve
     int pool_base;   // first slot of the half of the trial pool this round uses (0 outside look-ahead solves)
     int pool_cap;    // slots in it (Vs outside look-ahead solves)
-    int* gsel;       // [Bs] which copy of the gains (Kg, dg, dV: allocated twice) is the instance's current one
+    int* gsel;       // [Bs] the instance's current gains: copy 0 / 1 of (Kg, dg, dV: allocated twice), or 2 = still in the
+                     // arrays of the trial slot cur_src (adopted last round, copied into copy 0 during this one)
     int round_id;    // the round a launch belongs to (k_adopt: the round its jobs are for)
     int* job_round;  // [Bs] the round the instance's job is for (an instance dropped from the work list keeps a stale one)
     int* job_src;    // [Bs] the trajectory this round's backward job differentiates: -2 no job, -1 the current one, >= 0 a trial slot
     T* job_lamb;     // [Bs] the regularisation the job runs with
     int* job_ok;     // [Bs] the job's recursion met no non-PD Q_uu
+    int spec_all_below;  // work lists up to this length give every trial of a line search a job, longer ones only alpha = 1
     int* cur_src;    // [Bs] trial slot (other half of the pool) still holding the current trajectory, -1 once it is copied
+    // speculative jobs, one per trial slot: the backward pass that follows if that trial is the accepted one
+    int* t_job;      // [Vs] 1: this round differentiates the slot's trajectory and runs the recursion on it
+    T* jlamb_t;      // [Vs] with this regularisation
+    int* jok_t;      // [Vs] the recursion met no non-PD Q_uu
+    T* rec_t;        // [N+1][Vs / 32][28][32]  derivative records of the slots' trajectories (layout of rec)
+    T* Kg_t;         // [N][8][Vs]   gains of the slots' jobs
+    T* dg_t;         // [N][2][Vs]
+    T* dV_t;         // [2][Vs]
     // optional per-iteration trace, [trace_cap][Bs]
     int* tr_status;
     int* tr_alpha;
@@ -223,10 +235,13 @@ __device__ __forceinline__ View<T> view_of(const Dev<T>& D, int trial) {
     }
     return v;
 }
+// the control word counting the trial slots of the round D.round_id
+template <typename T>
+__device__ __forceinline__ int nv_index(const Dev<T>& D) { return D.spec ? CTL_NV2 + (D.round_id & 1) : int(CTL_NV); }
 template <typename T>
 __device__ __forceinline__ int view_count(const Dev<T>& D, int trial, int B) {
     if (!trial) return B;
-    int nv = D.ctl[CTL_NV];
+    int nv = D.ctl[nv_index(D)];
     return nv < D.pool_cap ? nv : D.pool_cap;
 }
 
@@ -253,6 +268,39 @@ template <typename T>
 __device__ __forceinline__ T* dg_of(const Dev<T>& D, int sel) { return D.dg + size_t(sel) * D.N * 2 * D.Bs; }
 template <typename T>
 __device__ __forceinline__ T* dV_of(const Dev<T>& D, int sel) { return D.dV + size_t(sel) * 2 * D.Bs; }
+
+// Where instance b's current gains are: `*stride` scalars between consecutive rows; K, d, dV point at the instance's
+// (or slot's) column.
+template <typename T>
+struct GainsAt {
+    const T* K;
+    const T* d;
+    const T* dV;
+    size_t stride;
+};
+template <typename T>
+__device__ __forceinline__ GainsAt<T> gains_at(const Dev<T>& D, int b) {
+    const int g = gains_sel(D, b);
+    GainsAt<T> G;
+    if (g == 2) {
+        const int cs = D.cur_src[b];
+        G.K = D.Kg_t + cs;
+        G.d = D.dg_t + cs;
+        G.dV = D.dV_t + cs;
+        G.stride = size_t(D.Vs);
+    } else {
+        G.K = Kg_of(D, g) + b;
+        G.d = dg_of(D, g) + b;
+        G.dV = dV_of(D, g) + b;
+        G.stride = size_t(D.Bs);
+    }
+    return G;
+}
+// field 0 of the record of step k of trial slot v (look-ahead solves; same tiling as rec_at, batch stride Vs)
+template <typename T>
+__device__ __forceinline__ T* rec_t_at(const Dev<T>& D, int k, int v) {
+    return D.rec_t + (size_t(k) * (D.Vs / kRecTile) + size_t(v / kRecTile)) * (kRecFields * kRecTile) + (v % kRecTile) * rl<T>();
+}
 
 // The per-template solver scalars (2 KB for all templates) copied into shared memory at the start of a kernel:
 // every thread of the step-parallel stages reads a dozen of them behind the load of its instance's template id, and
@@ -689,25 +737,50 @@ __device__ __forceinline__ void add_constraint_ref(bool alm, T c, const T* c_dot
 // model Jacobians l_u, l_uu, A, B) of step k of instance b.  masked != 0 (inside the solver): first commit an
 // accepted trial, then differentiate only where the record is stale.
 template <typename T, bool kAlm>
-__device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int part, int masked) {
+__device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int part, int masked, int slot = -1) {
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
 
     T x[4], ua = 0, us = 0;
     int ri = 0;
     // src: trial slot to commit; tsrc: trial slot to differentiate (-1 = the current trajectory's own arrays).
-    // masked == 2 (look-ahead rounds): the slot to commit is the one k_adopt took over from the verdict kernel, and
-    // what is differentiated is this round's job: a trial of the running line search (speculation), or the current
-    // trajectory where its record is stale.
+    // Look-ahead rounds.  masked == 2: the slot to commit is the one k_adopt took over from the verdict kernel, and what
+    // is differentiated (into the instance's record) is the instance's own job: a trial of its running line search, or
+    // the current trajectory where its record is stale.  masked == 3: the speculative job of trial slot `slot` (owned
+    // by instance b): its trajectory, into the slot's own record.
     int src = -1, tsrc = -1;
     bool diff = true;
     if (masked == 1) {
         src = tsrc = D.commit_src[b];
     } else if (masked == 2) {
-        src = D.cur_src[b];
+        src = tsrc = D.cur_src[b];
         const int job = job_of(D, b);
         diff = job >= 0 || (job == -1 && !D.rec_valid[b]);
-        tsrc = job >= 0 ? job : src;
+        if (job >= 0) tsrc = job;  // the instance's own job speculates on a trial of its running line search
+        if (src >= 0 && D.gsel[b] == 2) {
+            // the slot was adopted together with its job: its record and gains become the instance's (copy 0)
+            const T* rs = rec_t_at(D, k, src);
+            T* rd = rec_at(D, k, b);
+            if (part == 0) {
+#pragma unroll
+                for (int c = kRecLx; c < kRecLu; ++c) rd[rf<T>(c)] = rs[rf<T>(c)];
+                if (k < N) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) D.Kg[at(Bs, k, c, 8, b)] = D.Kg_t[at(Vs, k, c, 8, src)];
+                }
+            } else if (k < N) {
+#pragma unroll
+                for (int c = kRecLu; c < kRecFields; ++c) rd[rf<T>(c)] = rs[rf<T>(c)];
+                D.dg[at(Bs, k, 0, 2, b)] = D.dg_t[at(Vs, k, 0, 2, src)];
+                D.dg[at(Bs, k, 1, 2, b)] = D.dg_t[at(Vs, k, 1, 2, src)];
+                if (k == 0) {
+                    D.dV[b] = D.dV_t[src];
+                    D.dV[Bs + b] = D.dV_t[Vs + src];
+                }
+            }
+        }
+    } else if (masked == 3) {
+        tsrc = slot;
     }
     if (src >= 0) {
         // the accepted trial becomes the current trajectory; part 1 reads the state from the
@@ -752,7 +825,7 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
     const DevParams<T>& P = D.P[D.tmpl[b]];
     const bool alm = kAlm && P.solve_type == 1;
     const T rho = alm ? D.rho[b] : T(0);
-    T* rec = rec_at(D, k, b);
+    T* rec = masked == 3 ? rec_t_at(D, k, slot) : rec_at(D, k, b);
     if (part == 0) {
     const T rx = D.wx[P.wp_off + ri], ry = D.wy[P.wp_off + ri], ryaw = D.wyaw[P.wp_off + ri];
     const T ref[4] = {rx, ry, D.ref_velo[b], ryaw};
@@ -1029,8 +1102,11 @@ template <typename T, int kPart, bool kAlm>
 #ifndef CILQR_DERIVS1_MINB
 #define CILQR_DERIVS1_MINB 8
 #endif
-__global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIVS0_MINB : CILQR_DERIVS1_MINB)) k_derivs(Dev<T> D, int B, int masked, int par) {
+__global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIVS0_MINB : CILQR_DERIVS1_MINB)) k_derivs(Dev<T> D, int B, int masked, int par, int slot_y0 = 0) {
     __shared__ DevParams<T> sP[CILQR_B200_MAX_TEMPLATES];
+    // (blocks with nothing to do leave before staging the parameters)
+    if (masked == 2 && int(blockIdx.y) >= slot_y0 && (int(blockIdx.y) - slot_y0) * int(blockDim.x) >= view_count(D, 1, B)) return;
+    if (masked == 2 && int(blockIdx.y) < slot_y0 && int(blockIdx.y) * int(blockDim.x) >= D.ctl[CTL_NACT + par]) return;
     D.P = stage_params(D, sP);
     const size_t Bs = D.Bs;
     // two independent halves per (instance, step): part 0 = state terms (l_x, l_xx), part 1 = control
@@ -1043,7 +1119,17 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
     // solver: only the instances on this round's work list (running, or with a step to commit)
     const int* list = masked ? D.act + size_t(par) * Bs : nullptr;
     const int n = masked ? D.ctl[CTL_NACT + par] : B;
-    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n; idx += gridDim.y * blockDim.x)
+    if (masked == 2 && int(blockIdx.y) >= slot_y0) {
+        // look-ahead rounds: the blocks from slot_y0 on take the speculative jobs of this round's trial slots
+        const int nv = view_count(D, 1, B);
+        for (int i = (blockIdx.y - slot_y0) * blockDim.x + threadIdx.x; i < nv; i += (gridDim.y - slot_y0) * blockDim.x) {
+            const int v = D.pool_base + i;
+            if (D.t_job[v]) derivs_item<T, kAlm>(D, D.t_inst[v], k, part, 3, v);
+        }
+        return;
+    }
+    const int ny = masked == 2 ? slot_y0 : int(gridDim.y);
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n; idx += ny * blockDim.x)
         derivs_item<T, kAlm>(D, list ? list[idx] : idx, k, part, masked);
 }
 
@@ -1460,7 +1546,7 @@ __device__ __forceinline__ void claim_slots(const Dev<T>& D, int b, int want, in
     }
     int total = __shfl_sync(0xffffffffu, incl, 31);
     int base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(&D.ctl[CTL_NV], total);
+    if (lane == 31 && total > 0) base = atomicAdd(&D.ctl[nv_index(D)], total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (want > 0) {
         const int r0 = base + incl - want;  // position inside this round's (half of the) pool
@@ -1618,23 +1704,32 @@ struct StagedRing {
 };
 
 // The backward pass of tile `tile` (32 consecutive instances, lane = instance) by the calling warp; see
-// k_backward_staged.  tile_slots < 0: slots claimed from the global trial pool (claim_slots); otherwise from the
-// tile's private region and the number of slots in use is returned.
+// k_backward_staged.  solver: 0 the stand-alone operator; 1 inside the sequential rounds (state transitions and slot
+// claims follow: tile_slots < 0: slots claimed from the global trial pool (claim_slots); otherwise from the tile's
+// private region and the number of slots in use is returned); 2 look-ahead rounds, the instances' own jobs (into the
+// spare copy of their gains); 3 look-ahead rounds, the speculative jobs of a tile of 32 trial slots (tile counts
+// slots of this round's half of the pool; records and gains are the slots' own arrays).
 template <typename T>
 __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, int tile, int B, int solver, int lane,
                                              int tile_base, int tile_slots) {
     const int N = D.N;
-    const size_t Bs = D.Bs;
     constexpr unsigned kStepBytes = kRecFields * 32 * sizeof(T);
-    const int b = tile * 32 + lane;
-    const bool in = b < B;
+    // index of my trajectory in the arrays the pass works on (instances: stride Bs; trial slots: stride Vs)
+    const bool slots = solver == 3;
+    const size_t S = slots ? size_t(D.Vs) : size_t(D.Bs);
+    const int first = slots ? D.pool_base + tile * 32 : tile * 32;
+    const int end = slots ? D.pool_base + view_count(D, 1, B) : B;
+    const int b = first + lane;
+    const bool in = b < end;
     int ph = PH_DONE;
     bool run = false;
     if (in) {
         if (!solver) {
             run = true;
+        } else if (solver == 3) {
+            run = D.t_job[b] != 0;
         } else if (solver == 2) {
-            run = job_of(D, b) != -2;  // look-ahead rounds: this round's job, into the spare copy of the gains
+            run = job_of(D, b) != -2;
         } else {
             D.commit_src[b] = -1;  // consumed by the derivative stage just before
             D.t_count[b] = 0;
@@ -1642,37 +1737,46 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
             run = ph == PH_BACKWARD;
         }
     }
-    const int gs = (solver == 2 && in) ? (D.gsel[b] ^ 1) : 0;
+    // where the gains go: the instance's arrays (sequential rounds, stand-alone operator), the spare copy of the
+    // instance's gains (copy 1 while the current ones are copy 0 or still in a slot, else copy 0), the slot's arrays
+    int gs = 0;
+    if (solver == 2 && in) gs = D.gsel[b] == 1 ? 0 : 1;
+    T* const Kbase = slots ? D.Kg_t : Kg_of(D, gs);
+    T* const dbase = slots ? D.dg_t : dg_of(D, gs);
+    T* const dVbase = slots ? D.dV_t : dV_of(D, gs);
+    T* const recbase = slots ? D.rec_t : D.rec;
     bool ok = true;
     if (__any_sync(0xffffffffu, run)) {
-        const T* tile_rec = rec_at(D, 0, tile * 32);
+        // field 0 of the tile's record of step 0; the record of step k is k * kRecFields * S scalars further on
+        const T* tile_rec = recbase + size_t(first / kRecTile) * (kRecFields * kRecTile);
         // the tile's record of step `step` (one contiguous block) -> ring slot issued % kStagedStages
         auto issue = [&](int step) {
             const unsigned s = R.issued % kStagedStages;
             if (lane == 0) {
                 const unsigned bar = smem_addr(&R.full[s]);
                 mbar_arrive_expect_tx(bar, kStepBytes);
-                bulk_load(smem_addr(&R.stage[s][0][0]), tile_rec + size_t(step) * kRecFields * Bs, kStepBytes, bar);
+                bulk_load(smem_addr(&R.stage[s][0][0]), tile_rec + size_t(step) * kRecFields * S, kStepBytes, bar);
             }
             ++R.issued;
         };
         for (int j = 0; j < kStagedStages && j < N; ++j) issue(N - 1 - j);
-        const T lamb = run ? (solver == 2 ? D.job_lamb[b] : D.lamb[b]) : T(0);
+        T lamb = T(0);
+        if (run) lamb = solver == 3 ? D.jlamb_t[b] : (solver == 2 ? D.job_lamb[b] : D.lamb[b]);
         T Vx[4], V[kVN];
         {
-            const T* rec = rec_at(D, N, in ? b : 0);
+            const T* rec = tile_rec + size_t(N) * kRecFields * S + (in ? lane : 0) * rl<T>();
 #pragma unroll
             for (int c = 0; c < 4; ++c) Vx[c] = rec[rf<T>(kRecLx + c)];
             load_terminal_V(rec, V);
         }
         T dV0 = 0, dV1 = 0;
-        T* Kp = Kg_of(D, gs) + size_t(N) * 8 * Bs + (in ? b : 0);
-        T* dp = dg_of(D, gs) + size_t(N) * 2 * Bs + (in ? b : 0);
+        T* Kp = Kbase + size_t(N) * 8 * S + (in ? b : first);
+        T* dp = dbase + size_t(N) * 2 * S + (in ? b : first);
         for (int i = N - 1; i >= 0; --i) {
             const unsigned s = R.consumed % kStagedStages, parity = (R.consumed / kStagedStages) & 1u;
             ++R.consumed;
-            Kp -= 8 * Bs;
-            dp -= 2 * Bs;
+            Kp -= 8 * S;
+            dp -= 2 * S;
             mbar_wait(smem_addr(&R.full[s]), parity);
             if (run) {
                 T K[8] = {0, 0, 0, 0, 0, 0, 0, 0}, d0 = 0, d1 = 0;
@@ -1688,22 +1792,21 @@ __device__ __forceinline__ int backward_tile(const Dev<T>& D, StagedRing<T>& R, 
                     }
                 }
                 dp[0] = d0;
-                dp[Bs] = d1;
+                dp[S] = d1;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) Kp[size_t(c) * Bs] = K[c];
+                for (int c = 0; c < 8; ++c) Kp[size_t(c) * S] = K[c];
             }
             __syncwarp();  // every lane is done with slot s
             if (i - kStagedStages >= 0) issue(i - kStagedStages);
         }
         if (run) {
-            T* dVp = dV_of(D, gs);
-            dVp[b] = dV0;
-            dVp[Bs + b] = dV1;
+            dVbase[b] = dV0;
+            dVbase[S + b] = dV1;
         }
     }
     if (in && !solver) D.status[b] = ok ? ST_RUNNING : ST_BWD_FAIL;
-    if (solver == 2) {
-        if (run) D.job_ok[b] = ok;
+    if (solver >= 2) {
+        if (run) (solver == 3 ? D.jok_t : D.job_ok)[b] = ok;
         return 0;
     }
     int want = 0, a0 = 0;
@@ -1730,7 +1833,12 @@ __global__ void __launch_bounds__(32) k_backward_staged(Dev<T> D, int B, int sol
     __syncwarp();
     StagedRing<T> R{stage, full, 0u, 0u};
     const int n_tiles = (B + 31) / 32;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) backward_tile(D, R, tile, B, solver, lane, 0, -1);
+    // look-ahead rounds: the tiles of this round's trial slots (speculative jobs) first, then the instances' own jobs
+    const int n_slot_tiles = solver == 2 ? (view_count(D, 1, B) + 31) / 32 : 0;
+    for (int t = blockIdx.x; t < n_slot_tiles + n_tiles; t += gridDim.x) {
+        if (t < n_slot_tiles) backward_tile(D, R, t, B, 3, lane, 0, -1);
+        else backward_tile(D, R, t - n_slot_tiles, B, solver, lane, 0, -1);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1946,7 +2054,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 // trial).  Positions travel through pos[step][trial][2]; step k is handed over by an arrival on the mbarrier
 // bars[k] (release) that the scan warps wait for (acquire) in phase `parity` — every barrier completes exactly
 // one phase per call, so the caller alternates parity and separates calls by a block-wide barrier.
-template <typename T, int G>
+template <typename T, int G, bool kLa>
 __device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kPipeTrials][2], unsigned long long* bars,
                                                     unsigned parity, int base, int count, bool roller, int scan_warp, int lane) {
     const int N = D.N;
@@ -1970,13 +2078,23 @@ __device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kP
         // the trajectory the search starts from: the instance's own arrays or, in a look-ahead solve, the trial
         // slot of the previous round that was accepted and is being copied there meanwhile; its gains: the
         // instance's current copy
-        const int cs = D.spec ? D.cur_src[b] : -1;
-        const T* Xc = cs >= 0 ? D.Xt + cs : D.X + b;
-        const T* Uc = cs >= 0 ? D.Ut + cs : D.U + b;
-        const size_t xs = cs >= 0 ? Vs : Bs;
-        const int gs = gains_sel(D, b);
-        const T* Kc = Kg_of(D, gs) + b;
-        const T* dc = dg_of(D, gs) + b;
+        // (kLa = false, the sequential rounds: always the instance's own arrays — base pointers from the parameter
+        // bank, no registers on a chain that has none to spare)
+        const int cs = kLa ? D.cur_src[b] : -1;
+        const T* Xc = (kLa && cs >= 0) ? D.Xt + cs : D.X + b;
+        const T* Uc = (kLa && cs >= 0) ? D.Ut + cs : D.U + b;
+        const size_t xs = (kLa && cs >= 0) ? Vs : Bs;
+        GainsAt<T> Gc;
+        if (kLa) {
+            Gc = gains_at(D, b);
+        } else {
+            Gc.K = D.Kg + b;
+            Gc.d = D.dg + b;
+            Gc.stride = Bs;
+        }
+        const T* Kc = Gc.K;
+        const T* dc = Gc.d;
+        const size_t gst = Gc.stride;
         // lane `role` of a pair owns control row `role`: its feedback row, u and d
         T xn[4], cx[4], cK[4], cu, cd;
 #pragma unroll
@@ -1994,18 +2112,18 @@ __device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kP
         for (int c = 0; c < 4; ++c)
             if (live && role == 0) D.Xt[at(Vs, 0, c, 4, v)] = xn[c];
         cu = Uc[size_t(role) * xs];
-        cd = dc[size_t(role) * Bs];
+        cd = dc[size_t(role) * gst];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) cK[c] = Kc[size_t(role * 4 + c) * Bs];
+        for (int c = 0; c < 4; ++c) cK[c] = Kc[size_t(role * 4 + c) * gst];
         for (int i = 0; i < N; ++i) {
             T nxx[4], nxK[4], nxu, nxd;
             const int ip = i + 1 < N ? i + 1 : i;
 #pragma unroll
             for (int c = 0; c < 4; ++c) nxx[c] = ld_early(Xc + size_t(ip * 4 + c) * xs);
             nxu = ld_early(Uc + size_t(ip * 2 + role) * xs);
-            nxd = ld_early(dc + size_t(ip * 2 + role) * Bs);
+            nxd = ld_early(dc + size_t(ip * 2 + role) * gst);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) nxK[c] = ld_early(Kc + size_t(ip * 8 + role * 4 + c) * Bs);
+            for (int c = 0; c < 4; ++c) nxK[c] = ld_early(Kc + size_t(ip * 8 + role * 4 + c) * gst);
             T fb = 0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) fb += cK[c] * (xn[c] - cx[c]);
@@ -2091,8 +2209,8 @@ __device__ __forceinline__ void rollout_match_group(const Dev<T>& D, T (*pos)[kP
 
 // G = scan lanes per trial: 16 (two blocks per SM) when the whole trial pool fits one wave that way,
 // 8 (four blocks per SM, a slower but still hidden scan) beyond that.
-template <typename T, int G>
-__global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_match(Dev<T> D, int B) {
+template <typename T, int G, bool kLa = false>
+__global__ void __launch_bounds__(pipe_threads(G), kLa ? 1 : (G == 16 ? 2 : 4)) k_rollout_match(Dev<T> D, int B) {
     __shared__ T pos[kPipeMaxSteps][kPipeTrials][2];
     __shared__ __align__(8) unsigned long long bars[kPipeMaxSteps];  // bars[k]: positions of step k are in the ring
     const int count = view_count(D, 1, B);
@@ -2104,7 +2222,7 @@ __global__ void __launch_bounds__(pipe_threads(G), G == 16 ? 2 : 4) k_rollout_ma
     // (slots are absolute: a look-ahead solve alternates between the two halves of the pool)
     const int v_end = D.pool_base + count;
     for (int base = D.pool_base + blockIdx.x * kPipeTrials; base < v_end; base += gridDim.x * kPipeTrials, parity ^= 1u) {
-        rollout_match_group<T, G>(D, pos, bars, parity, base, v_end, warp == 0, warp - 1, lane);
+        rollout_match_group<T, G, kLa>(D, pos, bars, parity, base, v_end, warp == 0, warp - 1, lane);
         __syncthreads();  // the ring is reused by the next group of trials
     }
 }
@@ -2118,8 +2236,8 @@ __device__ __forceinline__ void decide_instance(const Dev<T>& D, int b, int cnt)
     const int v0 = D.t_first[b];
     const int a0 = D.aidx[b];
     const T J_cur = D.J_cur[b];
-    const T* dVc = dV_of(D, gains_sel(D, b));
-    const T dV0 = dVc[b], dV1 = dVc[Bs + b];
+    const GainsAt<T> Gc = gains_at(D, b);
+    const T dV0 = Gc.dV[0], dV1 = Gc.dV[Gc.stride];
     bool ended = false;
     T last_J = J_cur;  // cost of the last trial looked at: what iter_step returns when every alpha was rejected (cpp:380)
     // trial costs four at a time (independent loads), then their verdicts in alpha order; the
@@ -2288,7 +2406,8 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
             D.ctl[CTL_ROUND] = round;
             *reinterpret_cast<unsigned long long*>(&D.ctl[CTL_TRIALS]) += static_cast<unsigned long long>(trials);
             *tally = 0ull;
-            D.ctl[CTL_NV] = 0;
+            // (look-ahead solves: this round's count is still being read on the other stream; re-arm the next round's)
+            D.ctl[D.spec ? CTL_NV2 + ((D.round_id + 1) & 1) : int(CTL_NV)] = 0;
             D.ctl[CTL_CHUNK] = 0;
             // consumed; the verdict kernel of the next round refills it (look-ahead solves: the derivative kernel of
             // this round, on the other stream, may still be reading it — k_adopt clears it)
@@ -2311,20 +2430,23 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
 // derivatives and the backward pass of the NEXT iteration depend on the verdict only through WHICH trajectory was
 // accepted and the regularisation that follows from it, and 96 % of the iterations of the slowest instances accept
 // the full step (alpha = 1, lambda *= decay).  So a round runs, next to the cost and verdict kernels of its trials
-// (stream A), a backward "job" per instance on a second stream (B): derivatives (k_derivs, masked = 2) and the
-// recursion (k_backward_staged, solver = 2) of
-//     * the alpha = 1 trial of the running line search, with lambda * decay  (speculation), or
-//     * the current trajectory with the current lambda, for an instance that has nothing to roll out this round
-//       (first iteration, after a rejected / shortened step, after a failed backward pass),
-// writing into the spare copy of the gains.  k_adopt joins the two streams: where the verdict asks for exactly the
-// backward pass the job ran (same trajectory, same lambda — bitwise), the spare copy becomes the current one and
-// the instance goes straight on to its next line search; otherwise the instance gets a job for what it needs and
-// sits the next round out.  Every instance performs the reference's sequence of operations on the same values —
-// the result bits do not depend on the mode — but an iteration costs rollout + derivatives + recursion instead of
-// the whole chain.  The derivative records of a speculated trial overwrite the instance's (rec_valid = 0 on a
-// miss: the reference's cache of cpp:469-474 is recomputed, same bits); accepted trials are copied into the
-// instance's arrays by the next round's derivative kernel while the rollouts read them from the slot (cur_src),
-// which is why a look-ahead solve alternates between two halves of the trial pool.
+// (stream A), backward "jobs" on a second stream (B): derivatives (k_derivs, masked = 2 / 3) and the recursion
+// (k_backward_staged, solver = 2 / 3) of
+//     * the trials of the running line searches, one job per trial slot, each with the lambda that follows if it is
+//       the accepted one (lambda * decay for alpha = 1, lambda otherwise) — records and gains in the slot's own arrays
+//       (rec_t, Kg_t, dg_t, dV_t); the alpha = 1 trial always, the others while the work list is short;
+//     * the instance's current trajectory — with lambda amplified, for a line search that is evaluating its last
+//       alphas (the all-rejected outcome, cpp:375-380), or with the current lambda for an instance that has nothing
+//       to roll out this round (first iteration, a verdict no job covered, a failed backward pass) — into the spare
+//       copy of the instance's gains.
+// k_adopt joins the two streams: where the verdict asks for exactly a backward pass that ran (same trajectory, same
+// lambda — bitwise), its gains become the instance's current ones (gsel) and the instance goes straight on to its
+// next line search; otherwise it gets a job for what it needs and sits the next round out.  Every instance performs
+// the reference's sequence of operations on the same values — the result bits do not depend on the mode — but an
+// iteration costs rollout + derivatives + recursion instead of the whole chain.  An accepted trial (with its record
+// and gains, if its job was adopted) is copied into the instance's arrays by the next round's derivative kernel
+// while the rollouts and the verdict read it from the slot (cur_src, gsel = 2), which is why a look-ahead solve
+// alternates between two halves of the trial pool.
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) k_adopt(Dev<T> D, int par_next) {
@@ -2333,6 +2455,9 @@ __global__ void __launch_bounds__(128) k_adopt(Dev<T> D, int par_next) {
     const int* list = D.act + size_t(par_next) * Bs;
     const int n = D.ctl[CTL_NACT + par_next];
     const int n_pad = (n + 31) & ~31;  // whole warps: claim_slots is a warp collective
+    // every trial of a line search gets a job (and its all-rejected outcome one on the instance) once the work list is
+    // short; a long list speculates on the full step only (a job costs a derivative pass and a recursion)
+    const bool spec_all = n <= D.spec_all_below;
     if (blockIdx.x == 0 && threadIdx.x == 0) D.ctl[CTL_NACT + (par_next ^ 1)] = 0;  // the list this round consumed
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_pad; idx += gridDim.x * blockDim.x) {
         const bool in = idx < n;
@@ -2340,26 +2465,64 @@ __global__ void __launch_bounds__(128) k_adopt(Dev<T> D, int par_next) {
         int want = 0, a0 = 0;
         if (in) {
             const int cs = D.commit_src[b];  // accepted this round (a slot of this round's half), or -1
-            D.cur_src[b] = cs;
-            D.commit_src[b] = -1;
-            D.t_count[b] = 0;
+            int g = D.gsel[b];
+            if (g == 2) g = 0;  // the slot adopted a round ago has been copied into copy 0 meanwhile (k_derivs)
             int ph = D.phase[b];
             const int job = D.job_round[b] == D.round_id - 1 ? D.job_src[b] : -2;  // the round that just ended
             D.job_round[b] = D.round_id;
-            // the backward pass the verdict asks for: over trajectory cs (-1 = the unchanged current one) with lamb[b]
-            const bool hit = ph == PH_BACKWARD && job != -2 && job == cs && D.job_lamb[b] == D.lamb[b];
-            if (hit) D.gsel[b] ^= 1;
-            else if (job >= 0) D.rec_valid[b] = 0;  // the speculated trial's record replaced the current trajectory's
-            after_backward(D, b, hit, hit && D.job_ok[b] != 0, ph, &want, &a0);
+            // The backward pass the verdict asks for is the one over trajectory cs (-1 = the unchanged current one)
+            // with lamb[b]: adopted if a job ran exactly that — the accepted slot's, or the instance's own.
+            bool hit = false, ok = false;
+            if (ph == PH_BACKWARD) {
+                const T lamb = D.lamb[b];
+                if (job != -2 && job == cs && D.job_lamb[b] == lamb) {
+                    // the instance's own job: over the trial that was accepted (cs >= 0), or over the unchanged
+                    // current trajectory (cs == -1)
+                    hit = true;
+                    ok = D.job_ok[b] != 0;
+                    g ^= 1;  // the spare copy becomes the current one
+                } else if (cs >= 0 && D.t_job[cs] && D.jlamb_t[cs] == lamb) {
+                    hit = true;
+                    ok = D.jok_t[cs] != 0;
+                    g = 2;  // gains (and record) stay in the slot's arrays for the coming round
+                }
+            }
+            // (a job of the instance over a trial wrote that trial's record over the current trajectory's)
+            if (job >= 0 && !(hit && g != 2)) D.rec_valid[b] = 0;
+            D.gsel[b] = g;
+            D.cur_src[b] = cs;
+            D.commit_src[b] = -1;
+            D.t_count[b] = 0;
+            after_backward(D, b, hit, ok, ph, &want, &a0);
             ph = D.phase[b];
+            // an instance that still needs a backward pass runs it next round (and sits the rollouts out)
             D.job_src[b] = ph == PH_BACKWARD ? -1 : -2;
             if (ph == PH_BACKWARD) D.job_lamb[b] = D.lamb[b];
         }
         claim_slots(D, b, want, a0, lane);  // D.pool_base / pool_cap: the half of the pool the next round uses
-        if (in && want > 0 && a0 == 0 && D.t_count[b] > 0) {
-            // speculate on the full step: accepted with status RUNNING, lambda *= decay (end_iteration)
-            D.job_src[b] = D.t_first[b];
-            D.job_lamb[b] = D.lamb[b] * D.P[D.tmpl[b]].lamb_decay;
+        if (in && want > 0) {
+            const int cnt = D.t_count[b], v0 = D.t_first[b];
+            const DevParams<T>& P = D.P[D.tmpl[b]];
+            const T lamb = D.lamb[b];
+            // the backward pass that follows if trial i is the accepted one: lambda *= decay after a full step
+            // (ST_RUNNING), unchanged after a shortened one (ST_SMALL_STEP) — end_iteration
+            // The instance's own job takes the likeliest outcome and costs no copies when adopted (record and gains
+            // are written where the instance keeps them): the full step, or — once the round evaluates the last
+            // alpha — every step rejected (ST_FWD_FAIL: the current record, recomputed if a job overwrote it, with
+            // lambda amplified).  The other trials get jobs of their own slot while the work list is short.
+            const bool last = spec_all && cnt > 0 && a0 + cnt >= kNumAlphas;
+            for (int i = 0; i < cnt; ++i) {
+                const int a = a0 + i;
+                D.t_job[v0 + i] = ((a == 0 && last) || (a > 0 && spec_all)) ? 1 : 0;
+                D.jlamb_t[v0 + i] = a == 0 ? lamb * P.lamb_decay : lamb;
+            }
+            if (last) {
+                D.job_src[b] = -1;
+                D.job_lamb[b] = std_max(P.lamb_amplify, lamb * P.lamb_amplify);
+            } else if (a0 == 0 && cnt > 0) {
+                D.job_src[b] = v0;
+                D.job_lamb[b] = lamb * P.lamb_decay;
+            }
         }
     }
 }
@@ -2372,7 +2535,7 @@ __global__ void __launch_bounds__(128) k_gains_home(Dev<T> D, int B) {
     const int N = D.N;
     const int row = blockIdx.y;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-        if (!D.gsel[b]) continue;
+        if (D.gsel[b] != 1) continue;  // (2: the final commit has just copied the slot's gains into copy 0)
         if (row < N * 8) D.Kg[size_t(row) * Bs + b] = Kg_of(D, 1)[size_t(row) * Bs + b];
         else if (row < N * 10) D.dg[size_t(row - N * 8) * Bs + b] = dg_of(D, 1)[size_t(row - N * 8) * Bs + b];
         else D.dV[size_t(row - N * 10) * Bs + b] = dV_of(D, 1)[size_t(row - N * 10) * Bs + b];
