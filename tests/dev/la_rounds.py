@@ -12,6 +12,7 @@ os.environ["CILQR_PROFILE_DUMP"] = path
 with cb.BatchSolver(pb.templates, B, N, pb.max_obs, dt) as s:
     s.upload(pb)
     s.set_option(s.OPT_LOOKAHEAD, 16384 if la else 0)
+    if len(sys.argv) > 3: s.set_option(s.OPT_STAGED_BACKWARD, int(sys.argv[3]))
     s.solve_resident(B)
     s.set_option(s.OPT_PROFILE_STAGES, 1)
     s.solve_resident(B)

@@ -109,7 +109,8 @@ def test_kernel_variants_return_the_same_bits(cfg, dtype):
     outs = []
     with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, dtype) as s:
         for threshold, pipe, staged in ((1 << 30, 0, 1), (1 << 30, 16, 1), (1 << 30, 8, 0), (1 << 30, 1, 0),
-                                        (1 << 30, 1, 1), (0, 1, 1), (100, 1, 1)):
+                                        (1 << 30, 1, 1), (0, 1, 1), (100, 1, 1), (1 << 30, 1, 2), (1 << 30, 0, 2)):
+            # staged 2: the backward pass on four lanes per trajectory (k_backward_lanes)
             # threshold 100: the solve starts on the throughput kernels and moves to the latency ones
             # (work-list variants) once fewer than 100 instances are still running
             s.set_option(s.OPT_PREFETCH_BELOW, threshold)

@@ -76,7 +76,9 @@ struct Base {
     int bench_prefetch = -1;  // stage operator / roofline leg: -1 = the variant the solver uses at that batch
     unsigned scan_epoch = 0;  // tags the look-back words of one verdict launch (never 0, 30 bits)
     int pipeline = 1;  // latency regime: rollout and waypoint match as one two-stage kernel
-    int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
+    int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory (2: four lanes per
+                       // trajectory — 28 % fewer instructions per warp and step but 4.2 instead of 3.2 clocks per
+                       // instruction: 45 against 47 us per launch, profiles/r02_backward_lanes.txt; not the default)
     int wide_step = 1; // bandwidth-bound rounds widen a line search step by step (2, 4, 8, 6 alphas) instead of all at once
     int repack = 1;    // survivors moved into a dense prefix whenever they are down to half of the slots in use
     // look-ahead rounds (k_adopt): batches up to lookahead_below run next iteration's backward pass alongside the
@@ -436,6 +438,20 @@ static const int kBwThreads = [] { const char* e = getenv("CILQR_BW_THREADS"); c
 inline dim3 bw_grid(int n) { return dim3(std::max(1, std::min((n + kBwThreads - 1) / kBwThreads, 2 * kGridCap))); }
 // k_backward_staged: one warp per tile of 32 instances, at most 16 warps per SM
 inline dim3 staged_grid(int B) { return dim3(std::max(1, std::min((B + 31) / 32, 148 * 16))); }
+// The staged backward pass over `count` trajectories (tiles of 32): one warp per tile (k_backward_staged), or —
+// h->staged == 2 — four lanes per trajectory, one CTA of four warps per tile (k_backward_lanes).  Same bits.
+template <typename T>
+inline void launch_staged_backward(Base* h, cudaStream_t st, const Dev<T>& D, int count, int B, int solver) {
+#ifndef CILQR_PARITY
+    if (h->staged == 2) {
+        k_backward_lanes<T><<<dim3(std::max(1, std::min((count + 31) / 32, 148 * 8))), 128, 0, st>>>(D, B, solver);
+        h->launches++;
+        return;
+    }
+#endif
+    k_backward_staged<T><<<staged_grid(count), 32, 0, st>>>(D, B, solver);
+    h->launches++;
+}
 // step-parallel stages (k_cost, k_derivs): x = step, y = blocks of trajectories
 inline dim3 gk(int count, int rows) { return dim3(rows, std::max(1, std::min((count + 127) / 128, kGridCap))); }
 
@@ -855,7 +871,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
                 LAUNCH_ON(h, sb, (k_derivs<T, -1, false>), dim3(2 * (N + 1), y_list + y_slots), 128, Dl, B, 2, par, y_list);
             }
             mark_stage_b(h, 1);
-            LAUNCH_ON(h, sb, k_backward_staged<T>, staged_grid(B + (launched > 0 ? std::min(trial_bound, 2 * n_bound + 1024) : 0)), 32, Dl, B, 2);
+            launch_staged_backward<T>(h, sb, Dl, B + (launched > 0 ? std::min(trial_bound, 2 * n_bound + 1024) : 0), B, 2);
             if (la_serial == 2) CK(cudaDeviceSynchronize());
             mark_stage_b(h, -1);
             CK(cudaEventRecord(h->ev_join[e], sb));
@@ -895,7 +911,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         h->D.wide_step = (!lat && h->wide_step) ? 1 : 0;
         switch (backward_variant<T>(h, n_bound, B, lat)) {
             case 2:  // small batch: one warp per tile of 32 instances, records staged through shared memory
-                LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 1);
+                launch_staged_backward<T>(h, h->stream, h->D, B, B, 1);
                 break;
             case 1:  // a short work list is spread over one warp per scheduler (see k_backward)
                 if (lat) LAUNCH(h, (k_backward<T, true>), gs1(std::max(n_bound, 148 * 128)), 128, h->D, B, 1, par);
@@ -1216,7 +1232,7 @@ int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const 
     {
         const int variant = h->bench_prefetch >= 0 ? h->bench_prefetch : backward_variant<T>(h, B, B, B <= h->prefetch_below);
         if (variant == 2) {
-            LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
+            launch_staged_backward<T>(h, h->stream, h->D, B, B, 0);
         } else if (variant == 1) {
             LAUNCH(h, (k_backward<T, true>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
         } else {
@@ -1271,7 +1287,7 @@ int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float
         CK(cudaEventRecord(h->t0, h->stream));
         const int variant = h->bench_prefetch >= 0 ? h->bench_prefetch : backward_variant<T>(h, B, B, B <= h->prefetch_below);
         if (variant == 2) {
-            LAUNCH(h, k_backward_staged<T>, staged_grid(B), 32, h->D, B, 0);
+            launch_staged_backward<T>(h, h->stream, h->D, B, B, 0);
         } else if (variant == 1) {
             LAUNCH(h, (k_backward<T, true>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
         } else {
@@ -1530,7 +1546,7 @@ int do_set_option(Impl<T>* h, int option, int value) {
             h->pipeline = value;
             return 0;
         case CILQR_OPT_STAGED_BACKWARD:
-            h->staged = value ? 1 : 0;
+            h->staged = value < 0 ? 0 : (value > 2 ? 2 : value);  // 1: one lane per trajectory, 2: four
             return 0;
         case CILQR_OPT_WIDE_STEP:
             h->wide_step = value ? 1 : 0;
