@@ -1,3 +1,2 @@
-timeout 300 python tests/dev/lookahead_dbg.py C1:4096:f64 C3:4096:f64 C1:4096:f32 C2:2048:f64 2>&1 | grep -v "^    " 
-timeout 300 python tests/dev/lookahead_ab.py C1:4096:f64 C1:1024:f64 C3:4096:f64 C1:256:f64 2>&1
-python tests/dev/la_stages.py C1:4096:f64 2>&1 | tail -1; python tests/dev/la_stages.py C1:1024:f64 2>&1 | tail -1
+for m in 0 1; do echo "== CILQR_LA_COST_LATE=$m"; CILQR_LA_COST_LATE=$m python tests/dev/lookahead_ab.py C1:256:f64 C1:512:f64 C1:1024:f64 2>&1 | grep "lookahead=1" | awk 'NR%2==0'; done
+python tests/dev/lookahead_ab.py C1:256:f64 C1:512:f64 C1:1024:f64 2>&1 | grep "lookahead=0\|same" | awk 'NR%3!=1'

@@ -11,24 +11,29 @@ path = "/tmp/prof_dump.txt"
 os.environ["CILQR_PROFILE_DUMP"] = path
 with cb.BatchSolver(pb.templates, B, N, pb.max_obs, dt) as s:
     s.upload(pb)
-    s.set_option(s.OPT_LOOKAHEAD, 16384 if la else 0)
+    s.set_option(s.OPT_LOOKAHEAD, la)
     if len(sys.argv) > 3: s.set_option(s.OPT_STAGED_BACKWARD, int(sys.argv[3]))
     s.solve_resident(B)
     s.set_option(s.OPT_PROFILE_STAGES, 1)
     s.solve_resident(B)
 rows = np.loadtxt(path)
-names = {0: "derivs", 1: "backward", 2: "forward", 3: "ref_match", 4: "cost", 5: "decide"}
+names = {0: "derivs", 1: "backward", 2: "forward", 3: "ref_match", 4: "cost", 5: "decide", -1: "gap"}
 S = rows[rows[:, 0] == 0]; Bm = rows[rows[:, 0] == 1]
-first = 2 if la else 0
-starts = np.where(S[:, 1] == first)[0]
-print("%s la=%d rounds=%d total %.2f ms" % (spec, la, len(starts), (S[-1, 2] + S[-1, 3]) / 1e3))
-for r, i0 in enumerate(starts):
-    i1 = starts[r + 1] if r + 1 < len(starts) else len(S)
-    d = {names[int(x[1])]: x[3] for x in S[i0:i1]}
-    t0 = S[i0, 2]; t1 = S[i1, 2] if i1 < len(S) else S[-1, 2] + S[-1, 3]
-    if la:
-        bb = Bm[2 * r: 2 * r + 2]
+ends = np.where(S[:, 1] == -1)[0]
+print("%s la=%d rounds=%d total %.2f ms" % (spec, la, len(ends), (S[-1, 2] + S[-1, 3]) / 1e3))
+i0 = 0
+bj = 0
+for r, e in enumerate(ends):
+    seg = S[i0:e]
+    d = {}
+    for x in seg: d[names[int(x[1])]] = d.get(names[int(x[1])], 0) + x[3]
+    t0 = seg[0, 2] if len(seg) else 0
+    t1 = S[e, 2] + S[e, 3]
+    is_la = len(seg) and int(seg[0, 1]) == 2
+    if is_la:
+        bb = Bm[(Bm[:, 2] >= t0) & (Bm[:, 2] < t1) & (Bm[:, 1] >= 0)]
         d.update({"B:" + names[int(x[1])]: x[3] for x in bb})
         if len(bb): d["B:start"] = bb[0, 2] - t0
-    if r < 6 or r % 10 == 0 or r > len(starts) - 4:
-        print("  round %3d: %.1f us  " % (r, t1 - t0), {k: round(float(v), 1) for k, v in d.items()})
+    if r < 4 or r % 10 == 0 or r > len(ends) - 4:
+        print("  round %3d %s: %.1f us  " % (r, "LA" if is_la else "  ", t1 - t0), {k: round(float(v), 1) for k, v in d.items()})
+    i0 = e + 1

@@ -9,7 +9,7 @@ pb = cb.synthetic_batch(cfg, B, N=N)
 with cb.BatchSolver(pb.templates, B, N, pb.max_obs, dt) as s:
     s.upload(pb)
     for la in (0, 1):
-        s.set_option(s.OPT_LOOKAHEAD, 16384 if la else 0)
+        s.set_option(s.OPT_LOOKAHEAD, la)
         s.set_option(s.OPT_PROFILE_STAGES, 0)
         ts = []
         for r in range(5):

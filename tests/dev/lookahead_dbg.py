@@ -14,7 +14,7 @@ for spec in specs:
         s.enable_trace(100)
         def run(la):
             s.reset()
-            s.set_option(s.OPT_LOOKAHEAD, 16384 if la else 0)
+            s.set_option(s.OPT_LOOKAHEAD, la)
             out = s.solve(pb)
             return out, s.get_trace(B), s.counters()
         ref, rtr, rc = run(0)

@@ -13,7 +13,7 @@ for max_iter in (1, 2):
     with cb.BatchSolver(pb.templates, B, N, pb.max_obs, dt) as s:
         s.set_option(s.OPT_RUN_AHEAD, run_ahead)
         def run(la):
-            s.reset(); s.set_option(s.OPT_LOOKAHEAD, 16384 if la else 0); return s.solve(pb)
+            s.reset(); s.set_option(s.OPT_LOOKAHEAD, la); return s.solve(pb)
         ref = run(0)
         for rep in range(8):
             out = run(1)

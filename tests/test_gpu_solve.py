@@ -109,8 +109,7 @@ def test_kernel_variants_return_the_same_bits(cfg, dtype):
     outs = []
     with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, dtype) as s:
         for threshold, pipe, staged in ((1 << 30, 0, 1), (1 << 30, 16, 1), (1 << 30, 8, 0), (1 << 30, 1, 0),
-                                        (1 << 30, 1, 1), (0, 1, 1), (100, 1, 1), (1 << 30, 1, 2), (1 << 30, 0, 2)):
-            # staged 2: the backward pass on four lanes per trajectory (k_backward_lanes)
+                                        (1 << 30, 1, 1), (0, 1, 1), (100, 1, 1)):
             # threshold 100: the solve starts on the throughput kernels and moves to the latency ones
             # (work-list variants) once fewer than 100 instances are still running
             s.set_option(s.OPT_PREFETCH_BELOW, threshold)
@@ -133,8 +132,10 @@ def test_lookahead_rounds_return_the_same_bits(cfg, B, dtype):
         s.set_option(s.OPT_LOOKAHEAD, 0)
         ref = s.solve(pb)
         rounds_ref = s.counters()["rounds"]
-        s.set_option(s.OPT_LOOKAHEAD, 16384)  # (an explicit bound: by default only batches up to 512 use them)
-        for rep in range(3):
+        # 16384: look-ahead rounds from the start; 1 (the default): from the round on in which no more than 512 instances
+        # are still running (the whole solve for a batch of that size); 64: a switch late in the solve
+        for rep, bound in enumerate((16384, 16384, 1, 64)):
+            s.set_option(s.OPT_LOOKAHEAD, bound)
             s.reset()
             out = s.solve(pb)
             for f in ("u", "x", "J", "K", "d", "iters", "status", "exit_reason", "step_cost"):

@@ -76,9 +76,7 @@ struct Base {
     int bench_prefetch = -1;  // stage operator / roofline leg: -1 = the variant the solver uses at that batch
     unsigned scan_epoch = 0;  // tags the look-back words of one verdict launch (never 0, 30 bits)
     int pipeline = 1;  // latency regime: rollout and waypoint match as one two-stage kernel
-    int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory (2: four lanes per
-                       // trajectory — 28 % fewer instructions per warp and step but 4.2 instead of 3.2 clocks per
-                       // instruction: 45 against 47 us per launch, profiles/r02_backward_lanes.txt; not the default)
+    int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
     int wide_step = 1; // bandwidth-bound rounds widen a line search step by step (2, 4, 8, 6 alphas) instead of all at once
     int repack = 1;    // survivors moved into a dense prefix whenever they are down to half of the slots in use
     // look-ahead rounds (k_adopt): batches up to lookahead_below run next iteration's backward pass alongside the
@@ -87,6 +85,7 @@ struct Base {
     int lookahead_below = 0;  // set at create: min(kLookaheadMaxBatch, max_batch) when the spare buffers exist
     cudaStream_t stream_b = nullptr;
     cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_mid[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> prof_ev_b;  // stage profile of the second stream
     std::vector<int> prof_stage_b;
     // optional in-step stage profile: CUDA events around every stage launch of one solve
@@ -363,6 +362,7 @@ int create_impl(const cilqr_params_t* params, int device, int max_batch, int N, 
             for (int i = 0; i < 4; ++i) {
                 CK(cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->ev_mid[i], cudaEventDisableTiming));
             }
             h->lookahead_below = kLookaheadMaxBatch;
         }
@@ -438,17 +438,9 @@ static const int kBwThreads = [] { const char* e = getenv("CILQR_BW_THREADS"); c
 inline dim3 bw_grid(int n) { return dim3(std::max(1, std::min((n + kBwThreads - 1) / kBwThreads, 2 * kGridCap))); }
 // k_backward_staged: one warp per tile of 32 instances, at most 16 warps per SM
 inline dim3 staged_grid(int B) { return dim3(std::max(1, std::min((B + 31) / 32, 148 * 16))); }
-// The staged backward pass over `count` trajectories (tiles of 32): one warp per tile (k_backward_staged), or —
-// h->staged == 2 — four lanes per trajectory, one CTA of four warps per tile (k_backward_lanes).  Same bits.
+// The staged backward pass over `count` trajectories (tiles of 32): one warp per tile.
 template <typename T>
 inline void launch_staged_backward(Base* h, cudaStream_t st, const Dev<T>& D, int count, int B, int solver) {
-#ifndef CILQR_PARITY
-    if (h->staged == 2) {
-        k_backward_lanes<T><<<dim3(std::max(1, std::min((count + 31) / 32, 148 * 8))), 128, 0, st>>>(D, B, solver);
-        h->launches++;
-        return;
-    }
-#endif
     k_backward_staged<T><<<staged_grid(count), 32, 0, st>>>(D, B, solver);
     h->launches++;
 }
@@ -783,22 +775,35 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // Look-ahead rounds (see k_adopt): the whole solve of a latency-bound batch.  Needs the piped rollout and the
     // staged backward pass (their look-ahead forms are the ones written), no augmented-Lagrangian template (its
     // multiplier updates re-cost the current trajectory between iterations) and the spare buffers of create.
-    const bool la = !kParity && h->lookahead && Bfull <= std::min(h->lookahead_below, h->lookahead > 1 ? h->lookahead : kLookaheadDefault) &&
-                    Bfull <= h->prefetch_below && h->staged &&
-                    h->pipeline && N + 1 <= kPipeMaxSteps && !h->any_alm;
+    // A larger batch (of a handle that has the buffers) starts with sequential rounds — with thousands of instances the
+    // stages are throughput-bound and the two streams only get in each other's way — and moves to look-ahead rounds
+    // once its work list is down to that size: la_ok = the solve may, la = it is doing so.
+    const int la_switch = std::min(h->lookahead_below, h->lookahead > 1 ? h->lookahead : kLookaheadDefault);
+    const bool la_ok = !kParity && h->lookahead && Bfull <= h->lookahead_below && Bfull <= h->prefetch_below && h->staged &&
+                       h->pipeline && N + 1 <= kPipeMaxSteps && !h->any_alm;
+    bool la = la_ok && Bfull <= la_switch;
+    // sequential rounds of such a solve alternate between the halves of the trial pool too, so that the trial accepted
+    // in the last one is still in place when the first look-ahead round reads it
+    struct PoolGuard {
+        Dev<T>& D;
+        ~PoolGuard() { D.pool_base = 0, D.pool_cap = D.Vs; }
+    } pool_guard{h->D};
+    if (la_ok) h->D.pool_cap = h->D.Vs / 2;
     Dev<T> Dl = h->D;  // the launch arguments of a look-ahead round
     static const int la_serial = getenv("CILQR_LA_SERIAL") ? atoi(getenv("CILQR_LA_SERIAL")) : 0;  // debugging: 1 = everything on one stream
     const cudaStream_t sb = la_serial ? h->stream : h->stream_b;
-    if (la) {
+    static const int la_cost_late = getenv("CILQR_LA_COST_LATE") ? atoi(getenv("CILQR_LA_COST_LATE")) : 1;
+    if (la_ok) {
         Dl.spec = 1;
-        Dl.pool_cap = h->D.Vs / 2;
         Dl.wide_step = 0;
         static const int spec_all_env = getenv("CILQR_LA_SPEC_ALL") ? atoi(getenv("CILQR_LA_SPEC_ALL")) : 1024;
         Dl.spec_all_below = spec_all_env;
+    }
+    if (la) {
         // jobs of round 0: every instance needs the backward pass of its initial trajectory
         Dl.round_id = 0;
         Dl.pool_base = 0;
-        LAUNCH(h, k_adopt<T>, gs1(B), 128, Dl, 0);
+        LAUNCH(h, k_adopt<T>, gs1(B), 128, Dl, 0, 1);
     }
     // the spin below must not outlive a device fault or a stalled kernel: every kSpinCheck polls the stream is
     // queried (a sticky error, or an idle stream whose progress words still say "rounds outstanding", ends the
@@ -842,6 +847,15 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             B = n_bound;
         }
         const int par = launched & 1;  // which of the two work lists this round reads
+        if (la_ok && !la && launched > 0 && n_bound <= la_switch) {
+            // from here on look-ahead rounds: what the verdict kernel of the last sequential round left behind is taken
+            // over as if no job had run (every instance that needs a backward pass gets one for this round)
+            la = true;
+            Dl.round_id = launched;
+            Dl.pool_base = par * Dl.pool_cap;
+            LAUNCH(h, k_adopt<T>, gs1(n_bound), 128, Dl, par, 1);
+        }
+        h->D.pool_base = la_ok ? par * h->D.pool_cap : 0;
         if (la) {
             // stream S: rollouts + match | costs, verdict |        adopt
             // stream B:                  | derivatives, recursion /
@@ -870,6 +884,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
                 const int y_slots = launched > 0 ? std::max(1, std::min((trial_bound + 127) / 128, 2 * y_list + 8)) : 0;
                 LAUNCH_ON(h, sb, (k_derivs<T, -1, false>), dim3(2 * (N + 1), y_list + y_slots), 128, Dl, B, 2, par, y_list);
             }
+            if (la_cost_late) CK(cudaEventRecord(h->ev_mid[e], sb));
             mark_stage_b(h, 1);
             launch_staged_backward<T>(h, sb, Dl, B + (launched > 0 ? std::min(trial_bound, 2 * n_bound + 1024) : 0), B, 2);
             if (la_serial == 2) CK(cudaDeviceSynchronize());
@@ -877,6 +892,9 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             CK(cudaEventRecord(h->ev_join[e], sb));
             nvtxRangePop();
             nvtxRangePushA("K2 trial costs, K7 verdict, adopt");
+            // the step costs wait for the derivative kernel: both are step-parallel fp64 work and slow each other down
+            // (measured), whereas the recursion that follows on the other stream occupies a handful of warps
+            if (la_cost_late) CK(cudaStreamWaitEvent(h->stream, h->ev_mid[e], 0));
             mark_stage(h, 4);
             if (launched > 0) LAUNCH(h, (k_cost<T, 4, false>), gk(trial_bound, N + 1), 128, Dl, B, 1);
             mark_stage(h, 5);
@@ -885,13 +903,13 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             CK(cudaStreamWaitEvent(h->stream, h->ev_join[e], 0));
             Dl.round_id = launched + 1;
             Dl.pool_base = (par ^ 1) * Dl.pool_cap;
-            LAUNCH(h, k_adopt<T>, gs1(n_bound), 128, Dl, par ^ 1);
+            LAUNCH(h, k_adopt<T>, gs1(n_bound), 128, Dl, par ^ 1, 0);
             nvtxRangePop();
             mark_stage(h, -1);
             ++launched;
             continue;
         }
-        const int trial_bound = int(std::min<long long>(h->D.Vs, (long long)n_bound * kNumAlphas));
+        const int trial_bound = int(std::min<long long>(h->D.pool_cap, (long long)n_bound * kNumAlphas));
         const bool lat = n_bound <= h->prefetch_below;
         mark_stage(h, 0);
         nvtxRangePushA("K3+K4 derivatives");
@@ -984,7 +1002,6 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
                     const auto& id = st ? h->prof_stage_b : h->prof_stage;
                     for (size_t i = 0; i + 1 < id.size(); ++i) {
                         float ms = 0, t0 = 0;
-                        if (id[i] < 0) continue;
                         cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
                         cudaEventElapsedTime(&t0, h->prof_ev[0], ev[i]);
                         fprintf(f, "%d %d %.2f %.2f\n", st, id[i], t0 * 1e3f, ms * 1e3f);
@@ -1546,7 +1563,7 @@ int do_set_option(Impl<T>* h, int option, int value) {
             h->pipeline = value;
             return 0;
         case CILQR_OPT_STAGED_BACKWARD:
-            h->staged = value < 0 ? 0 : (value > 2 ? 2 : value);  // 1: one lane per trajectory, 2: four
+            h->staged = value ? 1 : 0;
             return 0;
         case CILQR_OPT_WIDE_STEP:
             h->wide_step = value ? 1 : 0;
@@ -1610,6 +1627,7 @@ int do_destroy(Impl<T>* h) {
     for (int i = 0; i < 4; ++i) {
         if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
         if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+        if (h->ev_mid[i]) cudaEventDestroy(h->ev_mid[i]);
     }
     if (h->stream_b) cudaStreamDestroy(h->stream_b);
     if (h->t0) cudaEventDestroy(h->t0);

@@ -1341,101 +1341,17 @@ __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T&
 // :118-120).  A symmetric recursion (10 entries) is cheaper and numerically better behaved, but it sails through
 // where the reference fails (measured: tests/test_gpu_truth_bound.py), i.e. it is a different algorithm on exactly
 // the configs the benchmark names.  Same products as the reference, A and B in their sparse form, sums in the
-// reference's order; FMA contraction is the only liberty taken — and it is spelled out (e_mul / e_add / e_fma are
-// single IEEE operations the compiler neither fuses nor splits), because the step exists in two shapes that must
-// return the same bits: one thread per trajectory (riccati_step), and four lanes per trajectory, one per column of
-// V_xx (riccati_step4: latency-bound batches, where the recursion is bound by one warp's instruction stream).
-__device__ __forceinline__ double e_mul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float e_mul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double e_add(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float e_add(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double e_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
-__device__ __forceinline__ float e_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-
-// The non-trivial entries of a step's Jacobians: A = I + {02, 03, 12, 13, 32}, B = {01, 11, 20, 31} (utils.cpp:313-337).
-template <typename T>
-struct StepAB {
-    T a02, a03, a12, a13, a32, b01, b11, b20, b31;
-    // (x A)[2] and (x A)[3] for a row vector x — equally (A^T x)[2], (A^T x)[3]
-    __device__ __forceinline__ T mix2(T x0, T x1, T x2, T x3) const { return e_fma(a32, x3, e_add(e_fma(a12, x1, e_mul(a02, x0)), x2)); }
-    __device__ __forceinline__ T mix3(T x0, T x1, T x3) const { return e_add(e_fma(a13, x1, e_mul(a03, x0)), x3); }
-    // (B^T x)[1]; (B^T x)[0] = b20 x2
-    __device__ __forceinline__ T bmix(T x0, T x1, T x3) const { return e_fma(b31, x3, e_fma(b11, x1, e_mul(b01, x0))); }
-};
-
-// Q_uu + lambda I from G = B^T V (2x4, row-major), its positive-definiteness verdict and its inverse.
-template <typename T>
-struct QuuInv {
-    T q00, q01, q10, q11;  // Q_uu (regularised; both off-diagonals kept, as the reference computes them)
-    T n00, n01, n10, n11;  // -(Q_uu)^-1
-    bool not_pd;
-};
-template <typename T>
-__device__ __forceinline__ QuuInv<T> quu_inverse(const StepAB<T>& J, const T* G, T luu0, T luu1, T luu2, T lamb) {
-    QuuInv<T> Q;
-    Q.q00 = e_add(e_fma(G[2], J.b20, luu0), lamb);
-    Q.q01 = e_add(luu1, e_fma(G[3], J.b31, e_fma(G[1], J.b11, e_mul(G[0], J.b01))));
-    Q.q10 = e_fma(G[6], J.b20, luu1);
-    Q.q11 = e_add(e_add(luu2, e_fma(G[7], J.b31, e_fma(G[5], J.b11, e_mul(G[4], J.b01)))), lamb);
-    // LLT positive-definiteness test (Eigen::LLT, lower, unblocked: fail iff a00 <= 0 or
-    // a11 - (a10 / sqrt(a00))^2 <= 0; NaN passes), as a predicate: nothing is stored when it fails.
-    // The sqrt / divide sequence is ~40 instructions on a serial chain that is bound by its
-    // instruction stream, and the test passes by a wide margin on almost every step, so a
-    // sufficient condition is tried first: in floating point (a10 / sqrt(a00))^2 is
-    // a10^2 / a00 within 5 roundings, so a00 > 0 and a00 a11 - a10^2 > 64 eps a10^2 guarantees that
-    // the exact sequence passes too.  Anything else (near-singular, non-positive, NaN, inf) takes the
-    // exact sequence, so the verdict is always the reference's.
-    Q.not_pd = false;
-    {
-        const T a10sq = e_mul(Q.q10, Q.q10);
-        const bool surely_pd = Q.q00 > T(0) && e_fma(Q.q00, Q.q11, -a10sq) > e_mul(T(64) * kEps<T>(), a10sq);
-        if (!surely_pd) {
-            const T l10 = Q.q10 / m_sqrt(Q.q00);
-            Q.not_pd = (Q.q00 <= T(0)) || (e_fma(-l10, l10, Q.q11) <= T(0));
-        }
-    }
-    const T invdet = T(1) / e_fma(Q.q00, Q.q11, -e_mul(Q.q10, Q.q01));
-    Q.n00 = -e_mul(Q.q11, invdet);
-    Q.n01 = -e_mul(-Q.q01, invdet);
-    Q.n10 = -e_mul(-Q.q10, invdet);
-    Q.n11 = -e_mul(Q.q00, invdet);
-    return Q;
-}
-// one column of the gains and of K^T Q_uu from the column (qux0, qux1) of Q_ux
-template <typename T>
-__device__ __forceinline__ void gain_column(const QuuInv<T>& Q, T qux0, T qux1, T* k0, T* k1, T* m0, T* m1) {
-    *k0 = e_fma(Q.n01, qux1, e_mul(Q.n00, qux0));
-    *k1 = e_fma(Q.n11, qux1, e_mul(Q.n10, qux0));
-    *m0 = e_fma(*k1, Q.q10, e_mul(*k0, Q.q00));
-    *m1 = e_fma(*k1, Q.q11, e_mul(*k0, Q.q01));
-}
-// x' = ((x + (m0 a0 + m1 a1)) + (k0 b0 + k1 b1)) + (q0 c0 + q1 c1): one entry of the three-term value update (cpp:427-432)
-template <typename T>
-__device__ __forceinline__ T value_entry(T x, T m0, T m1, T a0, T a1, T k0, T k1, T b0, T b1, T q0, T q1, T c0, T c1) {
-    const T t1 = e_fma(m1, a1, e_mul(m0, a0));
-    const T t2 = e_fma(k1, b1, e_mul(k0, b0));
-    const T t3 = e_fma(q1, c1, e_mul(q0, c0));
-    return e_add(e_add(e_add(x, t1), t2), t3);
-}
-template <typename T>
-__device__ __forceinline__ void reduction_terms(const QuuInv<T>& Q, T d0, T d1, T Qu0, T Qu1, T& dV0, T& dV1) {
-    // expected cost reduction (cpp:435-436)
-    const T h0 = e_mul(T(0.5), d0), h1 = e_mul(T(0.5), d1);
-    dV0 = e_add(dV0, e_fma(e_fma(h1, Q.q11, e_mul(h0, Q.q01)), d1, e_mul(e_fma(h1, Q.q10, e_mul(h0, Q.q00)), d0)));
-    dV1 = e_add(dV1, e_fma(d1, Qu1, e_mul(d0, Qu0)));
-}
-
+// reference's order; FMA contraction is the only liberty taken.
 template <typename T>
 __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T& dV0, T& dV1, T* K, T& d0, T& d1) {
-    StepAB<T> J;
-    J.a02 = r[kRecA + 0], J.a03 = r[kRecA + 1], J.a12 = r[kRecA + 2], J.a13 = r[kRecA + 3], J.a32 = r[kRecA + 4];
-    J.b01 = r[kRecB + 0], J.b11 = r[kRecB + 1], J.b20 = r[kRecB + 2], J.b31 = r[kRecB + 3];
-    // P = A^T V: rows 0 and 1 are V's, rows 2 and 3 mix in columns 2 and 3 of A
+    const T a02 = r[kRecA + 0], a03 = r[kRecA + 1], a12 = r[kRecA + 2], a13 = r[kRecA + 3], a32 = r[kRecA + 4];
+    const T b01 = r[kRecB + 0], b11 = r[kRecB + 1], b20 = r[kRecB + 2], b31 = r[kRecB + 3];
+    // P = A^T V: rows 0 and 1 are V's, rows 2 and 3 mix in columns 2 and 3 of A (A = I + {02, 03, 12, 13, 32})
     T P2[4], P3[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        P2[c] = J.mix2(V[0 * 4 + c], V[1 * 4 + c], V[2 * 4 + c], V[3 * 4 + c]);
-        P3[c] = J.mix3(V[0 * 4 + c], V[1 * 4 + c], V[3 * 4 + c]);
+        P2[c] = a02 * V[0 * 4 + c] + a12 * V[1 * 4 + c] + V[2 * 4 + c] + a32 * V[3 * 4 + c];
+        P3[c] = a03 * V[0 * 4 + c] + a13 * V[1 * 4 + c] + V[3 * 4 + c];
     }
     // Q_xx = l_xx + P A (l_xx symmetric, upper triangle in the record)
     T Qxx[16];
@@ -1445,53 +1361,95 @@ __device__ __forceinline__ bool riccati_step(const T* r, T lamb, T* Vx, T* V, T&
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const T* p = P[i];
-            Qxx[i * 4 + 0] = e_add(r[kRecLxx + sym[i * 4 + 0]], p[0]);
-            Qxx[i * 4 + 1] = e_add(r[kRecLxx + sym[i * 4 + 1]], p[1]);
-            Qxx[i * 4 + 2] = e_add(r[kRecLxx + sym[i * 4 + 2]], J.mix2(p[0], p[1], p[2], p[3]));
-            Qxx[i * 4 + 3] = e_add(r[kRecLxx + sym[i * 4 + 3]], J.mix3(p[0], p[1], p[3]));
+            Qxx[i * 4 + 0] = r[kRecLxx + sym[i * 4 + 0]] + p[0];
+            Qxx[i * 4 + 1] = r[kRecLxx + sym[i * 4 + 1]] + p[1];
+            Qxx[i * 4 + 2] = r[kRecLxx + sym[i * 4 + 2]] + (a02 * p[0] + a12 * p[1] + p[2] + a32 * p[3]);
+            Qxx[i * 4 + 3] = r[kRecLxx + sym[i * 4 + 3]] + (a03 * p[0] + a13 * p[1] + p[3]);
         }
     }
     // Q_x = l_x + A^T V_x ; Q_u = l_u + B^T V_x
     T Qx[4];
-    Qx[0] = e_add(r[kRecLx + 0], Vx[0]);
-    Qx[1] = e_add(r[kRecLx + 1], Vx[1]);
-    Qx[2] = e_add(r[kRecLx + 2], J.mix2(Vx[0], Vx[1], Vx[2], Vx[3]));
-    Qx[3] = e_add(r[kRecLx + 3], J.mix3(Vx[0], Vx[1], Vx[3]));
-    const T Qu0 = e_fma(J.b20, Vx[2], r[kRecLu + 0]);
-    const T Qu1 = e_add(r[kRecLu + 1], J.bmix(Vx[0], Vx[1], Vx[3]));
+    Qx[0] = r[kRecLx + 0] + Vx[0];
+    Qx[1] = r[kRecLx + 1] + Vx[1];
+    Qx[2] = r[kRecLx + 2] + (a02 * Vx[0] + a12 * Vx[1] + Vx[2] + a32 * Vx[3]);
+    Qx[3] = r[kRecLx + 3] + (a03 * Vx[0] + a13 * Vx[1] + Vx[3]);
+    const T Qu0 = r[kRecLu + 0] + b20 * Vx[2];
+    const T Qu1 = r[kRecLu + 1] + (b01 * Vx[0] + b11 * Vx[1] + b31 * Vx[3]);
     // G = B^T V (2x4): row 0 = b20 V[2][.], row 1 = b01 V[0][.] + b11 V[1][.] + b31 V[3][.]
-    T G[8];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        G[c] = e_mul(J.b20, V[2 * 4 + c]);
-        G[4 + c] = J.bmix(V[0 * 4 + c], V[1 * 4 + c], V[3 * 4 + c]);
-    }
+    const T G00 = b20 * V[8], G01 = b20 * V[9], G02 = b20 * V[10], G03 = b20 * V[11];
+    const T G10 = b01 * V[0] + b11 * V[4] + b31 * V[12];
+    const T G11 = b01 * V[1] + b11 * V[5] + b31 * V[13];
+    const T G12 = b01 * V[2] + b11 * V[6] + b31 * V[14];
+    const T G13 = b01 * V[3] + b11 * V[7] + b31 * V[15];
     // Q_ux = G A (2x4)
     T Qux[8];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        Qux[4 * q + 0] = G[4 * q + 0];
-        Qux[4 * q + 1] = G[4 * q + 1];
-        Qux[4 * q + 2] = J.mix2(G[4 * q + 0], G[4 * q + 1], G[4 * q + 2], G[4 * q + 3]);
-        Qux[4 * q + 3] = J.mix3(G[4 * q + 0], G[4 * q + 1], G[4 * q + 3]);
+    Qux[0] = G00;
+    Qux[1] = G01;
+    Qux[2] = a02 * G00 + a12 * G01 + G02 + a32 * G03;
+    Qux[3] = a03 * G00 + a13 * G01 + G03;
+    Qux[4] = G10;
+    Qux[5] = G11;
+    Qux[6] = a02 * G10 + a12 * G11 + G12 + a32 * G13;
+    Qux[7] = a03 * G10 + a13 * G11 + G13;
+    // Q_uu = l_uu + G B + lambda I  (both off-diagonals kept, as the reference computes them)
+    const T Quu00 = (r[kRecLuu + 0] + G02 * b20) + lamb;
+    const T Quu01 = r[kRecLuu + 1] + (G00 * b01 + G01 * b11 + G03 * b31);
+    const T Quu10 = r[kRecLuu + 1] + G12 * b20;
+    const T Quu11 = (r[kRecLuu + 2] + (G10 * b01 + G11 * b11 + G13 * b31)) + lamb;
+    // LLT positive-definiteness test (Eigen::LLT, lower, unblocked: fail iff a00 <= 0 or
+    // a11 - (a10 / sqrt(a00))^2 <= 0; NaN passes), as a predicate: nothing is stored when it fails.
+    // The sqrt / divide sequence is ~40 instructions on a serial chain that is bound by its
+    // instruction stream, and the test passes by a wide margin on almost every step, so a
+    // sufficient condition is tried first: in floating point (a10 / sqrt(a00))^2 is
+    // a10^2 / a00 within 5 roundings, so a00 > 0 and a00 a11 - a10^2 > 64 eps a10^2 guarantees that
+    // the exact sequence passes too.  Anything else (near-singular, non-positive, NaN, inf) takes the
+    // exact sequence, so the verdict is always the reference's.
+    bool not_pd = false;
+    {
+        const T a10sq = Quu10 * Quu10;
+        const bool surely_pd = Quu00 > T(0) && (Quu00 * Quu11 - a10sq) > T(64) * kEps<T>() * a10sq;
+        if (!surely_pd) {
+            const T l10 = Quu10 / m_sqrt(Quu00);
+            not_pd = (Quu00 <= T(0)) || (Quu11 - l10 * l10 <= T(0));
+        }
     }
-    const QuuInv<T> Q = quu_inverse(J, G, r[kRecLuu + 0], r[kRecLuu + 1], r[kRecLuu + 2], lamb);
-    d0 = e_fma(Q.n01, Qu1, e_mul(Q.n00, Qu0));
-    d1 = e_fma(Q.n11, Qu1, e_mul(Q.n10, Qu0));
+    const T invdet = T(1) / (Quu00 * Quu11 - Quu10 * Quu01);
+    const T i00 = Quu11 * invdet, i01 = -Quu01 * invdet, i10 = -Quu10 * invdet, i11 = Quu00 * invdet;
+    d0 = (-i00) * Qu0 + (-i01) * Qu1;
+    d1 = (-i10) * Qu0 + (-i11) * Qu1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        K[c] = (-i00) * Qux[c] + (-i01) * Qux[4 + c];
+        K[4 + c] = (-i10) * Qux[c] + (-i11) * Qux[4 + c];
+    }
+    if (not_pd) return false;
+    // value function update (cpp:427-432), regularised Q_uu
     T M0[4], M1[4];  // K^T Q_uu, columns 0 and 1
 #pragma unroll
-    for (int c = 0; c < 4; ++c) gain_column(Q, Qux[c], Qux[4 + c], &K[c], &K[4 + c], &M0[c], &M1[c]);
-    if (Q.not_pd) return false;
-    // value function update (cpp:427-432), regularised Q_uu
+    for (int c = 0; c < 4; ++c) {
+        M0[c] = K[c] * Quu00 + K[4 + c] * Quu10;
+        M1[c] = K[c] * Quu01 + K[4 + c] * Quu11;
+    }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) Vx[c] = value_entry(Qx[c], M0[c], M1[c], d0, d1, K[c], K[4 + c], Qu0, Qu1, Qux[c], Qux[4 + c], d0, d1);
+    for (int c = 0; c < 4; ++c) {
+        T t1 = M0[c] * d0 + M1[c] * d1;
+        T t2 = K[c] * Qu0 + K[4 + c] * Qu1;
+        T t3 = Qux[c] * d0 + Qux[4 + c] * d1;
+        Vx[c] = ((Qx[c] + t1) + t2) + t3;
+    }
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-            V[rr * 4 + cc] = value_entry(Qxx[rr * 4 + cc], M0[rr], M1[rr], K[cc], K[4 + cc], K[rr], K[4 + rr], Qux[cc], Qux[4 + cc],
-                                         Qux[rr], Qux[4 + rr], K[cc], K[4 + cc]);
-    reduction_terms(Q, d0, d1, Qu0, Qu1, dV0, dV1);
+        for (int cc = 0; cc < 4; ++cc) {
+            T t1 = M0[rr] * K[cc] + M1[rr] * K[4 + cc];
+            T t2 = K[rr] * Qux[cc] + K[4 + rr] * Qux[4 + cc];
+            T t3 = Qux[rr] * K[cc] + Qux[4 + rr] * K[4 + cc];
+            V[rr * 4 + cc] = ((Qxx[rr * 4 + cc] + t1) + t2) + t3;
+        }
+    // expected cost reduction (cpp:435-436)
+    const T h0 = T(0.5) * d0, h1 = T(0.5) * d1;
+    dV0 += (h0 * Quu00 + h1 * Quu10) * d0 + (h0 * Quu01 + h1 * Quu11) * d1;
+    dV1 += d0 * Qu0 + d1 * Qu1;
     return true;
 }
 
@@ -1882,241 +1840,6 @@ __global__ void __launch_bounds__(32) k_backward_staged(Dev<T> D, int B, int sol
         backward_tile(D, R, st ? t : t - n_slot_tiles, B, st ? 3 : solver, lane, 0, -1);
     }
 }
-
-#ifndef CILQR_PARITY
-// ---------------------------------------------------------------------------
-// K5 on four lanes per trajectory (latency-bound batches).  The staged recursion above is bound by the instruction
-// stream of its one warp per tile (~560 instructions per step, fp64 issuing at one instruction per two clocks); here
-// lane c of a trajectory's four owns column c of V_xx and of everything derived from it (P = A^T V, Q_xx, Q_ux, K,
-// K^T Q_uu), the 2x2 block (Q_uu, its verdict and inverse, d, the expected reduction) is replicated, and the columns
-// meet twice per step in shared memory (the rows of P and G for Q_xx / Q_ux / Q_uu; K, K^T Q_uu and Q_ux for the value
-// update).  A tile of 32 trajectories is one CTA of four warps (eight trajectories each) around the same ring of bulk
-// copies.  Every entry is formed by the same explicit operations as in riccati_step: same bits.
-// ---------------------------------------------------------------------------
-constexpr int kLanesXch = 54;  // exchange scalars per trajectory: P 16 | G 8 | (K0 K1 M0 M1 Qux0 Qux1) x 4 columns | V_x 4, padded
-                               // so that the eight trajectories of a warp fall into different banks (128-bit accesses)
-template <typename T>
-struct alignas(2 * sizeof(T)) Pair {  // two consecutive scalars of an exchange area, moved as one access
-    T x, y;
-};
-template <typename T>
-struct Lanes4Smem {
-    T stage[kStagedStages][kRecFields][32];
-    Pair<T> xch[32][kLanesXch / 2];
-    unsigned long long full[kStagedStages];
-};
-
-// The step for lane c of its trajectory.  rec: field 0 of the trajectory's record in the ring; X: the trajectory's
-// exchange area; v[0..3]: column c of V_xx; Vx: replicated.  Executed by whole warps (the exchanges synchronise the
-// warp); `commit` = false leaves v, Vx, dV untouched (a trajectory that is not running, or has failed before).
-// Returns false when Q_uu + lambda I fails the LLT test (K, d undefined then).
-template <typename T>
-__device__ __forceinline__ bool riccati_step4(const T* rec, Pair<T>* X, int c, const int* lxx_off, T lamb, bool commit, T* Vx, T* v,
-                                              T& dV0, T& dV1, T& k0, T& k1, T& d0, T& d1) {
-    StepAB<T> J;
-    J.a02 = rec[rf<T>(kRecA + 0)], J.a03 = rec[rf<T>(kRecA + 1)], J.a12 = rec[rf<T>(kRecA + 2)], J.a13 = rec[rf<T>(kRecA + 3)];
-    J.a32 = rec[rf<T>(kRecA + 4)];
-    J.b01 = rec[rf<T>(kRecB + 0)], J.b11 = rec[rf<T>(kRecB + 1)], J.b20 = rec[rf<T>(kRecB + 2)], J.b31 = rec[rf<T>(kRecB + 3)];
-    T* Xs = reinterpret_cast<T*>(X);
-    // column c of P = A^T V and of G = B^T V, published row-major
-    Xs[0 * 4 + c] = v[0];
-    Xs[1 * 4 + c] = v[1];
-    Xs[2 * 4 + c] = J.mix2(v[0], v[1], v[2], v[3]);
-    Xs[3 * 4 + c] = J.mix3(v[0], v[1], v[3]);
-    Xs[16 + c] = e_mul(J.b20, v[2]);
-    Xs[20 + c] = J.bmix(v[0], v[1], v[3]);
-    __syncwarp();
-    // column c of x A for a row x: x[c] itself (c < 2), mix2 (c = 2) or mix3 (c = 3); written so that the four lanes
-    // run one instruction sequence: both mixes start with w1 x1 + w0 x0, then add x2 resp. x3, and only mix2 has the
-    // a32 x3 term at the end
-    const bool c2 = c == 2, lo = c < 2;
-    const T w0 = c2 ? J.a02 : J.a03, w1 = c2 ? J.a12 : J.a13;
-    auto col_of = [&](T x0, T x1, T x2, T x3) {
-        const T u = e_add(e_fma(w1, x1, e_mul(w0, x0)), c2 ? x2 : x3);
-        const T m = c2 ? e_fma(J.a32, x3, u) : u;
-        return lo ? (c == 0 ? x0 : x1) : m;
-    };
-    T Qxx[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const Pair<T> a = X[2 * i], b = X[2 * i + 1];  // row i of P
-        Qxx[i] = e_add(rec[lxx_off[i]], col_of(a.x, a.y, b.x, b.y));
-    }
-    T G[8];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const Pair<T> g = X[8 + q];
-        G[2 * q] = g.x;
-        G[2 * q + 1] = g.y;
-    }
-    const T qux0 = col_of(G[0], G[1], G[2], G[3]), qux1 = col_of(G[4], G[5], G[6], G[7]);
-    const QuuInv<T> Q = quu_inverse(J, G, rec[rf<T>(kRecLuu + 0)], rec[rf<T>(kRecLuu + 1)], rec[rf<T>(kRecLuu + 2)], lamb);
-    const T Qxc = e_add(rec[lxx_off[4]], col_of(Vx[0], Vx[1], Vx[2], Vx[3]));  // lxx_off[4]: l_x[c]
-    const T Qu0 = e_fma(J.b20, Vx[2], rec[rf<T>(kRecLu + 0)]);
-    const T Qu1 = e_add(rec[rf<T>(kRecLu + 1)], J.bmix(Vx[0], Vx[1], Vx[3]));
-    d0 = e_fma(Q.n01, Qu1, e_mul(Q.n00, Qu0));
-    d1 = e_fma(Q.n11, Qu1, e_mul(Q.n10, Qu0));
-    T m0, m1;
-    gain_column(Q, qux0, qux1, &k0, &k1, &m0, &m1);
-    const bool good = !Q.not_pd;
-    // column c's share of the value update, published for the other columns
-    const T nVx = value_entry(Qxc, m0, m1, d0, d1, k0, k1, Qu0, Qu1, qux0, qux1, d0, d1);
-    X[12 + 3 * c] = Pair<T>{k0, k1};
-    X[12 + 3 * c + 1] = Pair<T>{m0, m1};
-    X[12 + 3 * c + 2] = Pair<T>{qux0, qux1};
-    Xs[48 + c] = nVx;
-    __syncwarp();
-    T nv[4];
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-        const Pair<T> kr = X[12 + 3 * rr], mr = X[12 + 3 * rr + 1], qr = X[12 + 3 * rr + 2];
-        nv[rr] = value_entry(Qxx[rr], mr.x, mr.y, k0, k1, kr.x, kr.y, qux0, qux1, qr.x, qr.y, k0, k1);
-    }
-    const Pair<T> x01 = X[24], x23 = X[25];
-    T n0 = dV0, n1 = dV1;
-    reduction_terms(Q, d0, d1, Qu0, Qu1, n0, n1);
-    if (commit && good) {
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) v[rr] = nv[rr];
-        Vx[0] = x01.x, Vx[1] = x01.y, Vx[2] = x23.x, Vx[3] = x23.y;
-        dV0 = n0;
-        dV1 = n1;
-    }
-    return good;
-}
-
-// backward_tile on four lanes per trajectory: same contract (solver, slot tiles), called by all 128 threads of a CTA.
-template <typename T>
-__device__ __forceinline__ void backward_tile4(const Dev<T>& D, Lanes4Smem<T>& M, unsigned& issued, unsigned& consumed, int tile,
-                                               int B, int solver) {
-    const int N = D.N;
-    constexpr unsigned kStepBytes = kRecFields * 32 * sizeof(T);
-    const int tid = threadIdx.x, lane = tid & 31, c = tid & 3, j = tid >> 2;  // trajectory j of the tile, column c
-    const bool slots = solver == 3;
-    const size_t S = slots ? size_t(D.Vs) : size_t(D.Bs);
-    const int first = slots ? D.pool_base + tile * 32 : tile * 32;
-    const int end = slots ? D.pool_base + view_count(D, 1, B) : B;
-    const int b = first + j;
-    const bool in = b < end;
-    int ph = PH_DONE;
-    bool run = false;
-    if (in) {
-        if (!solver) {
-            run = true;
-        } else if (solver == 3) {
-            run = D.t_job[b] != 0;
-        } else if (solver == 2) {
-            run = job_of(D, b) != -2;
-        } else {
-            ph = D.phase[b];
-            run = ph == PH_BACKWARD;
-        }
-    }
-    int gs = 0;
-    if (solver == 2 && in) gs = D.gsel[b] == 1 ? 0 : 1;
-    T* const Kbase = slots ? D.Kg_t : Kg_of(D, gs);
-    T* const dbase = slots ? D.dg_t : dg_of(D, gs);
-    T* const dVbase = slots ? D.dV_t : dV_of(D, gs);
-    T* const recbase = slots ? D.rec_t : D.rec;
-    bool ok = true;
-    if (__syncthreads_or(run)) {
-        const T* tile_rec = recbase + size_t(first / kRecTile) * (kRecFields * kRecTile);
-        auto issue = [&](int step) {
-            const unsigned s = issued % kStagedStages;
-            if (tid == 0) {
-                const unsigned bar = smem_addr(&M.full[s]);
-                mbar_arrive_expect_tx(bar, kStepBytes);
-                bulk_load(smem_addr(&M.stage[s][0][0]), tile_rec + size_t(step) * kRecFields * S, kStepBytes, bar);
-            }
-            ++issued;
-        };
-        for (int q = 0; q < kStagedStages && q < N; ++q) issue(N - 1 - q);
-        T lamb = T(0);
-        if (run) lamb = solver == 3 ? D.jlamb_t[b] : (solver == 2 ? D.job_lamb[b] : D.lamb[b]);
-        // where my column's entries of the symmetric l_xx sit in a record, and l_x[c]
-        int lxx_off[5];
-        {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int lo = i < c ? i : c, hi = i < c ? c : i;  // upper triangle, row-major: 00 01 02 03 11 12 13 22 23 33
-                lxx_off[i] = rf<T>(kRecLxx + lo * 4 - lo * (lo - 1) / 2 + (hi - lo));
-            }
-            lxx_off[4] = rf<T>(kRecLx + c);
-        }
-        T Vx[4], v[4];
-        {
-            const T* rec = tile_rec + size_t(N) * kRecFields * S + j * rl<T>();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) Vx[q] = rec[rf<T>(kRecLx + q)];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = rec[lxx_off[q]];  // V_xx at the horizon = l_xx[N] (symmetric)
-        }
-        T dV0 = 0, dV1 = 0;
-        T* Kp = Kbase + size_t(N) * 8 * S + (in ? b : first);
-        T* dp = dbase + size_t(N) * 2 * S + (in ? b : first);
-        for (int i = N - 1; i >= 0; --i) {
-            const unsigned s = consumed % kStagedStages, parity = (consumed / kStagedStages) & 1u;
-            ++consumed;
-            Kp -= 8 * S;
-            dp -= 2 * S;
-            mbar_wait(smem_addr(&M.full[s]), parity);
-            T k0, k1, d0, d1;
-            const bool good = riccati_step4(&M.stage[s][0][0] + j * rl<T>(), M.xch[j], c, lxx_off, lamb, run && ok, Vx, v, dV0, dV1,
-                                            k0, k1, d0, d1);
-            if (run) {
-                if (!(ok && good)) {
-                    // rows not reached stay zero, as in the reference (cpp:392-393, :418)
-                    ok = false;
-                    k0 = k1 = d0 = d1 = 0;
-                }
-                Kp[size_t(c) * S] = k0;
-                Kp[size_t(4 + c) * S] = k1;
-                if (c < 2) dp[size_t(c) * S] = c ? d1 : d0;
-            }
-            __syncthreads();  // every warp is done with ring slot s (and the exchange areas)
-            if (i - kStagedStages >= 0) issue(i - kStagedStages);
-        }
-        if (run && c == 0) {
-            dVbase[b] = dV0;
-            dVbase[S + b] = dV1;
-        }
-    }
-    if (in && !solver && c == 0) D.status[b] = ok ? ST_RUNNING : ST_BWD_FAIL;
-    if (solver >= 2) {
-        if (run && c == 0) (solver == 3 ? D.jok_t : D.job_ok)[b] = ok;
-        return;
-    }
-    if (!solver) return;
-    int want = 0, a0 = 0;
-    if (in && c == 0) {
-        D.commit_src[b] = -1;  // consumed by the derivative stage just before
-        D.t_count[b] = 0;
-        after_backward(D, b, run, ok, ph, &want, &a0);
-    }
-    claim_slots(D, in ? b : 0, want, a0, lane);
-}
-
-template <typename T>
-__global__ void __launch_bounds__(128) k_backward_lanes(Dev<T> D, int B, int solver) {
-    __shared__ Lanes4Smem<T> M;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < kStagedStages; ++s) mbar_init(smem_addr(&M.full[s]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    unsigned issued = 0, consumed = 0;
-    const int n_tiles = (B + 31) / 32;
-    const int n_slot_tiles = solver == 2 ? (view_count(D, 1, B) + 31) / 32 : 0;
-    // (one inlined copy of the tile body: the recursion's code is large, and a warp that runs alone on its scheduler
-    // waits for every instruction-cache miss)
-    for (int t = blockIdx.x; t < n_slot_tiles + n_tiles; t += gridDim.x) {
-        const bool st = t < n_slot_tiles;
-        backward_tile4(D, M, issued, consumed, st ? t : t - n_slot_tiles, B, st ? 3 : solver);
-    }
-}
-
-#endif  // !CILQR_PARITY
 
 // ---------------------------------------------------------------------------
 // K6  forward_pass (cpp:442-461): u' = u + K (x' - x) + alpha d, x' = f(x', u'),
@@ -2726,7 +2449,7 @@ __global__ void __launch_bounds__(128) k_decide(Dev<T> D, int B, int par, unsign
 // alternates between two halves of the trial pool.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) k_adopt(Dev<T> D, int par_next) {
+__global__ void __launch_bounds__(128) k_adopt(Dev<T> D, int par_next, int fresh) {
     const size_t Bs = D.Bs;
     const int lane = threadIdx.x & 31;
     const int* list = D.act + size_t(par_next) * Bs;
@@ -2745,7 +2468,9 @@ __global__ void __launch_bounds__(128) k_adopt(Dev<T> D, int par_next) {
             int g = D.gsel[b];
             if (g == 2) g = 0;  // the slot adopted a round ago has been copied into copy 0 meanwhile (k_derivs)
             int ph = D.phase[b];
-            const int job = D.job_round[b] == D.round_id - 1 ? D.job_src[b] : -2;  // the round that just ended
+            // (fresh: the first look-ahead round of a solve follows — nothing ran a job, and the job flags of the
+            // trial slots are whatever an earlier solve left)
+            const int job = (!fresh && D.job_round[b] == D.round_id - 1) ? D.job_src[b] : -2;  // the round that just ended
             D.job_round[b] = D.round_id;
             // The backward pass the verdict asks for is the one over trajectory cs (-1 = the unchanged current one)
             // with lamb[b]: adopted if a job ran exactly that — the accepted slot's, or the instance's own.
@@ -2758,7 +2483,7 @@ __global__ void __launch_bounds__(128) k_adopt(Dev<T> D, int par_next) {
                     hit = true;
                     ok = D.job_ok[b] != 0;
                     g ^= 1;  // the spare copy becomes the current one
-                } else if (cs >= 0 && D.t_job[cs] && D.jlamb_t[cs] == lamb) {
+                } else if (!fresh && cs >= 0 && D.t_job[cs] && D.jlamb_t[cs] == lamb) {
                     hit = true;
                     ok = D.jok_t[cs] != 0;
                     g = 2;  // gains (and record) stay in the slot's arrays for the coming round
