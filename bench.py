@@ -49,6 +49,7 @@ ROOFLINE_TRAFFIC_SOURCE = ("constant from the committed ncu --set full capture o
 EXTRA_CONFIGS = [("C1", 65536, "f64"), ("C1", 262144, "f64"), ("C2", 262144, "f64"), ("C3", 131072, "f64"),
                  ("C4", 131072, "f32")]
 MULTI_GPU_C3_PER_RANK = 131072  # x 8 ranks = BASELINE config C3 (1 048 576 mixed instances)
+MULTI_GPU_C4_PER_RANK = 524288  # x 8 ranks = BASELINE config C4 (4 194 304 instances, N = 200, 5 obstacles, fp32)
 CHECK_SLICE = 4096
 
 
@@ -313,12 +314,16 @@ def main():
     # device time goes, and the backward-pass kernel's live duration inside the step
     in_step = None
     if rank == 0:
+        # (sequential rounds for this one: in look-ahead rounds the stages overlap on two streams and their
+        # per-stream intervals include each other's waits)
         solver.set_option(solver.OPT_PROFILE_STAGES, 1)
+        solver.set_option(solver.OPT_LOOKAHEAD, 0)
         with torch.cuda.stream(stream):
             flush.add_(1.0)
             solver.solve_resident(B)
         st = solver.stage_times()
         solver.set_option(solver.OPT_PROFILE_STAGES, 0)
+        solver.set_option(solver.OPT_LOOKAHEAD, 1)
         total = sum(v[0] for v in st.values())
         bw_ms, bw_n = st["backward"]
         sz = 8 if args.dtype == "f64" else 4
@@ -328,7 +333,9 @@ def main():
             "backward_us_per_launch": 1e3 * bw_ms / max(bw_n, 1),
             "backward_GBps_if_all_instances_ran": (38 * N + 18) * sz * B / (1e6 * bw_ms / max(bw_n, 1)) if bw_ms else None,
             "note": "B=4096 records (63 MB) are L2-resident and only the running instances take part in a "
-                    "round: the step is latency-bound, the HBM roofline of this kernel is measured at B=262144",
+                    "round: the step is latency-bound, the HBM roofline of this kernel is measured at B=262144; "
+                    "stage times of a solve in sequential rounds (the timed steps switch to look-ahead rounds "
+                    "once <= 512 instances are still running)",
         }
 
     # ---- e2e: pinned host buffers through cilqr_b200_solve_batch ---------------------------------
@@ -424,6 +431,17 @@ def main():
             _, nhead = run_config(cb, "C3", CHECK_SLICE, "f64", local, first_id=nlo, reps=1, k5=False)
             theirs = cb.shard.result_checksum(nhead)
             rows = cb.shard.gather_ints(dist, dev, [mine, theirs, line["iter_steps"], int(line["solve_ms"] * 1000)])
+            # config C4 at its full per-GPU share (the "roofline run" of BASELINE.json: memory capacity, the
+            # > 2^19-instance paths, device-side generation of 524288 x 201 x 5 obstacle samples per rank)
+            c4 = [0, 0, 0]
+            try:
+                lo4 = cb.shard.weak_range(MULTI_GPU_C4_PER_RANK, rank)[0]
+                l4, _ = run_config(cb, "C4", MULTI_GPU_C4_PER_RANK, "f32", local, first_id=lo4, reps=1, k5=False)
+                c4 = [1, l4["iter_steps"], int(l4["solve_ms"] * 1000)]
+            except Exception as e:  # e.g. not enough free HBM on a shared box
+                if rank == 0:
+                    print("C4 leg skipped: %s" % str(e)[:200], file=sys.stderr)
+            rows4 = cb.shard.gather_ints(dist, dev, c4)
             if rank == 0:
                 ok = all(rows[(r + 1) % world][0] == rows[r][1] for r in range(world))
                 t_solve = max(r[3] for r in rows) / 1e6
@@ -436,6 +454,12 @@ def main():
                                                  "batch of their own; 64-bit checksums of (x, u, J, iters) bits "
                                                  "all-gathered and compared" % CHECK_SLICE},
                          "data": "generated on the device, ids [rank*%d, (rank+1)*%d)" % (per, per)}
+                if all(r[0] for r in rows4):
+                    t4 = max(r[2] for r in rows4) / 1e6
+                    multi["C4"] = {"instances": MULTI_GPU_C4_PER_RANK * world, "instances_per_gpu": MULTI_GPU_C4_PER_RANK,
+                                   "N": 200, "dtype": "f32", "solve_ms": round(t4 * 1e3, 2),
+                                   "iter_steps": sum(r[1] for r in rows4),
+                                   "iterations_per_s": round(sum(r[1] for r in rows4) / t4)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
