@@ -334,8 +334,8 @@ def main():
             "backward_GBps_if_all_instances_ran": (38 * N + 18) * sz * B / (1e6 * bw_ms / max(bw_n, 1)) if bw_ms else None,
             "note": "B=4096 records (63 MB) are L2-resident and only the running instances take part in a "
                     "round: the step is latency-bound, the HBM roofline of this kernel is measured at B=262144; "
-                    "stage times of a solve in sequential rounds (the timed steps switch to look-ahead rounds "
-                    "once <= 512 instances are still running)",
+                    "stage times of a solve in sequential rounds (look-ahead rounds are used "
+                    "only for batches of up to 512 instances by default)",
         }
 
     # ---- e2e: pinned host buffers through cilqr_b200_solve_batch ---------------------------------

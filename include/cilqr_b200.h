@@ -221,12 +221,15 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *  CILQR_OPT_WIDE_STEP (default 1): in bandwidth-bound rounds an instance in a streak of rejected steps
  *      evaluates 2, 4, 8, 6 more alphas per round instead of all that remain (same decisions, ~18 % fewer
  *      trials; latency-bound rounds keep evaluating all of them at once).
- *  CILQR_OPT_LOOKAHEAD (default 1): batches of up to 16384 instances (handles created for no more than that) run
- *      the derivatives and the backward pass of the NEXT iteration one device round early, on a second stream next
- *      to the cost and verdict kernels of the line search they depend on — speculating that the full step is
- *      accepted (cpp:362-366), which is what 96 % of the iterations of the slowest instances do — and adopt the
- *      result when the verdict asks for exactly that backward pass; an iteration then costs rollout + derivatives +
- *      recursion instead of the whole chain.  0 runs the stages of an iteration one after the other.
+ *  CILQR_OPT_LOOKAHEAD (default 1): look-ahead rounds.  The derivatives and the backward pass of the NEXT iteration
+ *      run one device round early, on a second stream next to the cost and verdict kernels of the line search they
+ *      depend on — one job per trial ("the backward pass that follows if this trial is the accepted one", cpp:362-366;
+ *      96 % of the iterations of the slowest instances accept the full step) plus one for the all-rejected outcome —
+ *      and the job the verdict asks for is adopted; an iteration then costs rollout + derivatives + recursion
+ *      instead of the whole chain.  1: batches of up to 512 instances (measured 5-9 % faster there, slower above);
+ *      n > 1: batches of up to n instances, and larger ones switch to look-ahead rounds once no more than n
+ *      instances are still running (n <= 16384; handles created for more than 16384 instances never use them);
+ *      0: the stages of an iteration always run one after the other.
  *  The regime threshold (CILQR_OPT_PREFETCH_BELOW) is applied per round to the number of instances still
  *      running, so a large batch moves to the latency-regime kernels for its stragglers. */
 typedef enum cilqr_option_t {

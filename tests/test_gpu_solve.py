@@ -132,9 +132,9 @@ def test_lookahead_rounds_return_the_same_bits(cfg, B, dtype):
         s.set_option(s.OPT_LOOKAHEAD, 0)
         ref = s.solve(pb)
         rounds_ref = s.counters()["rounds"]
-        # 16384: look-ahead rounds from the start; 1 (the default): from the round on in which no more than 512 instances
-        # are still running (the whole solve for a batch of that size); 64: a switch late in the solve
-        for rep, bound in enumerate((16384, 16384, 1, 64)):
+        # 16384: look-ahead rounds from the start; 512 / 64: from the round on in which no more than that many instances
+        # are still running; 1 (the default): only batches of up to 512 instances, from the start
+        for rep, bound in enumerate((16384, 16384, 512, 64, 1)):
             s.set_option(s.OPT_LOOKAHEAD, bound)
             s.reset()
             out = s.solve(pb)

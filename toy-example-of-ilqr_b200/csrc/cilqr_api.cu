@@ -779,8 +779,10 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // stages are throughput-bound and the two streams only get in each other's way — and moves to look-ahead rounds
     // once its work list is down to that size: la_ok = the solve may, la = it is doing so.
     const int la_switch = std::min(h->lookahead_below, h->lookahead > 1 ? h->lookahead : kLookaheadDefault);
+    // (the switch in the middle of a solve only on request — an explicit bound: it is worth 5 % on C1 x 4096 in fp32 and
+    // nothing in fp64, profiles/r02_lookahead.txt — so by default a larger batch runs exactly the sequential rounds)
     const bool la_ok = !kParity && h->lookahead && Bfull <= h->lookahead_below && Bfull <= h->prefetch_below && h->staged &&
-                       h->pipeline && N + 1 <= kPipeMaxSteps && !h->any_alm;
+                       h->pipeline && N + 1 <= kPipeMaxSteps && !h->any_alm && (Bfull <= la_switch || h->lookahead > 1);
     bool la = la_ok && Bfull <= la_switch;
     // sequential rounds of such a solve alternate between the halves of the trial pool too, so that the trial accepted
     // in the last one is still in place when the first look-ahead round reads it
