@@ -31,6 +31,12 @@
 // to half of the slots in use they are swapped into a dense prefix of every
 // array (k_plan_repack, k_swap_rows) — and back at the end of the solve.
 //
+// Look-ahead rounds (small batches, k_adopt).  The next iteration's derivatives and backward
+// pass are run one round early on a second stream, as "jobs" next to the cost and verdict
+// kernels of the line search they depend on — one per possible outcome of the verdict — and
+// the job the verdict asks for is adopted: same operations on the same values, one link of
+// the iteration's latency chain off the critical path.
+//
 // All kernels are grid-stride over device-side counts; the host sizes the grids
 // from the last list length it has seen (an upper bound: lists only shrink).
 #pragma once
