@@ -44,6 +44,8 @@
 #include "../../include/cilqr_b200.h"
 #include "cilqr_model.cuh"
 
+#include <type_traits>
+
 namespace cilqr {
 
 #ifndef CILQR_PARITY
@@ -517,6 +519,13 @@ __global__ void __launch_bounds__(128) k_ref_match(Dev<T> D, int B, int trial) {
     }
 }
 
+// do the active lanes of the warp hold the same value?
+__device__ __forceinline__ bool same_in_warp(int v) {
+    int pred;
+    __match_all_sync(__activemask(), v, &pred);
+    return pred != 0;
+}
+
 // acc up/lo, steer up/lo in the reference's order (cpp:222-228)
 template <typename T>
 __device__ __forceinline__ void ctrl_constraints(const DevParams<T>& P, T acc, T steer, T c[4]) {
@@ -585,12 +594,13 @@ __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int
         const int no = D.n_obs[b];
         if (no > 0) {
             EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
-            // kOb obstacles per trip: their loads are issued together and their barrier terms are
+            // Q obstacles per trip: their loads are issued together and their barrier terms are
             // independent, so the exponentials interleave; the sums keep the reference's order
-            for (int j = 0; j < no; j += kOb) {
-                T item[2 * kOb];
+            auto trip = [&](int j, auto qc) {
+                constexpr int Q = decltype(qc)::value;
+                T item[2 * Q];
 #pragma unroll
-                for (int q = 0; q < kOb; ++q) {
+                for (int q = 0; q < Q; ++q) {
                     const int jj = j + q < no ? j + q : j;
                     // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
                     // evaluated once per upload (k_obs_sincos), not once per cost evaluation
@@ -607,12 +617,23 @@ __device__ __forceinline__ T step_cost_of(const Dev<T>& D, const View<T>& V, int
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < kOb; ++q) {
+                for (int q = 0; q < Q; ++q) {
                     if (j + q < no) {
                         Jk += item[2 * q];
                         Jk += item[2 * q + 1];
                     }
                 }
+            };
+            if (kOb == 2 && same_in_warp(no)) {
+                // throughput regime (the kernel is bound by its fp64 instructions): whole pairs, then a last single
+                // obstacle on its own instead of a pair with a discarded duplicate (3 obstacles: 6 instead of 8 barrier
+                // terms) — where the warp agrees on the count; a mixed warp would serialise the extra trip
+                int j = 0;
+                for (; j + 2 <= no; j += 2) trip(j, std::integral_constant<int, 2>());
+                if (j < no) trip(j, std::integral_constant<int, 1>());
+            } else {
+                // latency regime: one trip for up to kOb obstacles (the padding of the last trip is idle issue slots there)
+                for (int j = 0; j < no; j += kOb) trip(j, std::integral_constant<int, kOb>());
             }
         }
         cost += Jk;
@@ -954,12 +975,13 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             EgoCircles<T> e = ego_circles(x, P.wheelbase, P.ref_point);
             // two obstacles per trip (independent exponentials interleave); accumulation in the
             // reference's order
-            for (int j = 0; j < no; j += 2) {
-                const bool two = j + 1 < no;
-                T tg[2][3], tH[2][6];
+            // (whole pairs, then a last single obstacle on its own: no discarded duplicate)
+            auto trip = [&](int j, auto qc) {
+                constexpr int Q = decltype(qc)::value;
+                T tg[Q][3], tH[Q][6];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int jj = (q && two) ? j + 1 : j;
+                for (int q = 0; q < Q; ++q) {
+                    const int jj = j + q;
                     // obstacle sample (x, y, sin yaw, cos yaw): the sin/cos of the input yaw is
                     // evaluated once per upload (k_obs_sincos), not once per cost evaluation
                     const T* ob = D.obs + (size_t(jj) * D.obs_len + D.obs_off + k) * 4 * Bs + b;
@@ -983,11 +1005,9 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
                     tH[q][3] = hf * (gfy * gfy) + hr * (gry * gry);
                     tH[q][4] = hf * (gfy * f3) + hr * (gry * r3);
                     tH[q][5] = hf * (f3 * f3) + hr * (r3 * r3);
-                    if (q == 0 || two) {
-                        zO += gf + gr;
-                        zOh += hf + hr;
-                    }
-                    if (alm && (q == 0 || two)) {
+                    zO += gf + gr;
+                    zOh += hf + hr;
+                    if (alm) {
                         mun[size_t(8 + 2 * jj) * Bs] =
                             std_min(std_max(mu[size_t(8 + 2 * jj) * Bs] + rho * cf, T(0)), P.max_mu);
                         mun[size_t(9 + 2 * jj) * Bs] =
@@ -995,20 +1015,23 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (q == 0 || two) {
-                        gx[0] += tg[q][0];
-                        gx[1] += tg[q][1];
-                        gx[3] += tg[q][2];
-                        H[0] += tH[q][0];
-                        H[1] += tH[q][1];
-                        H[3] += tH[q][2];
-                        H[4] += tH[q][3];
-                        H[6] += tH[q][4];
-                        H[9] += tH[q][5];
-                    }
+                for (int q = 0; q < Q; ++q) {
+                    gx[0] += tg[q][0];
+                    gx[1] += tg[q][1];
+                    gx[3] += tg[q][2];
+                    H[0] += tH[q][0];
+                    H[1] += tH[q][1];
+                    H[3] += tH[q][2];
+                    H[4] += tH[q][3];
+                    H[6] += tH[q][4];
+                    H[9] += tH[q][5];
                 }
-            }
+            };
+            // (no padded pair for a mixed warp here, unlike step_cost_of: a third copy of the body costs this kernel more
+            // in spills than the extra trip costs the mixed warps of C3 — measured)
+            int j = 0;
+            for (; j + 2 <= no; j += 2) trip(j, std::integral_constant<int, 2>());
+            if (j < no) trip(j, std::integral_constant<int, 1>());
         }
         // velocity terms have c_dot = (0, 0, +-1, 0), border terms (n0, n1, 0, 0), obstacle terms (gx, gy, 0, g3)
         zV *= T(0);
