@@ -751,6 +751,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     const int N = h->N;
     h->launches = 0;
     CK(cudaStreamSynchronize(h->stream));
+    if (h->stream_b) CK(cudaStreamSynchronize(h->stream_b));  // (nothing of a solve that ended in an error may still be running)
     // progress words written by the verdict kernel: [0] rounds completed << 32 | instances running,
     // [1] rounds completed << 32 | entries on the next round's work list
     volatile unsigned long long* progress = reinterpret_cast<volatile unsigned long long*>(h->h_ctl);
