@@ -73,3 +73,31 @@ def test_long_reference_line_and_template_errors():
         bad.tmpl[:] = 3                             # template never set
         with pytest.raises(cb.CilqrError):
             s.solve(bad)
+
+
+@pytest.mark.parametrize("max_iter", [0, 1, 2, 7])
+def test_lookahead_rounds_at_the_limits(max_iter):
+    """Look-ahead rounds (the default for batches this small) where the job machinery has little or nothing to
+    adopt: no iteration at all, a single one, a few; one instance and a handful; NaN / inf instances whose every
+    line search fails (the all-rejected job chain up to max_lamb) next to ordinary ones.  Same results as the
+    sequential rounds and as the oracle."""
+    pb = cb.synthetic_batch("C3", 21, N=30)
+    for td in pb.templates:
+        td.params = dict(td.params, max_iter=max_iter)
+    pb.x0[4, 1] = np.nan
+    pb.x0[9, 2] = np.inf
+    ref = op.solve_batch(pb, "f64")
+    with cb.BatchSolver(pb.templates, 21, pb.N, pb.max_obs, "f64") as s:
+        for bound in (0, 1):
+            s.set_option(s.OPT_LOOKAHEAD, bound)
+            outs = [s.solve(pb), s.solve(pb.slice(3, 4))]
+            if bound == 0:
+                seq = outs
+            assert np.array_equal(outs[0].iters, ref.iters)
+            assert np.array_equal(outs[0].exit_reason, ref.exit_reason)
+            ok = np.isfinite(ref.x).all(axis=(1, 2))
+            assert np.abs(outs[0].x[ok] - ref.x[ok]).max() < 1e-6
+            assert np.array_equal(outs[1].x, outs[0].x[3:4], equal_nan=True)
+        for a, b in zip(seq, outs):
+            for f in ("u", "x", "J", "K", "d", "iters", "status", "exit_reason", "step_cost"):
+                assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
