@@ -870,7 +870,9 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
             nvtxRangePushA("K6+K1 rollouts, waypoint match");
             if (launched > 0) {  // (round 0 has no trials: every instance starts with a backward job)
                 const int blocks = std::max(1, std::min((trial_bound + kPipeTrials - 1) / kPipeTrials, kGridCap));
-                const bool narrow = h->pipeline == 8 || (h->pipeline == 1 && trial_bound > 2 * 148 * kPipeTrials);
+                // (16 scan lanes per trial while the trials are likely to fit one wave of one block per SM: a round uses
+                // about one slot per instance, not the 20 the bound allows for; more than that only costs a second pass)
+                const bool narrow = h->pipeline == 8 || (h->pipeline == 1 && std::min(trial_bound, 3 * n_bound + 256) > 148 * kPipeTrials);
                 if (narrow) LAUNCH(h, (k_rollout_match<T, 8, true>), dim3(blocks), pipe_threads(8), Dl, B);
                 else LAUNCH(h, (k_rollout_match<T, 16, true>), dim3(blocks), pipe_threads(16), Dl, B);
             }

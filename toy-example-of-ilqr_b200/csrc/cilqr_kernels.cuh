@@ -2243,6 +2243,10 @@ __global__ void __launch_bounds__(pipe_threads(G), kLa ? 1 : (G == 16 ? 2 : 4)) 
     __shared__ T pos[kPipeMaxSteps][kPipeTrials][2];
     __shared__ __align__(8) unsigned long long bars[kPipeMaxSteps];  // bars[k]: positions of step k are in the ring
     const int count = view_count(D, 1, B);
+    // (the host sizes the grid from its bound of 20 slots per instance; most rounds use about one: blocks without a
+    // trial leave before setting the barriers up — they would otherwise hold an SM's block slot for a few microseconds
+    // each, and the look-ahead variant fits one block per SM)
+    if (int(blockIdx.x) * kPipeTrials >= count) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k <= D.N; k += blockDim.x) mbar_init(smem_addr(&bars[k]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
