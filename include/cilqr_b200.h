@@ -230,6 +230,12 @@ int cilqr_b200_counters(cilqr_handle_t* h, cilqr_counters_t* out);
  *      n > 1: batches of up to n instances, and larger ones switch to look-ahead rounds once no more than n
  *      instances are still running (n <= 16384; handles created for more than 16384 instances never use them);
  *      0: the stages of an iteration always run one after the other.
+ *  CILQR_OPT_FUSED_BACKWARD (default 1): in bandwidth-bound rounds of a barrier-type solve the backward pass computes
+ *      the control half of every derivative record (l_u, l_uu, A_k, B_k: cpp:540-610, utils.cpp:285-342) from
+ *      (v_k, yaw_k, u_k) itself instead of reading what the derivative stage wrote: 14 of the 28 record fields are
+ *      neither written nor read back, and the control half of the derivative stage is not launched.  0: the
+ *      derivative stage writes whole records in every round.  Also: CILQR_OPT_BENCH_PREFETCH = 3 selects this
+ *      flavour for cilqr_b200_bench_backward / cilqr_b200_stage_backward (which then need the trajectory loaded).
  *  The regime threshold (CILQR_OPT_PREFETCH_BELOW) is applied per round to the number of instances still
  *      running, so a large batch moves to the latency-regime kernels for its stragglers. */
 typedef enum cilqr_option_t {
@@ -242,7 +248,8 @@ typedef enum cilqr_option_t {
     CILQR_OPT_STAGED_BACKWARD = 6,
     CILQR_OPT_REPACK = 7,
     CILQR_OPT_WIDE_STEP = 8,
-    CILQR_OPT_LOOKAHEAD = 9
+    CILQR_OPT_LOOKAHEAD = 9,
+    CILQR_OPT_FUSED_BACKWARD = 10
 } cilqr_option_t;
 int cilqr_b200_set_option(cilqr_handle_t* h, int option, int value);
 

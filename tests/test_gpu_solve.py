@@ -144,6 +144,27 @@ def test_lookahead_rounds_return_the_same_bits(cfg, B, dtype):
             assert s.counters()["rounds"] <= rounds_ref * 1.35 + 4
 
 
+@pytest.mark.parametrize("cfg,B,dtype", [("C1", 700, "f64"), ("C2", 300, "f64"), ("C3", 900, "f64"), ("C3", 700, "f32")])
+def test_fused_backward_pass_returns_the_same_bits(cfg, B, dtype):
+    """Bandwidth-bound rounds compute the control half of the derivative records inside the backward pass instead of
+    storing it and reading it back (CILQR_OPT_FUSED_BACKWARD): same bits as whole records, whether the solve stays in
+    the bandwidth regime, starts there and moves to the latency-regime kernels with records cached from fused rounds
+    (threshold 200 / 40: the control half is filled in at the switch), or never enters it."""
+    pb = cb.synthetic_batch(cfg, B, N={"C2": 100}.get(cfg, 50))
+    with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, dtype) as s:
+        s.set_option(s.OPT_LOOKAHEAD, 0)
+        outs = []
+        for threshold, fused in ((1 << 30, 1), (0, 0), (0, 1), (200, 1), (40, 1), (200, 0)):
+            s.set_option(s.OPT_PREFETCH_BELOW, threshold)
+            s.set_option(s.OPT_FUSED_BACKWARD, fused)
+            s.reset()
+            outs.append(s.solve(pb))
+    assert int(outs[0].iters.sum()) > 2 * pb.B
+    for o in outs[1:]:
+        for f in ("u", "x", "J", "K", "d", "iters", "status", "exit_reason", "step_cost"):
+            assert np.array_equal(getattr(outs[0], f), getattr(o, f), equal_nan=True), f
+
+
 def test_fp32_first_iteration_vs_fp32_oracle():
     """fp32 amplifies the same sensitivity ~1e9 x more (SURVEY hard part 3), so the fp32 solve is held
     to the fp32 oracle in lockstep over the first iter_step only, where decisions still agree."""

@@ -193,6 +193,7 @@ class BatchSolver:
     OPT_REPACK = 7
     OPT_WIDE_STEP = 8
     OPT_LOOKAHEAD = 9
+    OPT_FUSED_BACKWARD = 10
     STAGES = ["derivs", "backward", "forward", "ref_match", "cost", "decide"]
 
     def stage_times(self):

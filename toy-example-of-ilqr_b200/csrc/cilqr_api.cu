@@ -79,6 +79,7 @@ struct Base {
     int staged = 1;    // latency-bound batches: backward pass fed by bulk async copies into shared memory
     int wide_step = 1; // bandwidth-bound rounds widen a line search step by step (2, 4, 8, 6 alphas) instead of all at once
     int repack = 1;    // survivors moved into a dense prefix whenever they are down to half of the slots in use
+    int fused_backward = 1;  // bandwidth-bound rounds: the backward pass computes the control half of the records itself
     // look-ahead rounds (k_adopt): batches up to lookahead_below run next iteration's backward pass alongside the
     // line search's cost / verdict kernels, on a second stream
     int lookahead = 1;
@@ -772,6 +773,7 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
     // the kernel variants (all variants of a stage return the same bits, so a big batch switches to
     // the latency-regime kernels for its stragglers).
     int launched = 0;
+    bool fused_rounds = false;  // rounds have run whose records hold no control half (see `fused` below)
     int level = 0, repack_bound[kRepackLevels], repack_off[kRepackLevels + 1] = {0};
     // Look-ahead rounds (see k_adopt): the whole solve of a latency-bound batch.  Needs the piped rollout and the
     // staged backward pass (their look-ahead forms are the ones written), no augmented-Lagrangian template (its
@@ -918,8 +920,20 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         const bool lat = n_bound <= h->prefetch_below;
         mark_stage(h, 0);
         nvtxRangePushA("K3+K4 derivatives");
+        // Bandwidth-bound rounds of a barrier-type solve: the backward pass computes the control half of the records
+        // (l_u, l_uu, A, B) from the trajectory itself (k_backward<T, true, true>), so only the state half of the
+        // derivative stage is launched and 14 of the 28 record fields are neither written nor read back.
+        const bool fused = !kParity && !lat && h->fused_backward && !h->any_alm;
         if (lat) {
+            if (fused_rounds) {
+                // the cached records of this solve have no control half yet: the latency-regime kernels read all 28 fields
+                LAUNCH_DERIVS(h, 1, gk(n_bound, N + 1), h->D, B, 5, par);
+                fused_rounds = false;
+            }
             LAUNCH_DERIVS(h, -1, gk(n_bound, 2 * (N + 1)), h->D, B, 1, par);
+        } else if (fused) {
+            LAUNCH_DERIVS(h, 0, gk(n_bound, N + 1), h->D, B, 4, par);
+            fused_rounds = true;
         } else {
             LAUNCH_DERIVS(h, 0, gk(n_bound, N + 1), h->D, B, 1, par);
             LAUNCH_DERIVS(h, 1, gk(n_bound, N + 1), h->D, B, 1, par);
@@ -932,7 +946,12 @@ int do_solve_resident(Impl<T>* h, int Bfull) {
         mark_stage(h, 1);
         nvtxRangePushA("K5 backward pass");
         h->D.wide_step = (!lat && h->wide_step) ? 1 : 0;
-        switch (backward_variant<T>(h, n_bound, B, lat)) {
+        switch (fused ? 3 : backward_variant<T>(h, n_bound, B, lat)) {
+#ifndef CILQR_PARITY
+            case 3:
+                LAUNCH(h, (k_backward<T, true, true>), bw_grid(n_bound), kBwThreads, h->D, B, 1, par);
+                break;
+#endif
             case 2:  // small batch: one warp per tile of 32 instances, records staged through shared memory
                 launch_staged_backward<T>(h, h->stream, h->D, B, B, 1);
                 break;
@@ -1255,6 +1274,10 @@ int stage_backward(Impl<T>* h, int B, const double* lx, const double* lu, const 
         const int variant = h->bench_prefetch >= 0 ? h->bench_prefetch : backward_variant<T>(h, B, B, B <= h->prefetch_below);
         if (variant == 2) {
             launch_staged_backward<T>(h, h->stream, h->D, B, B, 0);
+#ifndef CILQR_PARITY
+        } else if (variant == 3) {
+            LAUNCH(h, (k_backward<T, true, true>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
+#endif
         } else if (variant == 1) {
             LAUNCH(h, (k_backward<T, true>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
         } else {
@@ -1310,6 +1333,10 @@ int bench_backward(Impl<T>* h, int B, double lamb, int reps, int flush_l2, float
         const int variant = h->bench_prefetch >= 0 ? h->bench_prefetch : backward_variant<T>(h, B, B, B <= h->prefetch_below);
         if (variant == 2) {
             launch_staged_backward<T>(h, h->stream, h->D, B, B, 0);
+#ifndef CILQR_PARITY
+        } else if (variant == 3) {
+            LAUNCH(h, (k_backward<T, true, true>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
+#endif
         } else if (variant == 1) {
             LAUNCH(h, (k_backward<T, true>), bw_grid(B), kBwThreads, h->D, B, 0, 0);
         } else {
@@ -1576,11 +1603,14 @@ int do_set_option(Impl<T>* h, int option, int value) {
         case CILQR_OPT_REPACK:
             h->repack = value < 0 ? 0 : value;  // > 1: smallest batch that is still repacked (development)
             return 0;
+        case CILQR_OPT_FUSED_BACKWARD:
+            h->fused_backward = value ? 1 : 0;
+            return 0;
         case CILQR_OPT_LOOKAHEAD:  // 0 off, 1 the default batch bound, > 1 an explicit one
             h->lookahead = value < 0 ? 0 : value;
             return 0;
         case CILQR_OPT_BENCH_PREFETCH:
-            h->bench_prefetch = value < 0 ? -1 : (value > 2 ? 2 : value);
+            h->bench_prefetch = value < 0 ? -1 : (value > 3 ? 3 : value);
             return 0;
         default:
             return fail(CILQR_ERR_INVALID, "unknown option %d", option);

@@ -760,6 +760,34 @@ __device__ __forceinline__ void add_constraint_ref(bool alm, T c, const T* c_dot
 //     then differentiates only where the record is stale — the reference's
 //     cache rule for rejected steps (cpp:469-474).
 // ---------------------------------------------------------------------------
+#ifndef CILQR_PARITY
+// The control half of a step's record in the barrier solve type — l_u, l_uu (constraints of u_k: the reference's step
+// k + 1) and the model Jacobians A_k, B_k — from (v_k, yaw_k, u_k): out[0..13] in record order (l_u 2, l_uu 3, A 5, B 4).
+// Shared by the derivative kernel (which stores it) and the fused backward pass (which does not).
+template <typename T>
+__device__ __forceinline__ void control_fields(const DevParams<T>& P, T velo, T yaw, T ua, T us, T* out) {
+    T c[4];
+    ctrl_constraints(P, ua, us, c);
+    T g[4], h[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) constraint_weights(false, c[m], P.st_q1, P.st_q2, T(0), T(0), &g[m], &h[m]);
+    // (zA / zS: the zero entries of c_dot, as in the state half: an overflowed acceleration barrier
+    // poisons the steering entries and vice versa, both poison the off-diagonal)
+    const T zA = (g[0] + g[1]) * T(0), zS = (g[2] + g[3]) * T(0);
+    const T zAh = (h[0] + h[1]) * T(0), zSh = (h[2] + h[3]) * T(0);
+    const T gu0 = (g[0] + (-g[1])) + zS;
+    const T gu1 = (g[2] + (-g[3])) + zA;
+    const T hu0 = (h[0] + h[1]) + zSh;
+    const T hu1 = (h[2] + h[3]) + zAh;
+    out[0] = 2 * (ua * P.R[0]) + gu0;
+    out[1] = 2 * (us * P.R[1]) + gu1;
+    out[2] = 2 * P.R[0] + hu0;
+    out[3] = zAh + zSh;
+    out[4] = 2 * P.R[1] + hu1;
+    model_jacobians(velo, yaw, us, P.dt, P.wheelbase, P.ref_point, out + 5, out + 10);
+}
+#endif
+
 // The work of one thread of the derivative stage: half `part` (0 = state terms l_x, l_xx; 1 = control terms and
 // model Jacobians l_u, l_uu, A, B) of step k of instance b.  masked != 0 (inside the solver): first commit an
 // accepted trial, then differentiate only where the record is stale.
@@ -777,8 +805,14 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
     // by instance b): its trajectory, into the slot's own record.
     int src = -1, tsrc = -1;
     bool diff = true;
-    if (masked == 1) {
+    if (masked == 1 || masked == 4) {
+        // (4: a round whose backward pass computes the control half of the records itself — only the state half of
+        // this stage is launched, and it copies the accepted controls as well)
         src = tsrc = D.commit_src[b];
+    } else if (masked == 5) {
+        // the control half of the records that are still valid, after rounds that did not store it (first
+        // latency-regime round of a solve that began in the bandwidth regime)
+        if (!D.rec_valid[b] || D.commit_src[b] >= 0) return;
     } else if (masked == 2) {
         src = tsrc = D.cur_src[b];
         const int job = job_of(D, b);
@@ -821,6 +855,10 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             D.ridx[size_t(k) * Bs + b] = ri;
             for (int p = 0; p < kScPlanes; ++p)
                 D.sc[(size_t(p) * (N + 1) + k) * Bs + b] = D.sc_t[(size_t(p) * (N + 1) + k) * Vs + src];
+            if (masked == 4 && k < N) {
+                D.U[at(Bs, k, 0, 2, b)] = D.Ut[at(Vs, k, 0, 2, src)];
+                D.U[at(Bs, k, 1, 2, b)] = D.Ut[at(Vs, k, 1, 2, src)];
+            }
         } else if (k < N) {
             ua = D.Ut[at(Vs, k, 0, 2, src)];
             us = D.Ut[at(Vs, k, 1, 2, src)];
@@ -828,7 +866,7 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             D.U[at(Bs, k, 1, 2, b)] = us;
         }
     }
-    if (masked == 1 && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) return;
+    if ((masked == 1 || masked == 4) && (D.phase[b] != PH_BACKWARD || D.rec_valid[b])) return;
     if (masked == 2 && !diff) return;
     if (tsrc < 0) {
 #pragma unroll
@@ -1089,6 +1127,13 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
         rec[rf<T>(kRecLuu + 1)] = Hu[1];
         rec[rf<T>(kRecLuu + 2)] = 2 * P.R[1] + Hu[3];
 #else
+        if (!alm) {
+            T f[14];
+            control_fields(P, x[2], x[3], ua, us, f);
+#pragma unroll
+            for (int c2 = 0; c2 < 14; ++c2) rec[rf<T>(kRecLu + c2)] = f[c2];
+            return;
+        }
         T g[4], h[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m)
@@ -1515,6 +1560,78 @@ __device__ __forceinline__ void load_record(const T* p, T* r) {
 // tested exactly like Eigen::LLT (lower, unblocked): fail iff a pivot <= 0, NaN
 // passes (cpp:415-420); the inverse is the adjugate times 1/det (cpp:421).
 // Returns false on a non-PD Q_uu (d, K rows not reached are zeroed, as in the reference).
+#ifndef CILQR_PARITY
+// Fused flavour (bandwidth-bound rounds, barrier solve type): the control half of every record (l_u, l_uu, A, B: 14 of
+// the 28 fields) is computed here from (v, yaw, u) of the current trajectory instead of being written by the
+// derivative kernel and read back — 32 instead of 112 bytes read per step in fp64, no write at all — with the next
+// step's operands prefetched one step ahead like the plain register-prefetch flavour.  Same entry formulas
+// (control_fields), same recursion (riccati_step).
+template <typename T>
+__device__ __forceinline__ bool riccati_fused(const Dev<T>& D, const DevParams<T>& P, int b, T lamb) {
+    const int N = D.N;
+    const size_t Bs = D.Bs;
+    static_assert(kRecLu == 14, "state half first");
+    const T* rec = rec_at(D, N, b);
+    T Vx[4], V[kVN];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Vx[c] = rec[rf<T>(kRecLx + c)];
+    load_terminal_V(rec, V);
+    T dV0 = 0, dV1 = 0;
+    bool failed = false;
+    int i = N - 1;
+    // operands of step i: the state half of its record, v_i, yaw_i, u_i
+    T nxt[18];
+    auto fetch = [&](int step, T* o) {
+        const T* rp = rec_at(D, step, b);
+        if constexpr (rec_quads<T>()) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float4 v = ld_early4(rp + q * (4 * kRecTile));
+                o[4 * q + 0] = v.x, o[4 * q + 1] = v.y, o[4 * q + 2] = v.z, o[4 * q + 3] = v.w;
+            }
+            o[12] = ld_early(rp + rf<T>(12));
+            o[13] = ld_early(rp + rf<T>(13));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 14; ++c) o[c] = ld_early(rp + rf<T>(c));
+        }
+        o[14] = ld_early(D.X + at(Bs, step, 2, 4, b));
+        o[15] = ld_early(D.X + at(Bs, step, 3, 4, b));
+        o[16] = ld_early(D.U + at(Bs, step, 0, 2, b));
+        o[17] = ld_early(D.U + at(Bs, step, 1, 2, b));
+    };
+    fetch(i, nxt);
+    for (; i >= 0; --i) {
+        T r[kRecFields];
+#pragma unroll
+        for (int c = 0; c < 14; ++c) r[c] = nxt[c];
+        const T velo = nxt[14], yaw = nxt[15], ua = nxt[16], us = nxt[17];
+        fetch(i > 0 ? i - 1 : 0, nxt);
+        control_fields(P, velo, yaw, ua, us, r + 14);
+        T K[8], d0, d1;
+        if (!riccati_step(r, lamb, Vx, V, dV0, dV1, K, d0, d1)) {
+            failed = true;
+            break;
+        }
+        D.dg[at(Bs, i, 0, 2, b)] = d0;
+        D.dg[at(Bs, i, 1, 2, b)] = d1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) D.Kg[at(Bs, i, c, 8, b)] = K[c];
+    }
+    if (failed) {
+        for (; i >= 0; --i) {
+            D.dg[at(Bs, i, 0, 2, b)] = 0;
+            D.dg[at(Bs, i, 1, 2, b)] = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) D.Kg[at(Bs, i, c, 8, b)] = 0;
+        }
+    }
+    D.dV[b] = dV0;
+    D.dV[Bs + b] = dV1;
+    return !failed;
+}
+#endif
+
 template <typename T, bool kPrefetch>
 __device__ __forceinline__ bool riccati(const Dev<T>& D, int b, T lamb) {
     const int N = D.N;
@@ -1622,8 +1739,12 @@ __device__ __forceinline__ void after_backward(const Dev<T>& D, int b, bool ran,
 //     line search; then every searching instance claims its trial-pool slots
 //     for this round (warp-aggregated, one atomic per warp).
 // ---------------------------------------------------------------------------
-template <typename T, bool kPrefetch>
+template <typename T, bool kPrefetch, bool kFused = false>
 __global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver, int par) {
+#ifndef CILQR_PARITY
+    __shared__ DevParams<T> sP[kFused ? CILQR_B200_MAX_TEMPLATES : 1];
+    if (kFused) D.P = stage_params(D, sP);
+#endif
     const int lane = threadIdx.x & 31;
     const int n_threads = gridDim.x * blockDim.x;
     // solver: only the instances on this round's work list
@@ -1644,15 +1765,21 @@ __global__ void __launch_bounds__(128) k_backward(Dev<T> D, int B, int solver, i
         const int b = in ? (list ? list[idx] : idx) : 0;
         int want = 0, a0 = 0;
         if (in) {
+            auto recursion = [&]() {
+#ifndef CILQR_PARITY
+                if constexpr (kFused) return riccati_fused<T>(D, D.P[D.tmpl[b]], b, D.lamb[b]);
+#endif
+                return riccati<T, kPrefetch>(D, b, D.lamb[b]);
+            };
             if (!solver) {
-                bool ok = riccati<T, kPrefetch>(D, b, D.lamb[b]);
+                bool ok = recursion();
                 D.status[b] = ok ? ST_RUNNING : ST_BWD_FAIL;
             } else {
                 D.commit_src[b] = -1;  // consumed by the derivative stage just before
                 D.t_count[b] = 0;
                 const int ph = D.phase[b];
                 bool ok = true;
-                if (ph == PH_BACKWARD) ok = riccati<T, kPrefetch>(D, b, D.lamb[b]);
+                if (ph == PH_BACKWARD) ok = recursion();
                 after_backward(D, b, ph == PH_BACKWARD, ok, ph, &want, &a0);
             }
         }
@@ -2734,6 +2861,10 @@ __global__ void k_tile_records(Dev<T> D, int B0, int B) {
     if (b >= B || b < B0) return;
     const int k = row / kRecFields, c = row % kRecFields;
     rec_at(D, k, b)[rf<T>(c)] = rec_at(D, k, b % B0)[rf<T>(c)];
+    // the trajectory itself (the fused flavour of the backward pass reads v, yaw, u) and the template id
+    if (c < 4) D.X[at(D.Bs, k, c, 4, b)] = D.X[at(D.Bs, k, c, 4, b % B0)];
+    if (c < 2 && k < D.N) D.U[at(D.Bs, k, c, 2, b)] = D.U[at(D.Bs, k, c, 2, b % B0)];
+    if (row == 0) D.tmpl[b] = D.tmpl[b % B0];
 }
 
 // ---------------------------------------------------------------------------
