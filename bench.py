@@ -214,7 +214,9 @@ def run_config(cb, cfg, B, dtype, device, first_id=0, reps=2, k5=True):
             for t, td in enumerate(spec.templates):
                 s.set_template(t, dict(td.params, max_iter=1))
             s.generate(spec, B, first_id=first_id)
+            s.set_option(s.OPT_FUSED_BACKWARD, 0)  # (whole records wanted: the fused rounds do not store the control half)
             s.solve_resident(B)  # one iter_step: leaves the records of the initial trajectories
+            s.set_option(s.OPT_FUSED_BACKWARD, 1)
             ms, nbytes = s.bench_backward(B, 0.0, 8, True)
             done = s.download(B, want_gains=False).status
             for t, td in enumerate(spec.templates):
@@ -390,9 +392,23 @@ def main():
         rs.bench_tile_records(4096, Br)        # replicated on the device up to the roofline batch
         rs.bench_backward(Br, 0.0, 3, True)    # warm-up launches
         ms, nbytes = rs.bench_backward(Br, 0.0, 20, True)
+        # the flavour the solver runs in bandwidth-bound rounds: control half of the records (l_u, l_uu, A, B) computed
+        # in the kernel from (v, yaw, u) instead of read back — fewer bytes, more arithmetic, same K / d bits
+        rs.set_option(rs.OPT_BENCH_PREFETCH, 3)
+        rs.bench_backward(Br, 0.0, 3, True)
+        ms_f, _ = rs.bench_backward(Br, 0.0, 20, True)
+        sz = 8 if dtype == "f64" else 4
+        bytes_f = float(28 * N + 18) * sz * Br
         rs.close()
         achieved = nbytes / (float(np.mean(ms)) * 1e-3) / 1e9
+        fused = {"kernel": "k_backward<T, prefetch, fused control half> (what the solver launches in bandwidth-bound rounds; "
+                           "replaces this kernel + the control half of the derivative stage)",
+                 "ms_per_launch": float(np.mean(ms_f)), "bytes_per_launch": bytes_f,
+                 "achieved": bytes_f / (float(np.mean(ms_f)) * 1e-3) / 1e9, "unit": "GB/s",
+                 "layout": "14 record fields + v, yaw, u read, K + d written: (28*N+18)*sizeof(T) bytes per trajectory",
+                 "note": "no longer bound by HBM: 8 more transcendentals per step in the recursion's thread"}
         return {"bound": "hbm", "kernel": "k_backward<T, prefetch> (backward_pass Riccati recursion, cpp:383-440)",
+                "fused_flavour": fused,
                 "dtype": dtype, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ROOFLINE_TRAFFIC_BYTES.get(dtype),
                 "traffic_source": ROOFLINE_TRAFFIC_SOURCE if dtype in ROOFLINE_TRAFFIC_BYTES else None,

@@ -7,6 +7,7 @@ import cilqr_b200 as cb
 def run(cfg, B, N, dtype):
     pb = cb.synthetic_batch(cfg, B, N=N)
     with cb.BatchSolver(pb.templates, pb.B, pb.N, pb.max_obs, dtype) as s:
+        s.set_option(s.OPT_FUSED_BACKWARD, 0)  # the backward bench below runs on the records the solves leave
         s.upload(pb)
         for rep in range(3):
             t = time.time(); s.solve_resident(B); out = s.download(B); dt = time.time() - t

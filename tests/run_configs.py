@@ -16,6 +16,7 @@ def run(cfg, B, dtype, N=None, reps=2):
     t_gen = time.perf_counter() - t0
     N = pb.N
     with cb.BatchSolver(pb.templates, B, N, pb.max_obs, dtype) as s:
+        s.set_option(s.OPT_FUSED_BACKWARD, 0)  # K5 below runs on the records the solve leaves: whole records wanted
         t0 = time.perf_counter()
         s.upload(pb)
         t_up = time.perf_counter() - t0

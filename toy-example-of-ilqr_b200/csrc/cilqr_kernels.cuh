@@ -31,6 +31,9 @@
 // to half of the slots in use they are swapped into a dense prefix of every
 // array (k_plan_repack, k_swap_rows) — and back at the end of the solve.
 //
+// Bandwidth-bound rounds fuse the control half of the derivative records (l_u, l_uu, A, B: functions
+// of v, yaw, u alone) into the backward pass (riccati_fused): it is neither stored nor read back.
+//
 // Look-ahead rounds (small batches, k_adopt).  The next iteration's derivatives and backward
 // pass are run one round early on a second stream, as "jobs" next to the cost and verdict
 // kernels of the line search they depend on — one per possible outcome of the verdict — and
@@ -1132,8 +1135,7 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             control_fields(P, x[2], x[3], ua, us, f);
 #pragma unroll
             for (int c2 = 0; c2 < 14; ++c2) rec[rf<T>(kRecLu + c2)] = f[c2];
-            return;
-        }
+        } else {
         T g[4], h[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m)
@@ -1164,6 +1166,9 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
         for (int c2 = 0; c2 < 5; ++c2) rec[rf<T>(kRecA + c2)] = ja[c2];
 #pragma unroll
         for (int c2 = 0; c2 < 4; ++c2) rec[rf<T>(kRecB + c2)] = jb[c2];
+#ifndef CILQR_PARITY
+        }  // alm
+#endif
     }
 }
 
