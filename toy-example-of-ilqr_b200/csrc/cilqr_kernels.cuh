@@ -794,7 +794,7 @@ __device__ __forceinline__ void control_fields(const DevParams<T>& P, T velo, T 
 // The work of one thread of the derivative stage: half `part` (0 = state terms l_x, l_xx; 1 = control terms and
 // model Jacobians l_u, l_uu, A, B) of step k of instance b.  masked != 0 (inside the solver): first commit an
 // accepted trial, then differentiate only where the record is stale.
-template <typename T, bool kAlm>
+template <typename T, bool kAlm, bool kPairs = true>
 __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int part, int masked, int slot = -1) {
     const int N = D.N;
     const size_t Bs = D.Bs, Vs = D.Vs;
@@ -1070,9 +1070,16 @@ __device__ __forceinline__ void derivs_item(const Dev<T>& D, int b, int k, int p
             };
             // (no padded pair for a mixed warp here, unlike step_cost_of: a third copy of the body costs this kernel more
             // in spills than the extra trip costs the mixed warps of C3 — measured)
-            int j = 0;
-            for (; j + 2 <= no; j += 2) trip(j, std::integral_constant<int, 2>());
-            if (j < no) trip(j, std::integral_constant<int, 1>());
+            if (kPairs) {
+                int j = 0;
+                for (; j + 2 <= no; j += 2) trip(j, std::integral_constant<int, 2>());
+                if (j < no) trip(j, std::integral_constant<int, 1>());
+            } else {
+                // bandwidth-bound rounds in fp64: one obstacle per trip — the kernel is short of registers, not of
+                // independent work (408 -> 356 bytes of spills), and a warp of mixed obstacle counts (C3) wastes no half
+                // trips: ~1 % of a C1 / C2 solve; fp32 keeps the pairs (C4, 5 obstacles: 454 against 466 ms)
+                for (int j = 0; j < no; ++j) trip(j, std::integral_constant<int, 1>());
+            }
         }
         // velocity terms have c_dot = (0, 0, +-1, 0), border terms (n0, n1, 0, 0), obstacle terms (gx, gy, 0, g3)
         zV *= T(0);
@@ -1209,7 +1216,7 @@ __global__ void __launch_bounds__(128, kPart < 0 ? 4 : (kPart == 0 ? CILQR_DERIV
     }
     const int ny = masked == 2 ? slot_y0 : int(gridDim.y);
     for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n; idx += ny * blockDim.x)
-        derivs_item<T, kAlm>(D, list ? list[idx] : idx, k, part, masked);
+        derivs_item<T, kAlm, (kPart < 0 || sizeof(T) == 4)>(D, list ? list[idx] : idx, k, part, masked);
 }
 
 // solve()'s bookkeeping after an iter_step (cpp:113-141): lambda schedule,
