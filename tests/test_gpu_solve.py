@@ -122,7 +122,8 @@ def test_kernel_variants_return_the_same_bits(cfg, dtype):
             assert np.array_equal(getattr(outs[0], f), getattr(o, f), equal_nan=True), f
 
 
-@pytest.mark.parametrize("cfg,B,dtype", [("C1", 333, "f64"), ("C3", 700, "f64"), ("C2", 200, "f64"), ("C3", 333, "f32"), ("C1", 2500, "f64")])
+@pytest.mark.parametrize("cfg,B,dtype", [("C1", 333, "f64"), ("C3", 700, "f64"), ("C2", 200, "f64"), ("C3", 333, "f32"), ("C1", 2500, "f64"),
+                                          ("C1", 6000, "f64")])  # (6000: the survivors are repacked before the switch)
 def test_lookahead_rounds_return_the_same_bits(cfg, B, dtype):
     """Look-ahead rounds (next iteration's derivatives + backward pass speculated one round early on a second
     stream, adopted when the verdict asks for exactly that pass: k_adopt) are an execution strategy: the same bits as
