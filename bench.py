@@ -377,6 +377,7 @@ def main():
     t_e2e_local = sum(e2e_ms) / 1e3
 
     # ---- reduce over ranks: max time, summed work --------------------------------------------------
+    per_rank_us = cb.shard.gather_ints(dist, dev, [int(1e6 * t_local / max(args.steps, 1)), int(1e6 * t_e2e_local / max(args.steps, 1))])
     (t_max, t_e2e), (iters_total, e2e_iters, launches) = cb.shard.reduce_max_sum(
         dist, dev, [t_local, t_e2e_local], [iters_total, e2e_iters, launches])
     solver.close()
@@ -495,6 +496,9 @@ def main():
             "e2e": {"value": e2e_iters / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": 1e3 * t_e2e / max(args.steps, 1)},
             "gpu_launches": launches,
+            # (value uses the max over ranks.  On the 8-GPU box of this round seven ranks run 15.2-15.7 ms per step and
+            # one — always the same GPU, with or without the ranks pinned to cores of their own — 16.3)
+            "per_rank_ms_per_step": [round(r[0] / 1e3, 3) for r in per_rank_us],
             "roofline": roofline,
             "roofline_f32": roofline_f32,
             "in_step": in_step,
